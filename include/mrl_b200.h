@@ -1,0 +1,152 @@
+/* mrl_b200.h - C ABI of the B200-native modular_rl policy-update path.
+ *
+ * The reference (ddlau/modular_rl) has no FFI: its hot path is three compiled Theano
+ * functions per updater plus scipy scans, called from Python.  Each entry point below
+ * replaces one of those call sites; citations are file:line under /root/reference.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mrl_last_error() gives the
+ *     message for the calling thread.  No exceptions cross the ABI.  Soft failures of the
+ *     algorithm (zero gradient, line-search failure) are reported as output flags, not errors.
+ *   - `loc` says where a caller buffer lives: MRL_HOST (pageable or pinned) or MRL_DEVICE.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls enqueue on it;
+ *     only functions that return scalars to the host synchronise it.
+ *   - caller memory is borrowed for the duration of the call and never freed by the library.
+ *   - one mrl_net / mrl_batch belongs to one (process, GPU).
+ */
+#ifndef MRL_B200_H
+#define MRL_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRL_HOST 0
+#define MRL_DEVICE 1
+/* dtypes of caller arrays */
+#define MRL_F32 0
+#define MRL_F64 1
+#define MRL_I32 2
+#define MRL_I64 3
+/* distribution heads: DiagGauss (core.py:402-438), Categorical (core.py:339-365), scalar value (agentzoo.py:53-59) */
+#define MRL_GAUSS 0
+#define MRL_CATEGORICAL 1
+#define MRL_VALUE 2
+/* hidden activations (Keras names, agentzoo.py:20-23) */
+#define MRL_TANH 0
+#define MRL_RELU 1
+#define MRL_SIGMOID 2
+
+typedef struct mrl_net mrl_net;
+typedef struct mrl_batch mrl_batch;
+typedef struct mrl_comm mrl_comm;
+
+const char* mrl_last_error(void);
+int mrl_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long mrl_launch_count(void);
+
+/* ---------------------------------------------------------------- batch (paths, flattened)
+ * Replaces the `concat([path[k] for path in paths])` host copies of trpo.py:74-77,
+ * ppo.py:61-64, core.py:653-654 and the per-call numpy->Theano downcast (keras_theano_setup.py:9). */
+int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int with_time_feature);
+int mrl_batch_destroy(mrl_batch* b);
+/* observations [N x ob_dim], row-major with leading dimension ld (elements) */
+int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long long ld, long long N, int loc, void* stream);
+/* CSR trajectory structure: offsets int64[n_paths+1] (offsets[n_paths] == N), terminated uint8[n_paths].
+ * Also materialises NnVf.preproc's feature t/timestep_limit (core.py:659-660) when the batch was
+ * created with_time_feature. */
+int mrl_batch_set_paths(mrl_batch* b, const long long* offsets, const unsigned char* terminated, int n_paths,
+                        double timestep_limit, int loc, void* stream);
+/* action [N] (int, Categorical) or [N x d] (float, DiagGauss); advantage [N]; oldprob [N x K] or [N x 2d]
+ * = the args of trpo.py:66.  adv may be NULL to keep the advantages mrl_batch_gae left on the device. */
+int mrl_batch_set_policy_inputs(mrl_batch* b, int head, int dout, const void* act, int act_dtype,
+                                const void* adv, int adv_dtype, const void* oldprob, int oldprob_dtype,
+                                int loc, void* stream);
+/* regression target [N] for the value net, already mixed by the caller (core.py:624) */
+int mrl_batch_set_vf_target(mrl_batch* b, const void* y, int dtype, int loc, void* stream);
+/* target = mixfrac * return + (1 - mixfrac) * ypred_old (core.py:622-624) from what mrl_batch_gae and
+ * mrl_net_predict_into_baseline left on the device (ypred_old == the GAE baseline: same theta) */
+int mrl_batch_mix_vf_target(mrl_batch* b, double mixfrac, void* stream);
+/* global timestep count when the batch is one shard of a data-parallel job (default: local N) */
+int mrl_batch_set_global_n(mrl_batch* b, long long n_global);
+long long mrl_batch_size(const mrl_batch* b);
+/* within-path time index (int32[N]) computed on the device - the bit-exact integer contract */
+int mrl_batch_get_time_index(mrl_batch* b, int* out, int loc, void* stream);
+
+/* compute_advantage (core.py:63-105): reward [N]; baseline [N] (NULL: use the values left by
+ * mrl_net_predict_into_baseline); writes return/advantage (float64, host or device, may be NULL) and keeps
+ * float32 advantages on the device for the policy update.  standardize != 0 applies (adv-mean)/std with
+ * population std and no epsilon (core.py:100-105); on a sharded batch the moments are merged over `comm`. */
+int mrl_batch_gae(mrl_batch* b, const void* reward, int reward_dtype, const void* baseline, int baseline_dtype,
+                  double gamma, double lam, int standardize, mrl_comm* comm, double* ret_out, double* adv_out,
+                  int loc, void* stream);
+
+/* ---------------------------------------------------------------- stand-alone scans */
+/* misc_utils.discount over a CSR batch + GAE deltas, no batch object (core.py:69-75) */
+int mrl_gae(const void* reward, int reward_dtype, const void* baseline, int baseline_dtype,
+            const long long* offsets, const unsigned char* terminated, int n_paths, long long N, double gamma,
+            double lam, double* ret_out, double* adv_out, int loc, void* stream);
+/* in place (x-mean)/std, population std; stats_out[3] = {n, mean, M2} (may be NULL) */
+int mrl_standardize(double* x, long long N, double* stats_out, int loc, void* stream);
+/* ZFilter over N consecutive samples of dimension d (filters.py:30-38, running_stat.py:9-30): sample t is
+ * normalised with running statistics that include samples 0..t and the incoming state {n, M[d], S[d]},
+ * which is updated in place (host memory). */
+int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, double* state_n, double* state_M,
+                     double* state_S, int demean, int destd, double clip, void* y, int y_dtype, int loc,
+                     void* stream);
+
+/* ---------------------------------------------------------------- network (policy or value MLP)
+ * dims[0..n_layers] = input dim, hidden sizes..., output dim (agentzoo.py:25-61).  Parameters are the
+ * reference's flat vector: per Dense layer [kernel(in,out) C-order, bias], then logstd (core.py:518-557). */
+int mrl_net_create(mrl_net** out, int device, int n_layers, const int* dims, int head, int activation);
+int mrl_net_destroy(mrl_net* n);
+long long mrl_net_num_params(const mrl_net* n);
+int mrl_net_set_params(mrl_net* n, const void* theta, int dtype, int loc, void* stream); /* SetFromFlat, core.py:526-540 */
+int mrl_net_get_params(mrl_net* n, float* theta, int loc, void* stream);                  /* GetFlat, core.py:518-523 */
+int mrl_net_set_comm(mrl_net* n, mrl_comm* comm);
+
+/* net output for every timestep of the batch, row-major [N x dout]: means (Gauss; std = exp(logstd) is
+ * state independent), softmax probabilities (Categorical) or values.  core.py:270, core.py:608 */
+int mrl_net_forward(mrl_net* n, mrl_batch* b, float* out, int loc, void* stream);
+/* NnVf.predict over the whole batch, result kept on the device as the GAE baseline (core.py:70) */
+int mrl_net_predict_into_baseline(mrl_net* n, mrl_batch* b, void* stream);
+/* compute_losses (trpo.py:69, ppo.py:57): out = {surr, kl, ent} */
+int mrl_net_losses(mrl_net* n, mrl_batch* b, double out[3], void* stream);
+/* compute_policy_gradient (trpo.py:68): g[P]; losses may be NULL */
+int mrl_net_policy_gradient(mrl_net* n, mrl_batch* b, float* g, int loc, double losses[3], void* stream);
+/* compute_fisher_vector_product (trpo.py:70), WITHOUT the cg_damping term (trpo.py:86-92 adds it) */
+int mrl_net_fvp(mrl_net* n, mrl_batch* b, const float* v, float* out, int loc, void* stream);
+/* compute_lossgrad (ppo.py:56): pensurr and its flat gradient; losses = {surr, kl, ent} */
+int mrl_net_ppo_lossgrad(mrl_net* n, mrl_batch* b, double kl_coeff, double kl_cutoff, int reverse_kl,
+                         double* pensurr, double* g, double losses[3], void* stream);
+/* NnRegression f_losses / f_lossgrad (core.py:613-617,670-671): losses = {loss, mse, l2}; g may be NULL */
+int mrl_net_vf_lossgrad(mrl_net* n, mrl_batch* b, double l2coeff, double losses[3], double* g, void* stream);
+
+/* TrpoUpdater.__call__ after the path concat (trpo.py:80-140): gradient, CG (trpo.py:165-200), step scaling
+ * (trpo.py:119-124), backtracking line search (trpo.py:143-159), parameter update or rollback.
+ * stats = {surr_before, surr_after, kl_before, kl_after, ent_before, ent_after};
+ * info  = {skipped (zero gradient, trpo.py:102), linesearch_success, accepted_backtrack_index,
+ *          cg_iterations_run, fvp_calls, loss_passes} */
+typedef struct {
+  double cg_damping, max_kl, residual_tol, accept_ratio;
+  int cg_iters, max_backtracks;
+} mrl_trpo_cfg;
+int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* cfg, double stats[6], int info[6],
+                      void* stream);
+/* debugging / tests: last step direction and full step (float64[P], host) */
+int mrl_net_get_trpo_vectors(mrl_net* n, double* stepdir, double* fullstep, double* scalars /* shs,lm,rate,rdotr */);
+
+/* ---------------------------------------------------------------- data-parallel communicator (NCCL)
+ * The reference is single-process (core.py:123-124 raises on `parallel`).  Sharding the timestep batch
+ * adds one sum over ranks after each batch reduction; see DESIGN.md "Multi-GPU". */
+int mrl_comm_unique_id(char id_out[128]);
+int mrl_comm_create(mrl_comm** out, const char id[128], int rank, int world, int device);
+int mrl_comm_destroy(mrl_comm* c);
+int mrl_comm_allreduce_f64(mrl_comm* c, double* buf, long long n, void* stream); /* in place, device memory */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,898 @@
+// C ABI (include/mrl_b200.h): host-side orchestration of the kernels.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/mrl_b200.h"
+#include "comm.h"
+
+#include <atomic>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define CKL(call, nk) \
+  do {                \
+    CK(call);         \
+    g_launches += nk; \
+  } while (0)
+#define RET(call)          \
+  do {                     \
+    int _r = (call);       \
+    if (_r) return _r;     \
+  } while (0)
+
+extern "C" const char* mrl_last_error(void) { return g_err.c_str(); }
+int mrl_set_error(const char* msg) { g_err = msg; return 1; }   // used by comm.cu
+extern "C" int mrl_version(void) { return 100; }
+extern "C" long long mrl_launch_count(void) { return g_launches.load(); }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static size_t dtype_size(int dt) { return (dt == MRL_F32 || dt == MRL_I32) ? 4 : 8; }
+
+// ======================================================================== batch
+struct mrl_batch {
+  int device = 0, ob_dim = 0, with_time = 0, xdim = 0, d0p = 0, d0r = 0;
+  long long N = 0, Nglobal = 0;
+  int n_tiles = 0, n_paths = 0;
+  double timestep_limit = 1.0;
+  unsigned long long version = 0;
+  int pol_head = -1, pol_dout = 0, naux_pol = 0;
+  bool has_baseline = false, has_adv32 = false, has_ret = false;
+  DevBuf Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
+      gather;
+};
+
+static int stage_in(DevBuf& stage, const void* src, size_t bytes, int loc, cudaStream_t st, const void** out) {
+  if (loc == MRL_DEVICE) {
+    *out = src;
+    return 0;
+  }
+  CK(stage.reserve(bytes));
+  CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, st));
+  *out = stage.p;
+  return 0;
+}
+
+extern "C" int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int with_time_feature) {
+  if (!out || ob_dim <= 0) return fail("mrl_batch_create: bad arguments");
+  CK(cudaSetDevice(device));
+  mrl_batch* b = new mrl_batch();
+  b->device = device;
+  b->ob_dim = ob_dim;
+  b->with_time = with_time_feature ? 1 : 0;
+  b->xdim = ob_dim + b->with_time;
+  b->d0p = round_up(b->xdim, 8);
+  b->d0r = round_up(b->xdim, 4);
+  *out = b;
+  return 0;
+}
+extern "C" int mrl_batch_destroy(mrl_batch* b) {
+  if (!b) return 0;
+  cudaSetDevice(b->device);
+  DevBuf* bufs[] = {&b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
+                    &b->stage2, &b->baseline, &b->ret, &b->adv, &b->adv32, &b->stats, &b->gather};
+  for (DevBuf* d : bufs) d->release();
+  delete b;
+  return 0;
+}
+extern "C" long long mrl_batch_size(const mrl_batch* b) { return b ? b->N : -1; }
+extern "C" int mrl_batch_set_global_n(mrl_batch* b, long long n) {
+  if (!b || n < b->N) return fail("mrl_batch_set_global_n: n_global < local N");
+  b->Nglobal = n;
+  return 0;
+}
+
+extern "C" int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long long ld, long long N, int loc,
+                                 void* stream) {
+  if (!b || !ob || N <= 0) return fail("mrl_batch_set_obs: bad arguments");
+  if (dtype != MRL_F32 && dtype != MRL_F64) return fail("mrl_batch_set_obs: observations must be f32 or f64");
+  if (ld < b->ob_dim) return fail("mrl_batch_set_obs: ld < ob_dim");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  b->N = N;
+  b->Nglobal = N;
+  b->n_tiles = (int)((N + MRL_TILE - 1) / MRL_TILE);
+  b->version++;
+  b->has_baseline = b->has_adv32 = b->has_ret = false;
+  b->pol_head = -1;
+  const void* src;
+  RET(stage_in(b->stage, ob, (size_t)N * ld * dtype_size(dtype), loc, st, &src));
+  CK(b->Xt.reserve((size_t)b->n_tiles * b->d0p * MRL_LDT * 4));
+  CK(b->Xr.reserve((size_t)b->n_tiles * MRL_TILE * b->d0r * 4));
+  CKL(launch_pack_tiles(src, dtype, ld, b->ob_dim, b->d0p, N, b->Xt.as<float>(), b->d0p, 0, b->n_tiles, st), 1);
+  CKL(launch_pack_rows(src, dtype, ld, b->ob_dim, N, b->Xr.as<float>(), b->d0r, (long long)b->n_tiles * MRL_TILE,
+                       st), 1);
+  return 0;
+}
+
+extern "C" int mrl_batch_set_paths(mrl_batch* b, const long long* offsets, const unsigned char* terminated,
+                                   int n_paths, double timestep_limit, int loc, void* stream) {
+  if (!b || !offsets || !terminated || n_paths <= 0) return fail("mrl_batch_set_paths: bad arguments");
+  if (b->N <= 0) return fail("mrl_batch_set_paths: set observations first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  CK(b->offsets.reserve((size_t)(n_paths + 1) * 8));
+  CK(b->terminated.reserve((size_t)n_paths));
+  cudaMemcpyKind kind = loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (loc == MRL_HOST) {
+    if (offsets[0] != 0 || offsets[n_paths] != b->N)
+      return fail("mrl_batch_set_paths: offsets must start at 0 and end at N=%lld", b->N);
+    for (int p = 0; p < n_paths; ++p)
+      if (offsets[p + 1] < offsets[p]) return fail("mrl_batch_set_paths: offsets not monotone at path %d", p);
+  }
+  CK(cudaMemcpyAsync(b->offsets.p, offsets, (size_t)(n_paths + 1) * 8, kind, st));
+  CK(cudaMemcpyAsync(b->terminated.p, terminated, (size_t)n_paths, kind, st));
+  b->n_paths = n_paths;
+  b->timestep_limit = timestep_limit;
+  CK(b->tindex.reserve((size_t)b->N * 4));
+  if (b->with_time) {
+    if (!(timestep_limit > 0)) return fail("mrl_batch_set_paths: timestep_limit must be > 0");
+    CKL(launch_time_feature(b->offsets.as<long long>(), n_paths, b->N, timestep_limit, b->Xt.as<float>(), b->d0p,
+                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), st), 1);
+  }
+  return 0;
+}
+
+extern "C" int mrl_batch_get_time_index(mrl_batch* b, int* out, int loc, void* stream) {
+  if (!b || !out || !b->with_time || b->n_paths <= 0) return fail("mrl_batch_get_time_index: no paths bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(out, b->tindex.p, (size_t)b->N * 4, loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (loc == MRL_HOST) CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mrl_batch_set_policy_inputs(mrl_batch* b, int head, int dout, const void* act, int act_dtype,
+                                           const void* adv, int adv_dtype, const void* oldprob, int oldprob_dtype,
+                                           int loc, void* stream) {
+  if (!b || !act || !oldprob || b->N <= 0) return fail("mrl_batch_set_policy_inputs: bad arguments");
+  if (head != MRL_GAUSS && head != MRL_CATEGORICAL) return fail("mrl_batch_set_policy_inputs: bad head");
+  if (oldprob_dtype != MRL_F32 && oldprob_dtype != MRL_F64) return fail("oldprob must be f32/f64");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  const long long N = b->N;
+  const int naux = head == MRL_GAUSS ? 1 + 3 * dout : 2 + dout;
+  CK(b->aux_pol.reserve((size_t)b->n_tiles * naux * MRL_LDT * 4));
+  float* aux = b->aux_pol.as<float>();
+  const void* src;
+  if (adv) {
+    RET(stage_in(b->stage2, adv, (size_t)N * dtype_size(adv_dtype), loc, st, &src));
+    CKL(launch_pack_tiles(src, adv_dtype, 1, 1, 1, N, aux, naux, 0, b->n_tiles, st), 1);
+  } else {
+    if (!b->has_adv32) return fail("mrl_batch_set_policy_inputs: adv == NULL but no advantages on the device");
+    CKL(launch_pack_tiles(b->adv32.p, MRL_F32, 1, 1, 1, N, aux, naux, 0, b->n_tiles, st), 1);
+  }
+  const int acols = head == MRL_GAUSS ? dout : 1;
+  if (head == MRL_GAUSS && act_dtype != MRL_F32 && act_dtype != MRL_F64) return fail("DiagGauss actions must be float");
+  RET(stage_in(b->stage2, act, (size_t)N * acols * dtype_size(act_dtype), loc, st, &src));
+  CKL(launch_pack_tiles(src, act_dtype, acols, acols, acols, N, aux, naux, 1, b->n_tiles, st), 1);
+  const int pcols = head == MRL_GAUSS ? 2 * dout : dout;
+  RET(stage_in(b->stage2, oldprob, (size_t)N * pcols * dtype_size(oldprob_dtype), loc, st, &src));
+  CKL(launch_pack_tiles(src, oldprob_dtype, pcols, pcols, pcols, N, aux, naux, 1 + acols, b->n_tiles, st), 1);
+  b->pol_head = head;
+  b->pol_dout = dout;
+  b->naux_pol = naux;
+  return 0;
+}
+
+__global__ void mix_target_kernel(const double* __restrict__ ret, const double* __restrict__ base, double mix,
+                                  long long N, float* __restrict__ aux) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (N + MRL_TILE - 1) / MRL_TILE * MRL_TILE) return;
+  const float v = t < N ? (float)(ret[t] * mix + base[t] * (1.0 - mix)) : 0.f;
+  aux[(t / MRL_TILE) * MRL_LDT + (t % MRL_TILE)] = v;
+}
+
+extern "C" int mrl_batch_set_vf_target(mrl_batch* b, const void* y, int dtype, int loc, void* stream) {
+  if (!b || !y || b->N <= 0) return fail("mrl_batch_set_vf_target: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  CK(b->aux_vf.reserve((size_t)b->n_tiles * MRL_LDT * 4));
+  const void* src;
+  RET(stage_in(b->stage2, y, (size_t)b->N * dtype_size(dtype), loc, st, &src));
+  CKL(launch_pack_tiles(src, dtype, 1, 1, 1, b->N, b->aux_vf.as<float>(), 1, 0, b->n_tiles, st), 1);
+  return 0;
+}
+// target = mixfrac * return + (1 - mixfrac) * ypred_old (core.py:622-624) from device-resident data
+extern "C" int mrl_batch_mix_vf_target(mrl_batch* b, double mixfrac, void* stream) {
+  if (!b || !b->has_ret || !b->has_baseline) return fail("mrl_batch_mix_vf_target: needs mrl_batch_gae first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  CK(b->aux_vf.reserve((size_t)b->n_tiles * MRL_LDT * 4));
+  const long long n = (long long)b->n_tiles * MRL_TILE;
+  mix_target_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b->ret.as<double>(), b->baseline.as<double>(),
+                                                                 mixfrac, b->N, b->aux_vf.as<float>());
+  CKL(cudaGetLastError(), 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------ GAE
+__global__ void merge_moments_kernel(const double* __restrict__ gathered, int world, double* __restrict__ stats) {
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double bn = gathered[3 * r], bm = gathered[3 * r + 1], b2 = gathered[3 * r + 2];
+    if (bn == 0.0) continue;
+    if (n == 0.0) { n = bn; mean = bm; m2 = b2; continue; }
+    const double tot = n + bn, d = bm - mean;
+    mean += d * (bn / tot);
+    m2 += b2 + d * d * (n * bn / tot);
+    n = tot;
+  }
+  stats[0] = n; stats[1] = mean; stats[2] = m2;
+}
+__global__ void place_moments_kernel(const double* __restrict__ stats, double* __restrict__ gathered, int world, int rank) {
+  const int i = threadIdx.x;
+  if (i < 3 * world) gathered[i] = (i / 3 == rank) ? stats[i % 3] : 0.0;
+}
+__global__ void f32_to_f64_kernel(const float* __restrict__ x, double* __restrict__ y, long long N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) y[i] = (double)x[i];
+}
+
+static int gae_impl(const void* reward_dev, int rdt, const void* base_dev, int bdt, const long long* off_dev,
+                    const unsigned char* term_dev, int n_paths, long long N, double gamma, double lam, double* ret,
+                    double* adv, cudaStream_t st) {
+  if (rdt != MRL_F32 && rdt != MRL_F64) return fail("reward must be f32/f64");
+  if (bdt != MRL_F32 && bdt != MRL_F64) return fail("baseline must be f32/f64");
+  CKL(launch_gae(reward_dev, rdt == MRL_F64, base_dev, bdt == MRL_F64, off_dev, term_dev, n_paths, N, gamma, lam,
+                 ret, adv, st), 1);
+  return 0;
+}
+
+extern "C" int mrl_batch_gae(mrl_batch* b, const void* reward, int reward_dtype, const void* baseline,
+                             int baseline_dtype, double gamma, double lam, int standardize, mrl_comm* comm,
+                             double* ret_out, double* adv_out, int loc, void* stream) {
+  if (!b || !reward || b->N <= 0 || b->n_paths <= 0) return fail("mrl_batch_gae: bind observations and paths first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  const long long N = b->N;
+  const void* r_dev;
+  RET(stage_in(b->stage2, reward, (size_t)N * dtype_size(reward_dtype), loc, st, &r_dev));
+  const void* v_dev;
+  int vdt = baseline_dtype;
+  if (baseline) {
+    if (loc == MRL_DEVICE) {
+      v_dev = baseline;
+    } else {
+      CK(b->gather.reserve((size_t)N * dtype_size(baseline_dtype)));
+      CK(cudaMemcpyAsync(b->gather.p, baseline, (size_t)N * dtype_size(baseline_dtype), cudaMemcpyHostToDevice, st));
+      v_dev = b->gather.p;
+    }
+    CK(b->baseline.reserve((size_t)N * 8));
+    if (vdt == MRL_F64) CK(cudaMemcpyAsync(b->baseline.p, v_dev, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+    else {
+      f32_to_f64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)v_dev, b->baseline.as<double>(), N);
+      CKL(cudaGetLastError(), 1);
+    }
+    b->has_baseline = true;
+  } else if (!b->has_baseline) {
+    return fail("mrl_batch_gae: baseline == NULL but mrl_net_predict_into_baseline was not called");
+  }
+  CK(b->ret.reserve((size_t)N * 8));
+  CK(b->adv.reserve((size_t)N * 8));
+  CK(b->adv32.reserve((size_t)N * 4));
+  CK(b->stats.reserve(64));
+  RET(gae_impl(r_dev, reward_dtype, b->baseline.p, MRL_F64, b->offsets.as<long long>(),
+               b->terminated.as<unsigned char>(), b->n_paths, N, gamma, lam, b->ret.as<double>(),
+               b->adv.as<double>(), st));
+  b->has_ret = true;
+  if (standardize) {
+    CKL(launch_moments(b->adv.as<double>(), N, b->stats.as<double>(), st), 2);
+    if (comm && mrl_comm_world(comm) > 1) {
+      const int world = mrl_comm_world(comm), rank = mrl_comm_rank(comm);
+      CK(b->gather.reserve((size_t)3 * world * 8 + 64));
+      place_moments_kernel<<<1, 3 * world, 0, st>>>(b->stats.as<double>(), b->gather.as<double>(), world, rank);
+      CKL(cudaGetLastError(), 1);
+      RET(mrl_comm_allreduce_f64(comm, b->gather.as<double>(), 3 * world, st));
+      merge_moments_kernel<<<1, 1, 0, st>>>(b->gather.as<double>(), world, b->stats.as<double>());
+      CKL(cudaGetLastError(), 1);
+    }
+    CKL(launch_normalize(b->adv.as<double>(), N, b->stats.as<double>(), b->adv32.as<float>(), st), 1);
+  } else {
+    cast_f64_f32(b->adv.as<double>(), b->adv32.as<float>(), N, st);
+    CKL(cudaGetLastError(), 1);
+  }
+  b->has_adv32 = true;
+  cudaMemcpyKind kind = loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (ret_out) CK(cudaMemcpyAsync(ret_out, b->ret.p, (size_t)N * 8, kind, st));
+  if (adv_out) CK(cudaMemcpyAsync(adv_out, b->adv.p, (size_t)N * 8, kind, st));
+  if (loc == MRL_HOST && (ret_out || adv_out)) CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mrl_gae(const void* reward, int reward_dtype, const void* baseline, int baseline_dtype,
+                       const long long* offsets, const unsigned char* terminated, int n_paths, long long N,
+                       double gamma, double lam, double* ret_out, double* adv_out, int loc, void* stream) {
+  if (!reward || !baseline || !offsets || !terminated || !ret_out || !adv_out || N <= 0 || n_paths <= 0)
+    return fail("mrl_gae: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (loc == MRL_DEVICE)
+    return gae_impl(reward, reward_dtype, baseline, baseline_dtype, offsets, terminated, n_paths, N, gamma, lam,
+                    ret_out, adv_out, st);
+  DevBuf r, v, o, t, ro, ao;
+  const size_t rb = (size_t)N * dtype_size(reward_dtype), vb = (size_t)N * dtype_size(baseline_dtype);
+  int rc = 0;
+  do {
+    if (r.reserve(rb) || v.reserve(vb) || o.reserve((size_t)(n_paths + 1) * 8) || t.reserve(n_paths) ||
+        ro.reserve((size_t)N * 8) || ao.reserve((size_t)N * 8)) { rc = fail("mrl_gae: out of device memory"); break; }
+    cudaMemcpyAsync(r.p, reward, rb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(v.p, baseline, vb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(o.p, offsets, (size_t)(n_paths + 1) * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t.p, terminated, n_paths, cudaMemcpyHostToDevice, st);
+    rc = gae_impl(r.p, reward_dtype, v.p, baseline_dtype, o.as<long long>(), t.as<unsigned char>(), n_paths, N,
+                  gamma, lam, ro.as<double>(), ao.as<double>(), st);
+    if (rc) break;
+    cudaMemcpyAsync(ret_out, ro.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(adv_out, ao.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail("mrl_gae: %s", cudaGetErrorString(e));
+  } while (0);
+  r.release(); v.release(); o.release(); t.release(); ro.release(); ao.release();
+  return rc;
+}
+
+extern "C" int mrl_standardize(double* x, long long N, double* stats_out, int loc, void* stream) {
+  if (!x || N <= 0) return fail("mrl_standardize: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf xd, sd;
+  double* xp = x;
+  if (loc == MRL_HOST) {
+    CK(xd.reserve((size_t)N * 8));
+    CK(cudaMemcpyAsync(xd.p, x, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    xp = xd.as<double>();
+  }
+  CK(sd.reserve(64));
+  CKL(launch_standardize(xp, N, sd.as<double>(), nullptr, st), 3);
+  if (loc == MRL_HOST) CK(cudaMemcpyAsync(x, xp, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  if (stats_out) CK(cudaMemcpyAsync(stats_out, sd.p, 24, loc == MRL_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  xd.release(); sd.release();
+  return 0;
+}
+
+extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, double* state_n, double* state_M,
+                                double* state_S, int demean, int destd, double clip, void* y, int y_dtype, int loc,
+                                void* stream) {
+  if (!x || !y || !state_n || !state_M || !state_S || N <= 0 || d <= 0) return fail("mrl_zfilter_scan: bad arguments");
+  if ((x_dtype != MRL_F32 && x_dtype != MRL_F64) || (y_dtype != MRL_F32 && y_dtype != MRL_F64))
+    return fail("mrl_zfilter_scan: x and y must be f32/f64");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf xd, yd, sd, scr;
+  int rc = 0;
+  do {
+    const size_t xb = (size_t)N * d * dtype_size(x_dtype), yb = (size_t)N * d * dtype_size(y_dtype);
+    const void* xp = x;
+    void* yp = y;
+    cudaError_t e = cudaSuccess;
+    if (loc == MRL_HOST) {
+      if ((e = xd.reserve(xb)) || (e = yd.reserve(yb))) { rc = fail("mrl_zfilter_scan: %s", cudaGetErrorString(e)); break; }
+      cudaMemcpyAsync(xd.p, x, xb, cudaMemcpyHostToDevice, st);
+      xp = xd.p; yp = yd.p;
+    }
+    if ((e = sd.reserve((size_t)(4 * d + 8) * 8)) || (e = scr.reserve((size_t)zfilter_scratch_doubles(N, d) * 8))) {
+      rc = fail("mrl_zfilter_scan: %s", cudaGetErrorString(e)); break;
+    }
+    cudaMemcpyAsync(sd.p, state_M, (size_t)d * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(sd.as<double>() + d, state_S, (size_t)d * 8, cudaMemcpyHostToDevice, st);
+    e = launch_zfilter_scan(xp, x_dtype == MRL_F64, N, d, *state_n, sd.as<double>(), demean, destd, clip, yp,
+                            y_dtype == MRL_F64, scr.as<double>(), st);
+    if (e != cudaSuccess) { rc = fail("mrl_zfilter_scan: %s", cudaGetErrorString(e)); break; }
+    g_launches += 4;
+    if (loc == MRL_HOST) cudaMemcpyAsync(y, yd.p, yb, cudaMemcpyDeviceToHost, st);
+    std::vector<double> out(2 * d + 1);
+    cudaMemcpyAsync(out.data(), sd.as<double>() + 2 * d, (size_t)(2 * d + 1) * 8, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = fail("mrl_zfilter_scan: %s", cudaGetErrorString(e)); break; }
+    memcpy(state_M, out.data(), (size_t)d * 8);
+    memcpy(state_S, out.data() + d, (size_t)d * 8);
+    *state_n = out[2 * d];
+  } while (0);
+  xd.release(); yd.release(); sd.release(); scr.release();
+  return rc;
+}
+
+// ======================================================================== network
+struct mrl_net {
+  int device = 0;
+  NetGeom g;
+  DevBuf theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
+      out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, scal, headout, stage;
+  unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
+  const mrl_batch* cache_batch = nullptr;
+  mrl_comm* comm = nullptr;
+  double* h_scal = nullptr;   // pinned
+  CgState* h_cg = nullptr;    // pinned
+  bool last_valid = false;
+};
+
+static int world_of(const mrl_net* n) { return n->comm ? mrl_comm_world(n->comm) : 1; }
+
+extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int* dims, int head, int activation) {
+  if (!out || !dims || n_layers < 1 || n_layers > MRL_MAX_LAYERS) return fail("mrl_net_create: 1..%d layers", MRL_MAX_LAYERS);
+  if (head < 0 || head > 2 || activation < 0 || activation > 2) return fail("mrl_net_create: bad head/activation");
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] <= 0) return fail("mrl_net_create: dims must be positive");
+  for (int l = 1; l <= n_layers; ++l)
+    if (dims[l] > 256) return fail("mrl_net_create: layer width %d > 256 not supported by the fused kernels", dims[l]);
+  if (dims[n_layers] > 64) return fail("mrl_net_create: output dim %d > 64 not supported", dims[n_layers]);
+  if (head == MRL_VALUE && dims[n_layers] != 1) return fail("mrl_net_create: value head needs output dim 1");
+  CK(cudaSetDevice(device));
+  mrl_net* n = new mrl_net();
+  n->device = device;
+  const int d = dims[n_layers];
+  const int naux = head == MRL_GAUSS ? 1 + 3 * d : (head == MRL_CATEGORICAL ? 2 + d : 1);
+  mrl_build_geom(&n->g, n_layers, dims, head, activation, naux);
+  int dev_smem = 0;
+  CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const size_t need = mid_backward_smem(n->g, head == MRL_VALUE ? MRL_MODE_GRAD : MRL_MODE_FVP) + 2048;
+  if (need > (size_t)dev_smem) {
+    delete n;
+    return fail("mrl_net_create: network needs %zu B of shared memory per CTA, device offers %d", need, dev_smem);
+  }
+  const size_t P = n->g.P;
+  cudaError_t e = cudaSuccess;
+  auto R = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.reserve(bytes); };
+  R(n->theta, P * 4); R(n->theta_prev, P * 4); R(n->theta_trial, P * 4); R(n->vflat, P * 4);
+  R(n->W1p, (size_t)n->g.d0p * n->g.n1p * 4); R(n->V1p, (size_t)n->g.d0p * n->g.n1p * 4);
+  R(n->img, (size_t)n->g.img_floats * 4); R(n->imgv, (size_t)n->g.img_floats * 4);
+  R(n->out32, P * 4); R(n->out64, P * 8); R(n->g32, P * 4);
+  R(n->cg_b, P * 8); R(n->cg_x, P * 8); R(n->cg_r, P * 8); R(n->cg_p, P * 8);
+  R(n->p32, P * 4); R(n->x32, P * 4); R(n->fullstep, P * 8);
+  R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8);
+  if (e == cudaSuccess) e = cudaMallocHost(&n->h_scal, 32 * 8);
+  if (e == cudaSuccess) e = cudaMallocHost(&n->h_cg, sizeof(CgState));
+  if (e == cudaSuccess) e = cudaMemset(n->theta.p, 0, P * 4);
+  if (e != cudaSuccess) {
+    mrl_net_destroy(n);
+    return fail("mrl_net_create: %s", cudaGetErrorString(e));
+  }
+  *out = n;
+  return 0;
+}
+
+extern "C" int mrl_net_destroy(mrl_net* n) {
+  if (!n) return 0;
+  cudaSetDevice(n->device);
+  DevBuf* bufs[] = {&n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
+                    &n->Z1, &n->cache, &n->D1r, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
+                    &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->scal,
+                    &n->headout, &n->stage};
+  for (DevBuf* d : bufs) d->release();
+  if (n->h_scal) cudaFreeHost(n->h_scal);
+  if (n->h_cg) cudaFreeHost(n->h_cg);
+  delete n;
+  return 0;
+}
+extern "C" long long mrl_net_num_params(const mrl_net* n) { return n ? n->g.P : -1; }
+extern "C" int mrl_net_set_comm(mrl_net* n, mrl_comm* c) {
+  if (!n) return fail("mrl_net_set_comm: null net");
+  n->comm = c;
+  return 0;
+}
+
+__global__ void negate_first(double* s) { s[0] = -s[0]; }
+__global__ void f64_to_f32_kernel(const double* __restrict__ x, float* __restrict__ y, long long N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) y[i] = (float)x[i];
+}
+void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st) {
+  if (N > 0) f64_to_f32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x, y, N);
+}
+
+static int repack(mrl_net* n, cudaStream_t st) {
+  CKL(launch_pack_params(n->g, n->theta.as<float>(), n->W1p.as<float>(), n->img.as<float>(), st), 1);
+  n->params_version++;
+  return 0;
+}
+
+extern "C" int mrl_net_set_params(mrl_net* n, const void* theta, int dtype, int loc, void* stream) {
+  if (!n || !theta) return fail("mrl_net_set_params: bad arguments");
+  if (dtype != MRL_F32 && dtype != MRL_F64) return fail("mrl_net_set_params: theta must be f32/f64");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  const size_t P = n->g.P;
+  const void* src;
+  RET(stage_in(n->stage, theta, P * dtype_size(dtype), loc, st, &src));
+  if (dtype == MRL_F32) {
+    if (src != n->theta.p) CK(cudaMemcpyAsync(n->theta.p, src, P * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    cast_f64_f32((const double*)src, n->theta.as<float>(), (long long)P, st);   // theta.astype(floatX), core.py:540
+    CKL(cudaGetLastError(), 1);
+  }
+  return repack(n, st);
+}
+extern "C" int mrl_net_get_params(mrl_net* n, float* theta, int loc, void* stream) {
+  if (!n || !theta) return fail("mrl_net_get_params: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  CK(cudaMemcpyAsync(theta, n->theta.p, (size_t)n->g.P * 4, loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (loc == MRL_HOST) CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------ passes
+struct Plan { int slab_tiles, n_slabs; };
+static Plan plan_for(const mrl_batch* b) {
+  Plan p;
+  p.slab_tiles = (b->n_tiles + 295) / 296;
+  if (p.slab_tiles < 1) p.slab_tiles = 1;
+  if (p.slab_tiles > MRL_MAX_SLAB_TILES) p.slab_tiles = MRL_MAX_SLAB_TILES;
+  p.n_slabs = (b->n_tiles + p.slab_tiles - 1) / p.slab_tiles;
+  return p;
+}
+
+static int check_pair(const mrl_net* n, const mrl_batch* b, bool need_aux) {
+  if (!n || !b) return fail("null net or batch");
+  if (b->N <= 0) return fail("batch has no observations");
+  if (n->device != b->device) return fail("net and batch live on different devices");
+  if (n->g.d[0] > b->xdim) return fail("net input dim %d > batch feature dim %d", n->g.d[0], b->xdim);
+  if (need_aux) {
+    if (n->g.head == MRL_VALUE) {
+      if (!b->aux_vf.p) return fail("value target not bound (mrl_batch_set_vf_target)");
+    } else {
+      if (b->pol_head != n->g.head || b->pol_dout != n->g.d[n->g.L])
+        return fail("policy inputs not bound for this head (mrl_batch_set_policy_inputs)");
+    }
+  }
+  return 0;
+}
+static const float* aux_of(const mrl_net* n, const mrl_batch* b) {
+  return n->g.head == MRL_VALUE ? b->aux_vf.as<float>() : b->aux_pol.as<float>();
+}
+
+static int reserve_ws(mrl_net* n, const mrl_batch* b, const Plan& pl) {
+  const NetGeom& g = n->g;
+  CK(n->Z1.reserve((size_t)b->n_tiles * g.d[1] * MRL_LDT * 4));
+  CK(n->cache.reserve((size_t)b->n_tiles * g.act_rows * MRL_LDT * 4));
+  CK(n->D1r.reserve((size_t)b->n_tiles * MRL_TILE * g.n1p * 4));
+  CK(n->part1.reserve((size_t)pl.n_slabs * g.d[0] * g.n1p * 4));
+  CK(n->partm.reserve((size_t)pl.n_slabs * g.pmid * 4));
+  CK(n->loss_part.reserve((size_t)pl.n_slabs * 4 * 8));
+  return 0;
+}
+
+// L1F + mid forward.  losses -> n->scal[0..3] (device, already scaled by 1/N_global and all-reduced)
+static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_cache, float* head_out,
+                        cudaStream_t st, int reverse_kl = 0) {
+  const NetGeom& g = n->g;
+  const Plan pl = plan_for(b);
+  RET(reserve_ws(n, b, pl));
+  // the batch tile has b->d0p feature rows; the net consumes the first g.d0p of them
+  NetGeom gl = g;
+  CKL(launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+  MidFwdArgs a;
+  a.img = n->img.as<float>();
+  a.Zt = n->Z1.as<float>();
+  a.aux = want_losses ? aux_of(n, b) : nullptr;
+  a.cache = want_cache ? n->cache.as<float>() : nullptr;
+  a.head_out = head_out;
+  a.loss_part = want_losses ? n->loss_part.as<double>() : nullptr;
+  a.N = b->N;
+  a.n_tiles = b->n_tiles;
+  a.slab_tiles = pl.slab_tiles;
+  a.reverse_kl = reverse_kl;
+  CKL(launch_mid_forward(g, a, pl.n_slabs, st), 1);
+  if (want_losses) {
+    CKL(launch_reduce_losses(n->loss_part.as<double>(), pl.n_slabs, 1.0 / (double)b->Nglobal, n->scal.as<double>(), st), 1);
+    if (world_of(n) > 1) RET(mrl_comm_allreduce_f64(n->comm, n->scal.as<double>(), 4, st));
+  }
+  if (want_cache) {
+    n->cache_params_version = n->params_version;
+    n->cache_batch_version = b->version;
+    n->cache_batch = b;
+  }
+  return 0;
+}
+static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
+  return n->cache_batch == b && n->cache_batch_version == b->version && n->cache_params_version == n->params_version;
+}
+
+// reverse sweep + layer-1 gradient + slab reduce -> out32 (float[P], device) and out64 (double[P]).
+static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
+                         const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
+  const NetGeom& g = n->g;
+  const Plan pl = plan_for(b);
+  RET(reserve_ws(n, b, pl));
+  if (!cache_ok(n, b)) RET(pass_forward(n, b, false, true, nullptr, st));
+  MidBwdArgs a;
+  a.img = n->img.as<float>();
+  a.imgv = nullptr;
+  a.Zt = nullptr;
+  if (mode == MRL_MODE_FVP) {
+    CKL(launch_pack_params(g, v_dev, n->V1p.as<float>(), n->imgv.as<float>(), st), 1);
+    CKL(launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+    a.imgv = n->imgv.as<float>();
+    a.Zt = n->Z1.as<float>();
+  }
+  a.aux = mode == MRL_MODE_GRAD ? aux_of(n, b) : nullptr;
+  a.cache = n->cache.as<float>();
+  a.coef = coef_dev;
+  a.D1r = n->D1r.as<float>();
+  a.partm = n->partm.as<float>();
+  a.N = b->N;
+  a.n_tiles = b->n_tiles;
+  a.slab_tiles = pl.slab_tiles;
+  a.mode = mode;
+  a.reverse_kl = reverse_kl;
+  CKL(launch_mid_backward(g, a, pl.n_slabs, st), 1);
+  CKL(launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
+                     b->n_tiles, pl.n_slabs, st), 1);
+  const int world = world_of(n);
+  // terms that are not sums over timesteps are divided by `world` so that the all-reduce restores them
+  const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;
+  CKL(launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
+                             l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
+                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32, out64, st), 1);
+  if (world > 1) {
+    RET(mrl_comm_allreduce_f64(n->comm, out64, g.P, st));
+    if (out32) {
+      cast_f64_f32(out64, out32, g.P, st);
+      CKL(cudaGetLastError(), 1);
+    }
+  }
+  return 0;
+}
+
+static int d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mrl_net_forward(mrl_net* n, mrl_batch* b, float* out, int loc, void* stream) {
+  RET(check_pair(n, b, false));
+  if (!out) return fail("mrl_net_forward: out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  const size_t bytes = (size_t)b->N * n->g.d[n->g.L] * 4;
+  float* dev = out;
+  if (loc == MRL_HOST) {
+    CK(n->headout.reserve(bytes));
+    dev = n->headout.as<float>();
+  }
+  RET(pass_forward(n, b, false, false, dev, st));
+  if (loc == MRL_HOST) RET(d2h_sync(out, dev, bytes, st));
+  return 0;
+}
+
+extern "C" int mrl_net_predict_into_baseline(mrl_net* n, mrl_batch* b, void* stream) {
+  RET(check_pair(n, b, false));
+  if (n->g.head != MRL_VALUE) return fail("mrl_net_predict_into_baseline: not a value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  CK(n->headout.reserve((size_t)b->N * 4));
+  CK(b->baseline.reserve((size_t)b->N * 8));
+  RET(pass_forward(n, b, false, false, n->headout.as<float>(), st));
+  f32_to_f64_kernel<<<(unsigned)((b->N + 255) / 256), 256, 0, st>>>(n->headout.as<float>(), b->baseline.as<double>(), b->N);
+  CKL(cudaGetLastError(), 1);
+  b->has_baseline = true;
+  return 0;
+}
+
+extern "C" int mrl_net_losses(mrl_net* n, mrl_batch* b, double out[3], void* stream) {
+  RET(check_pair(n, b, true));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  RET(pass_forward(n, b, true, false, nullptr, st));
+  RET(d2h_sync(n->h_scal, n->scal.p, 32, st));
+  if (n->g.head != MRL_VALUE) out[0] = -n->h_scal[0];   // surr = -(1/N) sum rho*adv  (trpo.py:42)
+  else out[0] = n->h_scal[0];
+  out[1] = n->h_scal[1];
+  out[2] = n->h_scal[2];
+  return 0;
+}
+
+static int copy_out(void* dst, const void* src_dev, size_t bytes, int loc, cudaStream_t st) {
+  CK(cudaMemcpyAsync(dst, src_dev, bytes, loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (loc == MRL_HOST) CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mrl_net_policy_gradient(mrl_net* n, mrl_batch* b, float* gout, int loc, double losses[3], void* stream) {
+  RET(check_pair(n, b, true));
+  if (n->g.head == MRL_VALUE) return fail("mrl_net_policy_gradient: value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  RET(pass_forward(n, b, true, true, nullptr, st));
+  RET(pass_backward(n, b, MRL_MODE_GRAD, nullptr, 0, nullptr, 0.0, n->g32.as<float>(), n->out64.as<double>(), st));
+  if (losses) {
+    RET(d2h_sync(n->h_scal, n->scal.p, 32, st));
+    losses[0] = -n->h_scal[0]; losses[1] = n->h_scal[1]; losses[2] = n->h_scal[2];
+  }
+  if (gout) RET(copy_out(gout, n->g32.p, (size_t)n->g.P * 4, loc, st));
+  return 0;
+}
+
+extern "C" int mrl_net_fvp(mrl_net* n, mrl_batch* b, const float* v, float* out, int loc, void* stream) {
+  RET(check_pair(n, b, false));
+  if (!v || !out) return fail("mrl_net_fvp: null vector");
+  if (n->g.head == MRL_VALUE) return fail("mrl_net_fvp: value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  const float* vdev = v;
+  if (loc == MRL_HOST) {
+    CK(cudaMemcpyAsync(n->vflat.p, v, (size_t)n->g.P * 4, cudaMemcpyHostToDevice, st));
+    vdev = n->vflat.as<float>();
+  }
+  RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, vdev, 0.0, n->out32.as<float>(), n->out64.as<double>(), st));
+  return copy_out(out, n->out32.p, (size_t)n->g.P * 4, loc, st);
+}
+
+extern "C" int mrl_net_ppo_lossgrad(mrl_net* n, mrl_batch* b, double kl_coeff, double kl_cutoff, int reverse_kl,
+                                    double* pensurr, double* gout, double losses[3], void* stream) {
+  RET(check_pair(n, b, true));
+  if (n->g.head == MRL_VALUE) return fail("mrl_net_ppo_lossgrad: value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  // forward: surr/kl/ent; kl(new||old) needs its own sum when reverse_kl: handled inside the forward by aux order
+  RET(pass_forward(n, b, true, true, nullptr, st, reverse_kl));
+  double* scal = n->scal.as<double>();
+  // scal[0] holds +mean(rho*adv): the coefficient kernel expects surr = -that
+  negate_first<<<1, 1, 0, st>>>(scal);
+  CKL(cudaGetLastError(), 1);
+  CKL(launch_ppo_coef(scal, kl_coeff, kl_cutoff, scal + 8, scal + 10, st), 1);
+  RET(pass_backward(n, b, MRL_MODE_GRAD, scal + 8, reverse_kl, nullptr, 0.0, nullptr, n->out64.as<double>(), st));
+  RET(d2h_sync(n->h_scal, n->scal.p, 16 * 8, st));
+  if (losses) { losses[0] = n->h_scal[0]; losses[1] = n->h_scal[1]; losses[2] = n->h_scal[2]; }
+  if (pensurr) *pensurr = n->h_scal[10];
+  if (gout) RET(d2h_sync(gout, n->out64.p, (size_t)n->g.P * 8, st));
+  return 0;
+}
+
+__global__ void l2_sum_kernel(const float* __restrict__ theta, int P, double coef, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s += (double)theta[i] * (double)theta[i];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) *out = coef * s;
+}
+
+extern "C" int mrl_net_vf_lossgrad(mrl_net* n, mrl_batch* b, double l2coeff, double losses[3], double* gout, void* stream) {
+  RET(check_pair(n, b, true));
+  if (n->g.head != MRL_VALUE) return fail("mrl_net_vf_lossgrad: not a value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  RET(pass_forward(n, b, true, gout != nullptr, nullptr, st));
+  l2_sum_kernel<<<1, 1024, 0, st>>>(n->theta.as<float>(), n->g.P, l2coeff, n->scal.as<double>() + 4);
+  CKL(cudaGetLastError(), 1);
+  if (gout) RET(pass_backward(n, b, MRL_MODE_GRAD, nullptr, 0, nullptr, 2.0 * l2coeff, nullptr, n->out64.as<double>(), st));
+  RET(d2h_sync(n->h_scal, n->scal.p, 8 * 8, st));
+  const double mse = n->h_scal[0], l2 = n->h_scal[4];
+  if (losses) { losses[0] = mse + l2; losses[1] = mse; losses[2] = l2; }
+  if (gout) RET(d2h_sync(gout, n->out64.p, (size_t)n->g.P * 8, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------ TRPO step
+extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* cfg, double stats[6], int info[6],
+                                 void* stream) {
+  RET(check_pair(n, b, true));
+  if (!cfg || !stats) return fail("mrl_net_trpo_step: null cfg/stats");
+  if (n->g.head == MRL_VALUE) return fail("mrl_net_trpo_step: value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  const NetGeom& g = n->g;
+  const int P = g.P;
+  int fvp_calls = 0, loss_passes = 0;
+  n->last_valid = false;
+
+  // gradient + losses at theta_old (trpo.py:94-95); the forward pass also fills the activation cache
+  CK(cudaMemcpyAsync(n->theta_prev.p, n->theta.p, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+  RET(pass_forward(n, b, true, true, nullptr, st));
+  loss_passes++;
+  RET(pass_backward(n, b, MRL_MODE_GRAD, nullptr, 0, nullptr, 0.0, n->g32.as<float>(), n->out64.as<double>(), st));
+  CKL(launch_cg_init(P, n->g32.as<float>(), n->cg_b.as<double>(), n->cg_x.as<double>(), n->cg_r.as<double>(),
+                     n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(), st), 1);
+  CK(cudaMemcpyAsync(n->h_scal, n->scal.p, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(n->h_cg, n->cgstate.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+  // CG does not depend on the host check below, so it is enqueued before the sync
+  for (int it = 0; it < cfg->cg_iters; ++it) {
+    RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
+                      n->out64.as<double>(), st));
+    fvp_calls++;
+    CKL(launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
+                       n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(), st), 1);
+  }
+  CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
+  RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),
+                    n->out64.as<double>(), st));
+  fvp_calls++;
+  CKL(launch_cg_finish(P, n->out32.as<float>(), cfg->cg_damping, cfg->max_kl, n->g32.as<float>(),
+                       n->cg_x.as<double>(), n->fullstep.as<double>(), n->cgstate.as<CgState>(), st), 1);
+  CK(cudaStreamSynchronize(st));   // h_scal / h_cg (first snapshot) are valid now
+  const double before[3] = {-n->h_scal[0], n->h_scal[1], n->h_scal[2]};
+  const double gmax = n->h_cg->gmax;
+  double after[3] = {before[0], before[1], before[2]};
+  int skipped = 0, success = 0, accepted = -1, cg_run = 0;
+  if (!(gmax > 1e-8)) {            // np.allclose(g, 0): |g_i| <= atol=1e-8  (trpo.py:102)
+    skipped = 1;
+  } else {
+    RET(d2h_sync(n->h_cg, n->cgstate.p, sizeof(CgState), st));
+    cg_run = n->h_cg->iters;
+    const double rate = n->h_cg->expected_rate;
+    const double fval = before[0];  // f(x) re-evaluates the same graph at the same theta (trpo.py:147)
+    for (int k = 0; k < cfg->max_backtracks; ++k) {
+      const double stepfrac = ldexp(1.0, -k);
+      CKL(launch_ls_candidate(P, n->theta_prev.as<float>(), n->fullstep.as<double>(), stepfrac,
+                              n->theta.as<float>(), st), 1);
+      RET(repack(n, st));
+      RET(pass_forward(n, b, true, false, nullptr, st));
+      loss_passes++;
+      RET(d2h_sync(n->h_scal, n->scal.p, 32, st));
+      const double newf = -n->h_scal[0];
+      const double actual = fval - newf, expected = rate * stepfrac, ratio = actual / expected;
+      if (ratio > cfg->accept_ratio && actual > 0) {
+        success = 1;
+        accepted = k;
+        after[0] = newf; after[1] = n->h_scal[1]; after[2] = n->h_scal[2];
+        break;
+      }
+    }
+    if (!success) {                // rollback (trpo.py:133 with theta = x)
+      CK(cudaMemcpyAsync(n->theta.p, n->theta_prev.p, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+      RET(repack(n, st));
+    }
+    n->last_valid = true;
+  }
+  stats[0] = before[0]; stats[1] = after[0];
+  stats[2] = before[1]; stats[3] = after[1];
+  stats[4] = before[2]; stats[5] = after[2];
+  if (info) {
+    info[0] = skipped; info[1] = success; info[2] = accepted; info[3] = cg_run; info[4] = fvp_calls;
+    info[5] = loss_passes;
+  }
+  return 0;
+}
+
+extern "C" int mrl_net_get_trpo_vectors(mrl_net* n, double* stepdir, double* fullstep, double* scalars) {
+  if (!n || !n->last_valid) return fail("mrl_net_get_trpo_vectors: no completed step");
+  CK(cudaSetDevice(n->device));
+  const size_t bytes = (size_t)n->g.P * 8;
+  if (stepdir) CK(cudaMemcpy(stepdir, n->cg_x.p, bytes, cudaMemcpyDeviceToHost));
+  if (fullstep) CK(cudaMemcpy(fullstep, n->fullstep.p, bytes, cudaMemcpyDeviceToHost));
+  if (scalars) {
+    CK(cudaMemcpy(n->h_cg, n->cgstate.p, sizeof(CgState), cudaMemcpyDeviceToHost));
+    scalars[0] = n->h_cg->shs; scalars[1] = n->h_cg->lm; scalars[2] = n->h_cg->expected_rate;
+    scalars[3] = n->h_cg->rdotr;
+  }
+  return 0;
+}

@@ -1,0 +1,80 @@
+// Internal launcher declarations shared between the .cu translation units.
+#pragma once
+#include "common.cuh"
+
+// ---- mlp_l1.cu
+cudaError_t launch_l1_forward_strided(const NetGeom& g, const float* Xt, int x_rows, const float* Bp, float* Zt,
+                                      int n_tiles, cudaStream_t st);
+cudaError_t launch_l1_grad(const NetGeom& g, const float* Xr, int d0r, const float* D1r, float* part1,
+                           int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st);
+cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* W1p, float* img, cudaStream_t st);
+cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
+                                   double scale, const float* theta, double l2c2, const float* vflat, double vls,
+                                   float* out32, double* out64, cudaStream_t st);
+cudaError_t launch_reduce_losses(const double* parts, int n_slabs, double scale, double* out, cudaStream_t st);
+cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncols, int ncols_out, long long N,
+                              float* dst, int rows_per_tile, int row_off, int n_tiles, cudaStream_t st);
+cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols, long long N, float* dst,
+                             int ldo, long long rows_out, cudaStream_t st);
+cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
+                                int d0p, int col, float* Xr, int d0r, int* tindex, cudaStream_t st);
+
+// ---- mlp_mid.cu
+struct MidFwdArgs {
+  const float* img;    // theta image
+  const float* Zt;     // layer-1 pre-activations, tile-major [n_tiles][d1][LDT]
+  const float* aux;    // side inputs, tile-major [n_tiles][naux][LDT] (nullptr: no losses)
+  float* cache;        // activations + head output, tile-major [n_tiles][act_rows][LDT] (nullptr: none)
+  float* head_out;     // row-major [N][d_L] head output (mean | probs | value), nullptr: none
+  double* loss_part;   // [n_slabs][4]
+  long long N;
+  int n_tiles, slab_tiles, reverse_kl;
+};
+struct MidBwdArgs {
+  const float* img;    // theta image
+  const float* imgv;   // tangent image (Fvp mode)
+  const float* Zt;     // Fvp: x . V1
+  const float* aux;
+  const float* cache;
+  const double* coef;  // device: {c_surr, c_kl} (gradient mode)
+  float* D1r;          // out: delta_1 row-major [n_tiles*64][n1p]
+  float* partm;        // out: [n_slabs][pmid]
+  long long N;
+  int n_tiles, slab_tiles, mode, reverse_kl;
+};
+size_t mid_forward_smem(const NetGeom& g);
+size_t mid_backward_smem(const NetGeom& g, int mode);
+cudaError_t launch_mid_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st);
+cudaError_t launch_mid_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st);
+
+// ---- vec_kernels.cu  (CG / line-search vector algebra on device-resident fp64 vectors)
+struct CgState {   // device-resident scalars
+  double rdotr, pz, alpha, beta, shs, lm, gdots, expected_rate, gmax;
+  int done, iters, pad0, pad1;
+};
+cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* r, double* p, float* p32,
+                           CgState* s, cudaStream_t st);
+cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
+                           float* p32, CgState* s, cudaStream_t st);
+cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st);
+cudaError_t launch_cg_finish(int P, const float* z32, double damping, double max_kl, const float* g,
+                             const double* x, double* fullstep, CgState* s, cudaStream_t st);
+cudaError_t launch_ls_candidate(int P, const float* theta_prev, const double* fullstep, double stepfrac,
+                                float* theta_new, cudaStream_t st);
+cudaError_t launch_ppo_coef(const double* losses, double kl_coeff, double kl_cutoff, double* coef,
+                            double* pen_out, cudaStream_t st);
+
+void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st);  // api.cu
+
+// ---- scan_kernels.cu
+cudaError_t launch_gae(const void* reward, int reward_f64, const void* baseline, int baseline_f64,
+                       const long long* offsets, const unsigned char* terminated, int n_paths, long long N,
+                       double gamma, double lam, double* ret, double* adv, cudaStream_t st);
+cudaError_t launch_standardize(double* adv, long long N, double* stats /* n, mean, M2 */, float* adv32,
+                               cudaStream_t st);
+cudaError_t launch_moments(const double* x, long long N, double* stats, cudaStream_t st);
+cudaError_t launch_normalize(double* x, long long N, const double* stats, float* x32, cudaStream_t st);
+cudaError_t launch_zfilter_scan(const void* x, int x_f64, long long N, int d, double n0, double* state_dev,
+                                int demean, int destd, double clip, void* y, int y_f64, double* scratch,
+                                cudaStream_t st);
+long long zfilter_scratch_doubles(long long N, int d);

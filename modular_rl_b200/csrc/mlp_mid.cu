@@ -1,0 +1,556 @@
+// Fused per-tile MLP chain for layers >= 2, the distribution heads, and the reverse sweeps.
+//
+// One CTA owns a slab of up to 16 tiles (1024 timesteps).  All weights of layers 2..L (plus
+// transposes and the tangent's weights for the R-op) live in shared memory for the CTA's
+// lifetime; per tile the activations of all layers are held feature-major in shared memory
+// ([feature][68]), every GEMM is a register-tiled SIMT FP32 product (4x4 per thread,
+// 32x16 per warp, both operands read with conflict-free broadcast LDS.128), and weight
+// gradients accumulate in shared memory until the slab is flushed as one fp32 partial.
+//
+//   mid_forward_kernel : h1 = act(Z1+b1), ..., head -> surr/kl/ent (or MSE) sums, activation cache
+//                        trpo.py:37-42,60-63 ; core.py:339-365,402-438 ; core.py:613-617
+//   mid_backward_kernel<GRAD> : dL/dz_L from the head, reverse sweep         trpo.py:43, ppo.py:47-49
+//   mid_backward_kernel<FVP>  : R-forward (Pearlmutter), Fisher metric, reverse sweep  trpo.py:45-58
+#include "common.cuh"
+#include "kernels.h"
+
+#define LOG_2PI 1.8378770664093453f
+#define LOG_2PIE 2.8378770664093453f
+#define MAX_DOUT 64
+
+struct Lane {
+  int warp, lane, rg, cg;
+  __device__ Lane() {
+    warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    rg = lane & 7;
+    cg = lane >> 3;
+  }
+};
+
+// acc[i][j] += sum_k A[k][r+i] * B[k][c+j]
+__device__ __forceinline__ void gemm_acc(float (&acc)[4][4], const float* __restrict__ A,
+                                         const float* __restrict__ B, int K, int ldb, int r, int c) {
+  const float* a = A + r;
+  const float* b = B + c;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(a + k * MRL_LDT);
+    const float4 bv = *reinterpret_cast<const float4*>(b + k * ldb);
+    acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+    acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
+    acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+    acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
+    acc[2][0] = fmaf(av.z, bv.x, acc[2][0]); acc[2][1] = fmaf(av.z, bv.y, acc[2][1]);
+    acc[2][2] = fmaf(av.z, bv.z, acc[2][2]); acc[2][3] = fmaf(av.z, bv.w, acc[2][3]);
+    acc[3][0] = fmaf(av.w, bv.x, acc[3][0]); acc[3][1] = fmaf(av.w, bv.y, acc[3][1]);
+    acc[3][2] = fmaf(av.w, bv.z, acc[3][2]); acc[3][3] = fmaf(av.w, bv.w, acc[3][3]);
+  }
+}
+
+// One warp job of  OUT[c][r] = epi(c, r, sum_k A1[k][r] B1[k][c] (+ sum_k A2[k][r] B2[k][c])).
+// job -> 32 rows x 16 cols; epi receives 4 consecutive rows of one column.
+template <class Epi>
+__device__ __forceinline__ void fwd_job(int job, const Lane& ln, const float* A1, const float* B1, int K1,
+                                        const float* A2, const float* B2, int K2, int ldb, int n_out,
+                                        Epi epi) {
+  const int rj = job & 1, cj = job >> 1;
+  const int r = rj * 32 + 4 * ln.rg;
+  const int c = cj * 16 + 4 * ln.cg;
+  const int cc = min(c, ldb - 4);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  gemm_acc(acc, A1, B1, K1, ldb, r, cc);
+  if (A2 != nullptr) gemm_acc(acc, A2, B2, K2, ldb, r, cc);
+  if (c == cc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < n_out) epi(c + j, r, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+  }
+}
+__device__ __forceinline__ int fwd_jobs(int n_out) { return 2 * ((n_out + 15) >> 4); }
+
+// One warp job of  G[m][n] += sum_r A[m][r] * D[n][r]   (32 m x 16 n per job)
+__device__ __forceinline__ void grad_job(int job, int n_nblk, const Lane& ln, const float* __restrict__ A,
+                                         int M, const float* __restrict__ D, int Nn, float* G, int ldg) {
+  const int m0 = (job / n_nblk) * 32, n0 = (job % n_nblk) * 16;
+  const int mg = ln.lane & 7, ng = ln.lane >> 3;
+  const float* ap[4];
+  const float* dp[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    ap[q] = A + min(m0 + mg + 8 * q, M - 1) * MRL_LDT;
+    dp[q] = D + min(n0 + ng + 4 * q, Nn - 1) * MRL_LDT;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < MRL_TILE; k += 4) {
+    float4 a[4], d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a[q] = *reinterpret_cast<const float4*>(ap[q] + k);
+      d[q] = *reinterpret_cast<const float4*>(dp[q] + k);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a[i].x, d[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, d[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, d[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, d[j].w, acc[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + mg + 8 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ng + 4 * j;
+      if (m < M && n < Nn) G[m * ldg + n] += acc[i][j];
+    }
+  }
+}
+
+// gb[j] += sum_r D[j][r] for 8 features per job
+__device__ __forceinline__ void bias_job(int job, const Lane& ln, const float* __restrict__ D, int Nn, float* gb) {
+  for (int q = 0; q < 8; ++q) {
+    const int j = job * 8 + q;
+    if (j >= Nn) break;
+    float s = D[j * MRL_LDT + ln.lane] + D[j * MRL_LDT + 32 + ln.lane];
+    s = warp_sum(s);
+    if (ln.lane == 0) gb[j] += s;
+  }
+}
+
+__device__ __forceinline__ void copy_f4(float* dst, const float* src, int nfloats) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d[i] = s[i];
+}
+
+// =====================================================================================
+template <int HEAD, int ACT>
+__global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom g, MidFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* img = smem;
+  float* act = img + g.bw_floats;
+  __shared__ double red[32];
+  __shared__ float sig[MAX_DOUT], logsig[MAX_DOUT];
+  const Lane ln;
+  const int tid = threadIdx.x;
+  const int L = g.L, dL = g.d[L];
+  const int slab = blockIdx.x;
+  const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
+
+  copy_f4(img, a.img, g.bw_floats);
+  __syncthreads();
+  if (HEAD == MRL_HEAD_GAUSS && tid < dL) {
+    const float ls = img[g.off_pm_logstd + tid];
+    logsig[tid] = ls;
+    sig[tid] = expf(ls);
+  }
+  double s_surr = 0.0, s_kl = 0.0, s_ent = 0.0;
+  float* headbuf = act + g.off_act[L] * MRL_LDT;
+
+  for (int tile = t0; tile < t1; ++tile) {
+    const int nvalid = (int)min((long long)MRL_TILE, a.N - (long long)tile * MRL_TILE);
+    {  // h1 = act(Z1 + b1)   (or the head pre-activation when L == 1)
+      const float4* zs = reinterpret_cast<const float4*>(a.Zt + (size_t)tile * g.d[1] * MRL_LDT);
+      float4* dst = reinterpret_cast<float4*>(act);
+      const float* b1 = img + g.off_b[1];
+      const int n4 = g.d[1] * (MRL_LDT / 4);
+      for (int i = tid; i < n4; i += MRL_MID_THREADS) {
+        float4 z = zs[i];
+        const float b = b1[i / (MRL_LDT / 4)];
+        if (L > 1) {
+          z.x = act_fn<ACT>(z.x + b); z.y = act_fn<ACT>(z.y + b);
+          z.z = act_fn<ACT>(z.z + b); z.w = act_fn<ACT>(z.w + b);
+        } else {
+          z.x += b; z.y += b; z.z += b; z.w += b;
+        }
+        dst[i] = z;
+      }
+    }
+    __syncthreads();
+    for (int l = 2; l <= L; ++l) {
+      const float* A = act + g.off_act[l - 1] * MRL_LDT;
+      float* O = act + g.off_act[l] * MRL_LDT;
+      const float* W = img + g.off_W[l];
+      const float* b = img + g.off_b[l];
+      const int nj = fwd_jobs(g.d[l]);
+      const bool last = (l == L);
+      for (int job = ln.warp; job < nj; job += MRL_MID_THREADS / 32) {
+        fwd_job(job, ln, A, W, g.d[l - 1], nullptr, nullptr, 0, g.ldw[l], g.d[l],
+                [&](int c, int r, float4 v) {
+                  const float bb = b[c];
+                  if (last) {
+                    v.x += bb; v.y += bb; v.z += bb; v.w += bb;
+                  } else {
+                    v.x = act_fn<ACT>(v.x + bb); v.y = act_fn<ACT>(v.y + bb);
+                    v.z = act_fn<ACT>(v.z + bb); v.w = act_fn<ACT>(v.w + bb);
+                  }
+                  *reinterpret_cast<float4*>(O + c * MRL_LDT + r) = v;
+                });
+      }
+      __syncthreads();
+    }
+    // ---- head: one thread per timestep
+    if (tid < MRL_TILE) {
+      const int r = tid;
+      const bool valid = r < nvalid;
+      const float* aux = a.aux ? a.aux + (size_t)tile * g.naux * MRL_LDT + r : nullptr;
+      if (HEAD == MRL_HEAD_GAUSS) {
+        if (aux) {
+          const float adv = aux[0];
+          float dl = 0.f, kl = 0.f, sls = 0.f;
+          for (int j = 0; j < dL; ++j) {
+            const float mu = headbuf[j * MRL_LDT + r];
+            const float ac = aux[(1 + j) * MRL_LDT];
+            const float m0 = aux[(1 + dL + j) * MRL_LDT];
+            const float s0 = aux[(1 + 2 * dL + j) * MRL_LDT];
+            const float sg = sig[j];
+            const float t = (ac - mu) / sg, t0 = (ac - m0) / s0;
+            const float lr = logsig[j] - logf(s0);           // log(sigma/sigma0)
+            dl += -0.5f * (t - t0) * (t + t0) - lr;           // logp - oldlogp, term by term
+            const float dm = m0 - mu;
+            // log(s1/s0) + (s0^2 + dm^2)/(2 s1^2) - 1/2, with the s0~s1 cancellation taken analytically
+            if (!a.reverse_kl) kl += lr + 0.5f * ((s0 - sg) * (s0 + sg) + dm * dm) / (sg * sg);
+            else kl += -lr + 0.5f * ((sg - s0) * (sg + s0) + dm * dm) / (s0 * s0);   // KL(new || old), ppo.py:40-41
+            sls += logsig[j];
+          }
+          if (valid) {
+            s_surr += (double)(expf(dl) * adv);
+            s_kl += (double)kl;
+            s_ent += (double)(sls + 0.5f * LOG_2PIE * dL);
+          }
+        }
+      } else if (HEAD == MRL_HEAD_CAT) {
+        float m = -INFINITY;
+        for (int j = 0; j < dL; ++j) m = fmaxf(m, headbuf[j * MRL_LDT + r]);
+        float s = 0.f;
+        for (int j = 0; j < dL; ++j) {
+          const float e = expf(headbuf[j * MRL_LDT + r] - m);
+          headbuf[j * MRL_LDT + r] = e;
+          s += e;
+        }
+        const float inv = 1.f / s;
+        float kl = 0.f, ent = 0.f, pa = 1.f, p0a = 1.f;
+        const int ai = aux ? (int)aux[1 * MRL_LDT] : 0;
+        for (int j = 0; j < dL; ++j) {
+          const float p = headbuf[j * MRL_LDT + r] * inv;
+          headbuf[j * MRL_LDT + r] = p;
+          if (aux) {
+            const float p0 = aux[(2 + j) * MRL_LDT];
+            kl += a.reverse_kl ? p * logf(p / p0) : p0 * logf(p0 / p);
+            ent -= p * logf(p);
+            if (j == ai) { pa = p; p0a = p0; }
+          }
+        }
+        if (aux && valid) {
+          s_surr += (double)((pa / p0a) * aux[0]);
+          s_kl += (double)kl;
+          s_ent += (double)ent;
+        }
+      } else {  // value head: squared error against the target row
+        if (aux && valid) {
+          const float df = aux[0] - headbuf[r];
+          s_surr += (double)df * (double)df;
+        }
+      }
+    }
+    __syncthreads();
+    if (a.cache) copy_f4(a.cache + (size_t)tile * g.act_rows * MRL_LDT, act, g.act_rows * MRL_LDT);
+    if (a.head_out) {
+      for (int i = tid; i < MRL_TILE * dL; i += MRL_MID_THREADS) {
+        const int r = i / dL, j = i % dL;
+        if (r < nvalid) a.head_out[((size_t)tile * MRL_TILE + r) * dL + j] = headbuf[j * MRL_LDT + r];
+      }
+    }
+    __syncthreads();
+  }
+  if (a.loss_part) {
+    double v0 = block_sum(s_surr, red);
+    double v1 = block_sum(s_kl, red);
+    double v2 = block_sum(s_ent, red);
+    if (tid == 0) {
+      double* o = a.loss_part + (size_t)slab * 4;
+      o[0] = v0; o[1] = v1; o[2] = v2; o[3] = 0.0;
+    }
+  }
+}
+
+// =====================================================================================
+template <int HEAD, int ACT, int MODE>
+__global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeom g, MidBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* img = smem;
+  float* imgv = img + g.img_floats;
+  float* G = imgv + (MODE == MRL_MODE_FVP ? g.bw_floats : 0);
+  float* GL = G + g.bw_floats;
+  const int gl_floats = (MODE == MRL_MODE_GRAD && HEAD == MRL_HEAD_GAUSS) ? g.d[g.L] * MRL_TILE : 0;
+  float* H = GL + gl_floats;
+  float* E = H + g.act_rows * MRL_LDT;
+  __shared__ float sig[MAX_DOUT], ivar[MAX_DOUT];
+  const Lane ln;
+  const int tid = threadIdx.x;
+  const int L = g.L, dL = g.d[L];
+  const int slab = blockIdx.x;
+  const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
+  constexpr int NW = MRL_MID_THREADS / 32;
+
+  copy_f4(img, a.img, g.img_floats);
+  if (MODE == MRL_MODE_FVP) copy_f4(imgv, a.imgv, g.bw_floats);
+  for (int i = tid; i < g.bw_floats + gl_floats; i += MRL_MID_THREADS) G[i] = 0.f;
+  __syncthreads();
+  if (HEAD == MRL_HEAD_GAUSS && tid < dL) {
+    const float ls = img[g.off_pm_logstd + tid];
+    sig[tid] = expf(ls);
+    ivar[tid] = expf(-2.f * ls);
+  }
+  double c_s = 1.0, c_k = 0.0;
+  if (MODE == MRL_MODE_GRAD && a.coef) { c_s = a.coef[0]; c_k = a.coef[1]; }
+  const float cs = (float)c_s, ck = (float)c_k;
+  float* Hh = H + g.off_act[L] * MRL_LDT;   // cached head output (mean | probs | value)
+  float* EH = E + g.off_act[L] * MRL_LDT;   // Rz_L, then delta_L
+  __syncthreads();
+
+  for (int tile = t0; tile < t1; ++tile) {
+    const int nvalid = (int)min((long long)MRL_TILE, a.N - (long long)tile * MRL_TILE);
+    copy_f4(H, a.cache + (size_t)tile * g.act_rows * MRL_LDT, g.act_rows * MRL_LDT);
+    if (MODE == MRL_MODE_FVP) {
+      // R-forward, layer 1: Rh1 = act'(h1) * (x.V1 + vb1).  Same thread wrote H[i] just above.
+      const float4* zs = reinterpret_cast<const float4*>(a.Zt + (size_t)tile * g.d[1] * MRL_LDT);
+      const float4* hs = reinterpret_cast<const float4*>(H);
+      float4* dst = reinterpret_cast<float4*>(E);
+      const float* vb1 = imgv + g.off_b[1];
+      const int n4 = g.d[1] * (MRL_LDT / 4);
+      for (int i = tid; i < n4; i += MRL_MID_THREADS) {
+        float4 z = zs[i];
+        const float b = vb1[i / (MRL_LDT / 4)];
+        if (L > 1) {
+          const float4 h = hs[i];
+          z.x = dact_from_h<ACT>(h.x) * (z.x + b); z.y = dact_from_h<ACT>(h.y) * (z.y + b);
+          z.z = dact_from_h<ACT>(h.z) * (z.z + b); z.w = dact_from_h<ACT>(h.w) * (z.w + b);
+        } else {
+          z.x += b; z.y += b; z.z += b; z.w += b;
+        }
+        dst[i] = z;
+      }
+    }
+    __syncthreads();
+    if (MODE == MRL_MODE_FVP) {
+      for (int l = 2; l <= L; ++l) {  // Rz_l = Rh_{l-1} W_l + h_{l-1} V_l + vb_l
+        const float* RA = E + g.off_act[l - 1] * MRL_LDT;
+        const float* HA = H + g.off_act[l - 1] * MRL_LDT;
+        const float* Hl = H + g.off_act[l] * MRL_LDT;
+        float* O = E + g.off_act[l] * MRL_LDT;
+        const float* W = img + g.off_W[l];
+        const float* V = imgv + g.off_W[l];
+        const float* vb = imgv + g.off_b[l];
+        const int nj = fwd_jobs(g.d[l]);
+        const bool last = (l == L);
+        for (int job = ln.warp; job < nj; job += NW) {
+          fwd_job(job, ln, RA, W, g.d[l - 1], HA, V, g.d[l - 1], g.ldw[l], g.d[l],
+                  [&](int c, int r, float4 v) {
+                    const float bb = vb[c];
+                    v.x += bb; v.y += bb; v.z += bb; v.w += bb;
+                    if (!last) {
+                      const float4 h = *reinterpret_cast<const float4*>(Hl + c * MRL_LDT + r);
+                      v.x *= dact_from_h<ACT>(h.x); v.y *= dact_from_h<ACT>(h.y);
+                      v.z *= dact_from_h<ACT>(h.z); v.w *= dact_from_h<ACT>(h.w);
+                    }
+                    *reinterpret_cast<float4*>(O + c * MRL_LDT + r) = v;
+                  });
+        }
+        __syncthreads();
+      }
+    }
+    // ---- head: delta_L (un-normalised; 1/N is applied by the slab reduce)
+    if (tid < MRL_TILE) {
+      const int r = tid;
+      const bool valid = r < nvalid;
+      const float* aux = a.aux ? a.aux + (size_t)tile * g.naux * MRL_LDT + r : nullptr;
+      if (MODE == MRL_MODE_FVP) {
+        if (HEAD == MRL_HEAD_GAUSS) {          // M = diag(1/sigma^2) on the mean block
+          for (int j = 0; j < dL; ++j) EH[j * MRL_LDT + r] = valid ? EH[j * MRL_LDT + r] * ivar[j] : 0.f;
+        } else if (HEAD == MRL_HEAD_CAT) {     // M = diag(p) - p p^T
+          float s = 0.f;
+          for (int j = 0; j < dL; ++j) s += Hh[j * MRL_LDT + r] * EH[j * MRL_LDT + r];
+          for (int j = 0; j < dL; ++j) {
+            const float p = Hh[j * MRL_LDT + r];
+            EH[j * MRL_LDT + r] = valid ? p * (EH[j * MRL_LDT + r] - s) : 0.f;
+          }
+        } else {
+          for (int j = 0; j < dL; ++j)
+            if (!valid) EH[j * MRL_LDT + r] = 0.f;
+        }
+      } else if (!valid) {
+        for (int j = 0; j < dL; ++j) EH[j * MRL_LDT + r] = 0.f;   // padded timesteps contribute nothing
+      } else {
+        if (HEAD == MRL_HEAD_GAUSS) {
+          const float adv = aux[0];
+          float dl = 0.f;
+          for (int j = 0; j < dL; ++j) {
+            const float mu = Hh[j * MRL_LDT + r];
+            const float ac = aux[(1 + j) * MRL_LDT];
+            const float m0 = aux[(1 + dL + j) * MRL_LDT];
+            const float s0 = aux[(1 + 2 * dL + j) * MRL_LDT];
+            const float t = (ac - mu) / sig[j], t0 = (ac - m0) / s0;
+            dl += -0.5f * (t - t0) * (t + t0) - (logf(sig[j]) - logf(s0));
+          }
+          const float w = -expf(dl) * adv * cs;
+          for (int j = 0; j < dL; ++j) {
+            const float mu = Hh[j * MRL_LDT + r];
+            const float ac = aux[(1 + j) * MRL_LDT];
+            const float m0 = aux[(1 + dL + j) * MRL_LDT];
+            const float s0 = aux[(1 + 2 * dL + j) * MRL_LDT];
+            const float iv = ivar[j];
+            const float t2 = (ac - mu) * (ac - mu) * iv;
+            float dkl_dmu, dkl_dls;
+            if (!a.reverse_kl) {
+              dkl_dmu = (mu - m0) * iv;
+              dkl_dls = ((sig[j] - s0) * (sig[j] + s0) - (m0 - mu) * (m0 - mu)) * iv;  // 1 - (s0^2+dm^2)/s1^2
+            } else {
+              const float i0 = 1.f / (s0 * s0);
+              dkl_dmu = (mu - m0) * i0;
+              dkl_dls = (sig[j] - s0) * (sig[j] + s0) * i0;                             // -1 + s1^2/s0^2
+            }
+            EH[j * MRL_LDT + r] = w * (ac - mu) * iv + ck * dkl_dmu;
+            GL[j * MRL_TILE + r] += w * (t2 - 1.f) + ck * dkl_dls;
+          }
+        } else if (HEAD == MRL_HEAD_CAT) {
+          const float adv = aux[0];
+          const int ai = (int)aux[1 * MRL_LDT];
+          const float pa = Hh[ai * MRL_LDT + r], p0a = aux[(2 + ai) * MRL_LDT];
+          const float w = -(pa / p0a) * adv * cs;
+          float klrow = 0.f;
+          if (a.reverse_kl)
+            for (int j = 0; j < dL; ++j) {
+              const float p = Hh[j * MRL_LDT + r];
+              klrow += p * logf(p / aux[(2 + j) * MRL_LDT]);
+            }
+          for (int j = 0; j < dL; ++j) {
+            const float p = Hh[j * MRL_LDT + r], p0 = aux[(2 + j) * MRL_LDT];
+            const float dk = a.reverse_kl ? p * (logf(p / p0) - klrow) : (p - p0);
+            EH[j * MRL_LDT + r] = w * ((j == ai ? 1.f : 0.f) - p) + ck * dk;
+          }
+        } else {
+          EH[r] = 2.f * (Hh[r] - aux[0]);   // d/dpred of (y - pred)^2
+        }
+      }
+    }
+    __syncthreads();
+    // ---- reverse sweep: layers L..2 (weights in shared memory)
+    for (int l = L; l >= 2; --l) {
+      const float* D = E + g.off_act[l] * MRL_LDT;
+      const float* Hp = H + g.off_act[l - 1] * MRL_LDT;
+      float* Ep = E + g.off_act[l - 1] * MRL_LDT;
+      const int M = g.d[l - 1], Nn = g.d[l];
+      const int n_delta = fwd_jobs(M);
+      const int n_nblk = (Nn + 15) >> 4;
+      const int n_grad = ((M + 31) >> 5) * n_nblk;
+      const int n_bias = (Nn + 7) >> 3;
+      const float* WT = img + g.off_WT[l];
+      for (int job = ln.warp; job < n_delta + n_grad + n_bias; job += NW) {
+        if (job < n_delta) {       // delta_{l-1} = (delta_l W_l^T) * act'(h_{l-1})
+          fwd_job(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, [&](int c, int r, float4 v) {
+            const float4 h = *reinterpret_cast<const float4*>(Hp + c * MRL_LDT + r);
+            v.x *= dact_from_h<ACT>(h.x); v.y *= dact_from_h<ACT>(h.y);
+            v.z *= dact_from_h<ACT>(h.z); v.w *= dact_from_h<ACT>(h.w);
+            *reinterpret_cast<float4*>(Ep + c * MRL_LDT + r) = v;
+          });
+        } else if (job < n_delta + n_grad) {
+          grad_job(job - n_delta, n_nblk, ln, Hp, M, D, Nn, G + g.off_W[l], g.ldw[l]);
+        } else {
+          bias_job(job - n_delta - n_grad, ln, D, Nn, G + g.off_b[l]);
+        }
+      }
+      __syncthreads();
+    }
+    {  // layer 1: bias gradient here, weight gradient by l1_grad_kernel from delta_1 (row-major)
+      const float* D1 = E;  // off_act[1] == 0
+      const int n1 = g.d[1];
+      for (int job = ln.warp; job < ((n1 + 7) >> 3); job += NW) bias_job(job, ln, D1, n1, G + g.off_b[1]);
+      float* out = a.D1r + (size_t)tile * MRL_TILE * g.n1p;
+      for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_MID_THREADS) {
+        const int r = i / g.n1p, c = i % g.n1p;
+        out[i] = (c < n1) ? D1[c * MRL_LDT + r] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+  if (gl_floats) {  // logstd gradient: reduce the per-timestep columns
+    for (int j = ln.warp; j < dL; j += NW) {
+      float s = GL[j * MRL_TILE + ln.lane] + GL[j * MRL_TILE + 32 + ln.lane];
+      s = warp_sum(s);
+      if (ln.lane == 0) G[g.off_pm_logstd + j] = s;
+    }
+    __syncthreads();
+  }
+  copy_f4(a.partm + (size_t)slab * g.pmid, G, g.bw_floats);
+}
+
+// =====================================================================================
+size_t mid_forward_smem(const NetGeom& g) { return ((size_t)g.bw_floats + (size_t)g.act_rows * MRL_LDT) * 4; }
+size_t mid_backward_smem(const NetGeom& g, int mode) {
+  size_t f = (size_t)g.img_floats + g.bw_floats + 2 * (size_t)g.act_rows * MRL_LDT;
+  if (mode == MRL_MODE_FVP) f += g.bw_floats;
+  if (mode == MRL_MODE_GRAD && g.head == MRL_HEAD_GAUSS) f += (size_t)g.d[g.L] * MRL_TILE;
+  return f * 4;
+}
+
+template <int HEAD, int ACT>
+static cudaError_t launch_fwd_t(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
+  const size_t sm = mid_forward_smem(g);
+  cudaError_t e = cudaFuncSetAttribute(mid_forward_kernel<HEAD, ACT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  mid_forward_kernel<HEAD, ACT><<<n_slabs, MRL_MID_THREADS, sm, st>>>(g, a);
+  return cudaGetLastError();
+}
+template <int HEAD, int ACT, int MODE>
+static cudaError_t launch_bwd_t(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  const size_t sm = mid_backward_smem(g, MODE);
+  cudaError_t e = cudaFuncSetAttribute(mid_backward_kernel<HEAD, ACT, MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  mid_backward_kernel<HEAD, ACT, MODE><<<n_slabs, MRL_MID_THREADS, sm, st>>>(g, a);
+  return cudaGetLastError();
+}
+
+#define DISPATCH_ACT(FN, HEADV, ...)                                     \
+  switch (g.act) {                                                       \
+    case MRL_ACT_TANH: return FN<HEADV, MRL_ACT_TANH>(__VA_ARGS__);      \
+    case MRL_ACT_RELU: return FN<HEADV, MRL_ACT_RELU>(__VA_ARGS__);      \
+    default: return FN<HEADV, MRL_ACT_SIGMOID>(__VA_ARGS__);             \
+  }
+
+cudaError_t launch_mid_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
+  switch (g.head) {
+    case MRL_HEAD_GAUSS: DISPATCH_ACT(launch_fwd_t, MRL_HEAD_GAUSS, g, a, n_slabs, st)
+    case MRL_HEAD_CAT: DISPATCH_ACT(launch_fwd_t, MRL_HEAD_CAT, g, a, n_slabs, st)
+    default: DISPATCH_ACT(launch_fwd_t, MRL_HEAD_VALUE, g, a, n_slabs, st)
+  }
+}
+
+template <int HEAD, int ACT>
+static cudaError_t launch_bwd_mode(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  if (a.mode == MRL_MODE_FVP) return launch_bwd_t<HEAD, ACT, MRL_MODE_FVP>(g, a, n_slabs, st);
+  return launch_bwd_t<HEAD, ACT, MRL_MODE_GRAD>(g, a, n_slabs, st);
+}
+
+cudaError_t launch_mid_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  switch (g.head) {
+    case MRL_HEAD_GAUSS: DISPATCH_ACT(launch_bwd_mode, MRL_HEAD_GAUSS, g, a, n_slabs, st)
+    case MRL_HEAD_CAT: DISPATCH_ACT(launch_bwd_mode, MRL_HEAD_CAT, g, a, n_slabs, st)
+    default: DISPATCH_ACT(launch_bwd_mode, MRL_HEAD_VALUE, g, a, n_slabs, st)
+  }
+}
