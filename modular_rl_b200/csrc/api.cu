@@ -812,7 +812,7 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   CK(cudaSetDevice(n->device));
   const NetGeom& g = n->g;
   const int P = g.P;
-  int fvp_calls = 0, loss_passes = 0;
+  int loss_passes = 0;
   n->last_valid = false;
 
   // gradient + losses at theta_old (trpo.py:94-95); the forward pass also fills the activation cache
@@ -828,14 +828,12 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   for (int it = 0; it < cfg->cg_iters; ++it) {
     RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
                       n->out64.as<double>(), st));
-    fvp_calls++;
     CKL(launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
                        n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(), st), 1);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
   RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),
                     n->out64.as<double>(), st));
-  fvp_calls++;
   CKL(launch_cg_finish(P, n->out32.as<float>(), cfg->cg_damping, cfg->max_kl, n->g32.as<float>(),
                        n->cg_x.as<double>(), n->fullstep.as<double>(), n->cgstate.as<CgState>(), st), 1);
   CK(cudaStreamSynchronize(st));   // h_scal / h_cg (first snapshot) are valid now
@@ -877,7 +875,8 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   stats[2] = before[1]; stats[3] = after[1];
   stats[4] = before[2]; stats[5] = after[2];
   if (info) {
-    info[0] = skipped; info[1] = success; info[2] = accepted; info[3] = cg_run; info[4] = fvp_calls;
+    info[0] = skipped; info[1] = success; info[2] = accepted; info[3] = cg_run;
+    info[4] = skipped ? 0 : cg_run + 1;   // Fvp evaluations the reference would make; launches after an early break are no-ops
     info[5] = loss_passes;
   }
   return 0;

@@ -18,6 +18,20 @@
 #define LOG_2PIE 2.8378770664093453f
 #define MAX_DOUT 64
 
+// g(u) = u - log1p(u) = u^2/2 - u^3/3 + ...  evaluated without the O(u) cancellation.  Both KL
+// formulas reduce to sums of g(.) of a relative deviation, which is what keeps a float32 per-row KL
+// accurate to 1e-7 RELATIVE even when kl ~ 1e-4 (mean KL is the quantity TRPO constrains).
+__device__ __forceinline__ float u_minus_log1p(float u) {
+  if (fabsf(u) < 0.2f) {
+    float p = 1.f / 12.f;
+    p = 1.f / 11.f - u * p; p = 1.f / 10.f - u * p; p = 1.f / 9.f - u * p; p = 1.f / 8.f - u * p;
+    p = 1.f / 7.f - u * p;  p = 1.f / 6.f - u * p;  p = 1.f / 5.f - u * p; p = 1.f / 4.f - u * p;
+    p = 1.f / 3.f - u * p;  p = 0.5f - u * p;
+    return u * u * p;
+  }
+  return u - log1pf(u);
+}
+
 struct Lane {
   int warp, lane, rg, cg;
   __device__ Lane() {
@@ -218,12 +232,14 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom
             const float s0 = aux[(1 + 2 * dL + j) * MRL_LDT];
             const float sg = sig[j];
             const float t = (ac - mu) / sg, t0 = (ac - m0) / s0;
-            const float lr = logsig[j] - logf(s0);           // log(sigma/sigma0)
+            const float lr = log1pf((sg - s0) / s0);         // log(sigma/sigma0)
             dl += -0.5f * (t - t0) * (t + t0) - lr;           // logp - oldlogp, term by term
             const float dm = m0 - mu;
             // log(s1/s0) + (s0^2 + dm^2)/(2 s1^2) - 1/2, with the s0~s1 cancellation taken analytically
-            if (!a.reverse_kl) kl += lr + 0.5f * ((s0 - sg) * (s0 + sg) + dm * dm) / (sg * sg);
-            else kl += -lr + 0.5f * ((sg - s0) * (sg + s0) + dm * dm) / (s0 * s0);   // KL(new || old), ppo.py:40-41
+            // = g(u) + u^2/2 + dm^2/(2 s1^2), u = (s0-s1)/s1   (reverse: roles of s0, s1 swapped, ppo.py:40-41)
+            const float den = a.reverse_kl ? s0 : sg;
+            const float u = (a.reverse_kl ? (sg - s0) : (s0 - sg)) / den;
+            kl += u_minus_log1p(u) + 0.5f * (u * u + (dm / den) * (dm / den));
             sls += logsig[j];
           }
           if (valid) {
@@ -249,7 +265,9 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom
           headbuf[j * MRL_LDT + r] = p;
           if (aux) {
             const float p0 = aux[(2 + j) * MRL_LDT];
-            kl += a.reverse_kl ? p * logf(p / p0) : p0 * logf(p0 / p);
+            // q log(q/w) = q g(v) - (w - q), v = (w-q)/q : no cancellation between the terms of the sum
+            const float q = a.reverse_kl ? p : p0, w = a.reverse_kl ? p0 : p;
+            kl += q * u_minus_log1p((w - q) / q) - (w - q);
             ent -= p * logf(p);
             if (j == ai) { pa = p; p0a = p0; }
           }
@@ -404,7 +422,7 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
             const float m0 = aux[(1 + dL + j) * MRL_LDT];
             const float s0 = aux[(1 + 2 * dL + j) * MRL_LDT];
             const float t = (ac - mu) / sig[j], t0 = (ac - m0) / s0;
-            dl += -0.5f * (t - t0) * (t + t0) - (logf(sig[j]) - logf(s0));
+            dl += -0.5f * (t - t0) * (t + t0) - log1pf((sig[j] - s0) / s0);
           }
           const float w = -expf(dl) * adv * cs;
           for (int j = 0; j < dL; ++j) {
