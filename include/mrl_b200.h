@@ -47,6 +47,14 @@ int mrl_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long mrl_launch_count(void);
 
+/* measurement hooks (bench.py): per-kernel-class CUDA-event timing on the launching stream, and the FP32
+ * FMA peak of the device.  mrl_profile_read synchronises the device; arrays have mrl_profile_kinds() entries. */
+int mrl_profile_enable(int on);
+int mrl_profile_kinds(void);
+const char* mrl_profile_kind_name(int kind);
+int mrl_profile_read(double* ms_out, long long* count_out);
+int mrl_measure_fp32_tflops(int device, double* tflops_out);
+
 /* ---------------------------------------------------------------- batch (paths, flattened)
  * Replaces the `concat([path[k] for path in paths])` host copies of trpo.py:74-77,
  * ppo.py:61-64, core.py:653-654 and the per-call numpy->Theano downcast (keras_theano_setup.py:9). */
@@ -69,6 +77,8 @@ int mrl_batch_set_vf_target(mrl_batch* b, const void* y, int dtype, int loc, voi
 /* target = mixfrac * return + (1 - mixfrac) * ypred_old (core.py:622-624) from what mrl_batch_gae and
  * mrl_net_predict_into_baseline left on the device (ypred_old == the GAE baseline: same theta) */
 int mrl_batch_mix_vf_target(mrl_batch* b, double mixfrac, void* stream);
+/* re-bind only the advantage column from the float32 advantages mrl_batch_gae left on the device */
+int mrl_batch_refresh_advantages(mrl_batch* b, void* stream);
 /* global timestep count when the batch is one shard of a data-parallel job (default: local N) */
 int mrl_batch_set_global_n(mrl_batch* b, long long n_global);
 long long mrl_batch_size(const mrl_batch* b);

@@ -35,6 +35,12 @@ _SIGS = {
     "mrl_last_error": (C.c_char_p, []),
     "mrl_version": (_I, []),
     "mrl_launch_count": (_LL, []),
+    "mrl_profile_enable": (_I, [_I]),
+    "mrl_profile_kinds": (_I, []),
+    "mrl_profile_kind_name": (C.c_char_p, [_I]),
+    "mrl_profile_read": (_I, [_P, _P]),
+    "mrl_measure_fp32_tflops": (_I, [_I, _P]),
+    "mrl_batch_refresh_advantages": (_I, [_P, _P]),
     "mrl_batch_create": (_I, [C.POINTER(_P), _I, _I, _I]),
     "mrl_batch_destroy": (_I, [_P]),
     "mrl_batch_set_obs": (_I, [_P, _P, _I, _LL, _LL, _I, _P]),

@@ -40,6 +40,62 @@ static int fail(const char* fmt, ...) {
     if (_r) return _r;     \
   } while (0)
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline)
+enum { PK_L1F = 0, PK_MIDF, PK_MIDB_GRAD, PK_MIDB_FVP, PK_L1G, PK_REDUCE, PK_CG, PK_GAE, PK_PACK, PK_COUNT };
+static const char* kPkNames[PK_COUNT] = {"l1_forward", "mid_forward", "mid_backward_grad", "mid_backward_fvp",
+                                         "l1_grad",    "reduce",      "cg_vector",         "gae",
+                                         "pack_params"};
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<int> kinds;
+  double ms[PK_COUNT] = {0};
+  long long cnt[PK_COUNT] = {0};
+};
+static Prof g_prof;
+static void prof_mark(int kind, cudaStream_t st, bool begin) {
+  if (!g_prof.on) return;
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.pool.push_back(e);
+  }
+  cudaEventRecord(g_prof.pool[g_prof.used++], st);
+  if (begin) g_prof.kinds.push_back(kind);
+}
+#define CKP(kind, call, nk)          \
+  do {                               \
+    prof_mark(kind, st, true);       \
+    CKL(call, nk);                   \
+    prof_mark(kind, st, false);      \
+  } while (0)
+
+extern "C" int mrl_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.kinds.clear();
+  for (int k = 0; k < PK_COUNT; ++k) { g_prof.ms[k] = 0; g_prof.cnt[k] = 0; }
+  return 0;
+}
+extern "C" int mrl_profile_kinds(void) { return PK_COUNT; }
+extern "C" const char* mrl_profile_kind_name(int k) { return (k >= 0 && k < PK_COUNT) ? kPkNames[k] : ""; }
+// Synchronises the device, folds all recorded intervals into the per-kind totals and returns them.
+extern "C" int mrl_profile_read(double* ms_out, long long* count_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 1; }
+  for (size_t i = 0; i < g_prof.kinds.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]);
+    g_prof.ms[g_prof.kinds[i]] += ms;
+    g_prof.cnt[g_prof.kinds[i]] += 1;
+  }
+  g_prof.used = 0;
+  g_prof.kinds.clear();
+  for (int k = 0; k < PK_COUNT; ++k) { ms_out[k] = g_prof.ms[k]; count_out[k] = g_prof.cnt[k]; }
+  return 0;
+}
+
 extern "C" const char* mrl_last_error(void) { return g_err.c_str(); }
 int mrl_set_error(const char* msg) { g_err = msg; return 1; }   // used by comm.cu
 extern "C" int mrl_version(void) { return 100; }
@@ -214,6 +270,57 @@ extern "C" int mrl_batch_set_policy_inputs(mrl_batch* b, int head, int dout, con
   return 0;
 }
 
+// advantage row of the policy side inputs <- the float32 advantages mrl_batch_gae left on the device
+extern "C" int mrl_batch_refresh_advantages(mrl_batch* b, void* stream) {
+  if (!b || !b->has_adv32 || b->pol_head < 0) return fail("mrl_batch_refresh_advantages: needs mrl_batch_gae and bound policy inputs");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(b->device));
+  CKL(launch_pack_tiles(b->adv32.p, MRL_F32, 1, 1, 1, b->N, b->aux_pol.as<float>(), b->naux_pol, 0, b->n_tiles, st), 1);
+  return 0;
+}
+
+// FP32 FMA throughput of this GPU (the pipe the SIMT GEMMs are bound by), for the roofline report.
+__global__ void fma_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-6f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+        a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999999f, c = 1e-7f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+extern "C" int mrl_measure_fp32_tflops(int device, double* tflops_out) {
+  if (!tflops_out) return fail("mrl_measure_fp32_tflops: null out");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  float* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, 0);
+    fma_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1, 0);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  g_launches += 5;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
+  return 0;
+}
+
 __global__ void mix_target_kernel(const double* __restrict__ ret, const double* __restrict__ base, double mix,
                                   long long N, float* __restrict__ aux) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,7 +380,7 @@ static int gae_impl(const void* reward_dev, int rdt, const void* base_dev, int b
                     double* adv, cudaStream_t st) {
   if (rdt != MRL_F32 && rdt != MRL_F64) return fail("reward must be f32/f64");
   if (bdt != MRL_F32 && bdt != MRL_F64) return fail("baseline must be f32/f64");
-  CKL(launch_gae(reward_dev, rdt == MRL_F64, base_dev, bdt == MRL_F64, off_dev, term_dev, n_paths, N, gamma, lam,
+  CKP(PK_GAE, launch_gae(reward_dev, rdt == MRL_F64, base_dev, bdt == MRL_F64, off_dev, term_dev, n_paths, N, gamma, lam,
                  ret, adv, st), 1);
   return 0;
 }
@@ -519,7 +626,7 @@ void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st) {
 }
 
 static int repack(mrl_net* n, cudaStream_t st) {
-  CKL(launch_pack_params(n->g, n->theta.as<float>(), n->W1p.as<float>(), n->img.as<float>(), st), 1);
+  CKP(PK_PACK, launch_pack_params(n->g, n->theta.as<float>(), n->W1p.as<float>(), n->img.as<float>(), st), 1);
   n->params_version++;
   return 0;
 }
@@ -598,7 +705,7 @@ static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_ca
   RET(reserve_ws(n, b, pl));
   // the batch tile has b->d0p feature rows; the net consumes the first g.d0p of them
   NetGeom gl = g;
-  CKL(launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+  CKP(PK_L1F, launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
   MidFwdArgs a;
   a.img = n->img.as<float>();
   a.Zt = n->Z1.as<float>();
@@ -610,7 +717,7 @@ static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_ca
   a.n_tiles = b->n_tiles;
   a.slab_tiles = pl.slab_tiles;
   a.reverse_kl = reverse_kl;
-  CKL(launch_mid_forward(g, a, pl.n_slabs, st), 1);
+  CKP(PK_MIDF, launch_mid_forward(g, a, pl.n_slabs, st), 1);
   if (want_losses) {
     CKL(launch_reduce_losses(n->loss_part.as<double>(), pl.n_slabs, 1.0 / (double)b->Nglobal, n->scal.as<double>(), st), 1);
     if (world_of(n) > 1) RET(mrl_comm_allreduce_f64(n->comm, n->scal.as<double>(), 4, st));
@@ -638,8 +745,8 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.imgv = nullptr;
   a.Zt = nullptr;
   if (mode == MRL_MODE_FVP) {
-    CKL(launch_pack_params(g, v_dev, n->V1p.as<float>(), n->imgv.as<float>(), st), 1);
-    CKL(launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+    CKP(PK_PACK, launch_pack_params(g, v_dev, n->V1p.as<float>(), n->imgv.as<float>(), st), 1);
+    CKP(PK_L1F, launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
     a.imgv = n->imgv.as<float>();
     a.Zt = n->Z1.as<float>();
   }
@@ -653,13 +760,13 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.slab_tiles = pl.slab_tiles;
   a.mode = mode;
   a.reverse_kl = reverse_kl;
-  CKL(launch_mid_backward(g, a, pl.n_slabs, st), 1);
-  CKL(launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
+  CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
+  CKP(PK_L1G, launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
                      b->n_tiles, pl.n_slabs, st), 1);
   const int world = world_of(n);
   // terms that are not sums over timesteps are divided by `world` so that the all-reduce restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;
-  CKL(launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
+  CKP(PK_REDUCE, launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
                              mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32, out64, st), 1);
   if (world > 1) {
@@ -828,7 +935,7 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   for (int it = 0; it < cfg->cg_iters; ++it) {
     RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
                       n->out64.as<double>(), st));
-    CKL(launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
+    CKP(PK_CG, launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
                        n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(), st), 1);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);

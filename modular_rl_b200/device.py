@@ -124,15 +124,36 @@ class DeviceBatch:
         return out
 
     def gae(self, reward, baseline, gamma, lam, standardize=True, comm: Optional[Comm] = None,
-            want_outputs=True, stream=None):
-        """-> (returns, advantages) float64 host arrays (or None, None)."""
+            want_outputs=True, out=None, stream=None):
+        """compute_advantage on the device.  reward/baseline: host arrays or CUDA tensors (both in the same
+        place); baseline=None uses what predict_into_baseline left.  Returns (returns, advantages) as
+        float64 arrays living where the inputs live (or (None, None) when want_outputs is False and no
+        `out=(ret, adv)` buffers are given)."""
         kr, pr, dr, lr, _ = _arg(reward, _F)
         kb, pb, db, lb, _ = _arg(baseline, _F)
-        ret = np.empty(self.N, np.float64) if want_outputs else None
-        adv = np.empty(self.N, np.float64) if want_outputs else None
+        assert baseline is None or lb == lr, "reward and baseline must live in the same place"
+        ret = adv = None
+        pret = padv = None
+        if out is not None:
+            ret, adv = out
+        elif want_outputs:
+            if lr == L.HOST:
+                ret, adv = np.empty(self.N, np.float64), np.empty(self.N, np.float64)
+            else:
+                import torch
+                ret = torch.empty(self.N, dtype=torch.float64, device=reward.device)
+                adv = torch.empty_like(ret)
+        if ret is not None:
+            _, pret, _, lo, _ = _arg(ret)
+            _, padv, _, _, _ = _arg(adv)
+            assert lo == lr, "output buffers must live where the inputs live"
         L.check(L.lib().mrl_batch_gae(self._h, pr, dr, pb, db, float(gamma), float(lam), int(standardize),
-                                      comm._h if comm else None, L.ptr(ret), L.ptr(adv), L.HOST, stream))
+                                      comm._h if comm else None, pret, padv, lr, stream))
         return ret, adv
+
+    def refresh_advantages(self, stream=None):
+        L.check(L.lib().mrl_batch_refresh_advantages(self._h, stream))
+        return self
 
 
 class DeviceNet:
