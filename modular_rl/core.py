@@ -1,0 +1,3 @@
+from modular_rl_b200.core import *  # noqa: F401,F403
+from modular_rl_b200 import core as _impl
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith('__')})

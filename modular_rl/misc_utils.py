@@ -1,0 +1,3 @@
+from modular_rl_b200.misc_utils import *  # noqa: F401,F403
+from modular_rl_b200 import misc_utils as _impl
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith('__')})

@@ -871,13 +871,14 @@ extern "C" int mrl_net_ppo_lossgrad(mrl_net* n, mrl_batch* b, double kl_coeff, d
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(n->device));
   // forward: surr/kl/ent; kl(new||old) needs its own sum when reverse_kl: handled inside the forward by aux order
-  RET(pass_forward(n, b, true, true, nullptr, st, reverse_kl));
+  RET(pass_forward(n, b, true, gout != nullptr, nullptr, st, reverse_kl));
   double* scal = n->scal.as<double>();
   // scal[0] holds +mean(rho*adv): the coefficient kernel expects surr = -that
   negate_first<<<1, 1, 0, st>>>(scal);
   CKL(cudaGetLastError(), 1);
   CKL(launch_ppo_coef(scal, kl_coeff, kl_cutoff, scal + 8, scal + 10, st), 1);
-  RET(pass_backward(n, b, MRL_MODE_GRAD, scal + 8, reverse_kl, nullptr, 0.0, nullptr, n->out64.as<double>(), st));
+  if (gout)   // gout == NULL: losses / pensurr only (compute_losses, ppo.py:57)
+    RET(pass_backward(n, b, MRL_MODE_GRAD, scal + 8, reverse_kl, nullptr, 0.0, nullptr, n->out64.as<double>(), st));
   RET(d2h_sync(n->h_scal, n->scal.p, 16 * 8, st));
   if (losses) { losses[0] = n->h_scal[0]; losses[1] = n->h_scal[1]; losses[2] = n->h_scal[2]; }
   if (pensurr) *pensurr = n->h_scal[10];

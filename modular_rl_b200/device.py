@@ -218,9 +218,10 @@ class DeviceNet:
         L.check(L.lib().mrl_net_fvp(self._h, batch._h, L.ptr(v), L.ptr(out), L.HOST, stream))
         return out
 
-    def ppo_lossgrad(self, batch: DeviceBatch, kl_coeff, kl_cutoff, reverse_kl=False, stream=None):
+    def ppo_lossgrad(self, batch: DeviceBatch, kl_coeff, kl_cutoff, reverse_kl=False, want_grad=True,
+                     stream=None):
         pen = C.c_double()
-        g = np.empty(self.P, np.float64)
+        g = np.empty(self.P, np.float64) if want_grad else None
         ls = np.zeros(3, np.float64)
         L.check(L.lib().mrl_net_ppo_lossgrad(self._h, batch._h, float(kl_coeff), float(kl_cutoff),
                                              int(bool(reverse_kl)), C.byref(pen), L.ptr(g), L.ptr(ls), stream))

@@ -1,0 +1,118 @@
+"""PPO with a penalised KL and L-BFGS (ppo.py:3-112) on the B200 path.
+
+pensurr = surr + kl_coeff*kl + 1000*(kl > 2*kl_target)*(kl - 2*kl_target)^2 with
+surr = -(1/N) sum (p/oldp)*adv (likelihood ratio, ppo.py:35-36,47).  L-BFGS-B stays scipy's routine
+on the host - the one the reference calls (ppo.py:85) - and each of its evaluations is one
+set_params + fused forward / reverse sweep on the device (mrl_net_ppo_lossgrad), where the chain-rule
+coefficient of the KL term is computed from the batch-wide KL without a host round trip.
+
+PpoSgdUpdater (ppo.py:115-258) is out of this path's scope.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import scipy.optimize
+
+from . import _lib as L
+from .core import EzFlat, concat
+from .device import DeviceBatch
+from .misc_utils import EzPickle, update_default_config, zipsame
+
+
+class PpoLbfgsUpdater(EzFlat, EzPickle):
+    options = [
+        ("kl_target", float, 1e-2, "Desired KL divergence between old and new policy"),
+        ("maxiter", int, 25, "Maximum number of iterations"),
+        ("reverse_kl", int, 0, "kl[new, old] instead of kl[old, new]"),
+        ("do_split", int, 0, "Do train/test split on batches"),
+    ]
+
+    def __init__(self, stochpol, usercfg):
+        EzPickle.__init__(self, stochpol, usercfg)
+        cfg = update_default_config(self.options, usercfg)
+        print("PPOUpdater", cfg)
+        self.stochpol = stochpol
+        self.cfg = cfg
+        self.kl_coeff = 1.0
+        EzFlat.__init__(self, stochpol.net)
+        self.loss_names = ["surr", "kl", "ent"]
+        self._train = DeviceBatch(stochpol.dims[0], with_time_feature=True)
+        self._test = DeviceBatch(stochpol.dims[0], with_time_feature=True)
+
+    def _bind(self, batch, ob, act, adv, prob):
+        batch.set_obs(np.asarray(ob).reshape(len(ob), -1))
+        batch.set_policy_inputs(self.stochpol.probtype.head, self.stochpol.dims[-1], act, adv, prob)
+        return batch
+
+    def _losses(self, batch):
+        """[surr, kl, ent] with the configured KL direction (ppo.py:39-43,57)."""
+        _, _, ls = self.stochpol.net.ppo_lossgrad(batch, 0.0, 1e300, self.cfg["reverse_kl"], want_grad=False)
+        return ls
+
+    def __call__(self, paths):
+        cfg = self.cfg
+        net = self.stochpol.net
+        prob_np = concat([path["prob"] for path in paths])
+        ob_no = concat([path["observation"] for path in paths])
+        action_na = concat([path["action"] for path in paths])
+        advantage_n = concat([path["advantage"] for path in paths])
+
+        N = ob_no.shape[0]
+        train_stop = int(0.75 * N) if cfg["do_split"] else N
+        tr, te = slice(0, train_stop), slice(train_stop, None)
+        train = self._bind(self._train, ob_no[tr], action_na[tr], advantage_n[tr], prob_np[tr])
+        kl_cutoff = cfg["kl_target"] * 2.0
+
+        thprev = self.get_params_flat().astype(np.float64)
+
+        def lossandgrad(th):
+            self.set_params_flat(th)
+            l, g, _ = net.ppo_lossgrad(train, self.kl_coeff, kl_cutoff, cfg["reverse_kl"])
+            return (l, g)
+
+        train_losses_before = self._losses(train)
+        if cfg["do_split"]:
+            test = self._bind(self._test, ob_no[te], action_na[te], advantage_n[te], prob_np[te])
+            test_losses_before = self._losses(test)
+
+        theta, _, opt_info = scipy.optimize.fmin_l_bfgs_b(lossandgrad, thprev, maxiter=cfg["maxiter"])
+        del opt_info['grad']
+        print(opt_info)
+        self.set_params_flat(theta)
+        train_losses_after = self._losses(train)
+        if cfg["do_split"]:
+            test_losses_after = self._losses(test)
+        klafter = train_losses_after[self.loss_names.index("kl")]
+        if klafter > 1.3 * cfg["kl_target"]:
+            self.kl_coeff *= 1.5
+            print("Got KL=%.3f (target %.3f). Increasing penalty coeff => %.3f." % (klafter, cfg["kl_target"], self.kl_coeff))
+        elif klafter < 0.7 * cfg["kl_target"]:
+            self.kl_coeff /= 1.5
+            print("Got KL=%.3f (target %.3f). Decreasing penalty coeff => %.3f." % (klafter, cfg["kl_target"], self.kl_coeff))
+        else:
+            print("KL=%.3f is close enough to target %.3f." % (klafter, cfg["kl_target"]))
+        info = OrderedDict()
+        for (name, lossbefore, lossafter) in zipsame(self.loss_names, train_losses_before, train_losses_after):
+            info[name + "_before"] = lossbefore
+            info[name + "_after"] = lossafter
+            info[name + "_change"] = lossafter - lossbefore
+        if cfg["do_split"]:
+            for (name, lossbefore, lossafter) in zipsame(self.loss_names, test_losses_before, test_losses_after):
+                info["test_" + name + "_before"] = lossbefore
+                info["test_" + name + "_after"] = lossafter
+                info["test_" + name + "_change"] = lossafter - lossbefore
+        return info
+
+
+class PpoSgdUpdater(object):
+    options = [
+        ("kl_target", float, 1e-2, ""),
+        ("epochs", int, 10, ""),
+        ("stepsize", float, 1e-3, ""),
+        ("do_split", int, 0, "do train/test split"),
+        ("kl_cutoff_coeff", float, 1000.0, ""),
+    ]
+
+    def __init__(self, stochpol, usercfg):
+        raise NotImplementedError("PpoSgdUpdater is outside the accelerated path (SURVEY 8f); "
+                                  "use TrpoUpdater or PpoLbfgsUpdater")

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""This script runs a policy gradient algorithm - same flags as the reference's run_pg.py
+(GENERAL_OPTIONS + --env --agent --plot + the agent's own option table, parsed in two passes,
+run_pg.py:79-102), with the policy update executed by the B200 library.
+
+  python run_pg.py --env CartPole-v0 --agent modular_rl.agentzoo.TrpoAgent --n_iter 20 --timesteps_per_batch 5000
+"""
+import argparse
+import os
+import pickle
+import shutil
+import sys
+
+import numpy as np
+
+from modular_rl import *  # noqa: F401,F403
+from modular_rl_b200.envs import make
+
+try:
+    from tabulate import tabulate
+except ImportError:  # pragma: no cover
+    def tabulate(rows):
+        return "\n".join("%-24s %s" % (k, v) for k, v in rows)
+
+
+def main():
+    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    update_argument_parser(parser, GENERAL_OPTIONS)
+    parser.add_argument("--env", default="CartPole-v0")
+    parser.add_argument("--agent", default="modular_rl.agentzoo.TrpoAgent")
+    parser.add_argument("--plot", action="store_true")
+    args, _ = parser.parse_known_args([arg for arg in sys.argv[1:] if arg not in ('-h', '--help')])
+    env = make(args.env)
+    env_spec = env.spec
+    mondir = args.outfile + ".dir"
+    if os.path.exists(mondir):
+        shutil.rmtree(mondir)
+    os.makedirs(mondir)
+    agent_ctor = get_agent_cls(args.agent)
+    update_argument_parser(parser, agent_ctor.options)
+    args = parser.parse_args()
+    if args.timestep_limit == 0:
+        args.timestep_limit = env_spec.max_episode_steps
+    cfg = args.__dict__
+    np.random.seed(args.seed)
+    agent = agent_ctor(env.observation_space, env.action_space, cfg)
+    if args.use_hdf:
+        hdf, diagnostics = prepare_h5_file(args)
+
+    counter = [0]
+
+    def callback(stats):
+        counter[0] += 1
+        print("*********** Iteration %i ****************" % counter[0])
+        print(tabulate([(k, v) for k, v in stats.items() if np.asarray(v).size == 1]))
+        if args.use_hdf:
+            for (stat, val) in stats.items():
+                if np.asarray(val).ndim == 0:
+                    diagnostics[stat].append(val)
+                else:
+                    assert val.ndim == 1
+                    diagnostics[stat].extend(val)
+            if args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
+                hdf['/agent_snapshots/%0.4i' % counter[0]] = np.array(pickle.dumps(agent, -1))
+        if args.plot:
+            animate_rollout(env, agent, min(500, args.timestep_limit))
+
+    run_policy_gradient_algorithm(env, agent, callback=callback, usercfg=cfg)
+
+    if args.use_hdf:
+        hdf['env_id'] = env_spec.id
+    env.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+"""The reference-facing Python API (agentzoo / updaters / compute_advantage / NnVf / ZFilter /
+run_pg flow) on the GPU, checked against the oracle on the same paths.  These read like the tests
+the reference would have for TrpoUpdater / compute_advantage: build `paths`, call the operator,
+compare the returned dict / the in-place path entries."""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from conftest import relerr  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _make_paths(rng, n_paths, d0, policy, tmax=60):
+    paths = []
+    for i in range(n_paths):
+        T = int(rng.integers(1, tmax + 1))
+        ob = np.clip(rng.standard_normal((T, d0)), -5, 5)          # float64, as the ZFilter emits
+        prob = policy._act_prob(ob)
+        np.random.seed(100 + i)
+        act = policy.probtype.sample(prob)
+        paths.append(dict(observation=ob, action=act, prob=prob, reward=rng.standard_normal(T),
+                          terminated=bool(rng.random() < 0.7)))
+    return paths
+
+
+def _oracle_spec(policy):
+    from oracle import policy_math as pm
+    from modular_rl_b200.core import DiagGauss
+    head = pm.GAUSS if isinstance(policy.probtype, DiagGauss) else pm.CAT
+    return pm.NetSpec(tuple(policy.dims), head)
+
+
+@pytest.mark.parametrize("kind", ["box", "discrete"])
+def test_compute_advantage_fit_and_trpo_updater(kind):
+    from modular_rl_b200 import agentzoo, core, spaces
+    from oracle import advantage as oadv, natgrad, policy_math as pm, valuefn
+    np.random.seed(0)
+    rng = np.random.default_rng(0)
+    ob_space = spaces.Box(-np.ones(6), np.ones(6))
+    ac_space = spaces.Box(-np.ones(2), np.ones(2)) if kind == "box" else spaces.Discrete(3)
+    cfg = dict(hid_sizes=[16, 8], timestep_limit=60, cg_damping=0.1, max_kl=0.01, gamma=0.98, lam=0.95)
+    agent = agentzoo.TrpoAgent(ob_space, ac_space, cfg)
+    assert {o[0] for o in agent.options} >= {"cg_damping", "max_kl", "hid_sizes", "gamma", "lam", "filter"}
+    paths = _make_paths(rng, 40, 6, agent.policy)
+    opaths = copy.deepcopy(paths)
+
+    # ---- compute_advantage (core.py:63-105), in place
+    vf_theta = agent.baseline.reg.net.get_params()
+    vspec = pm.NetSpec(tuple(agent.baseline.reg.net.dims), pm.VALUE)
+    opredict = lambda p: valuefn.vf_forward(vf_theta, vspec, valuefn.preproc(p["observation"], 60),
+                                            np.float64)[:, 0].astype(np.float32)
+    core.compute_advantage(agent.baseline, paths, 0.98, 0.95)
+    oadv.compute_advantage(opredict, opaths, 0.98, 0.95)
+    for p, o in zip(paths, opaths):
+        assert p["return"].dtype == np.float64 and p["advantage"].shape == o["advantage"].shape
+        assert np.allclose(p["return"], o["return"], rtol=1e-12, atol=1e-12)
+        assert np.allclose(p["baseline"], o["baseline"], rtol=1e-5, atol=1e-6)
+    assert relerr(np.concatenate([p["advantage"] for p in paths]),
+                  np.concatenate([o["advantage"] for o in opaths])) < 1e-5
+
+    # ---- baseline.fit (core.py:652-657 -> 619-637 -> 674-697)
+    for p, o in zip(paths, opaths):
+        o["advantage"], o["return"], o["baseline"] = p["advantage"], p["return"], p["baseline"]
+    vstats = agent.baseline.fit(paths)
+    x = np.concatenate([valuefn.preproc(o["observation"], 60) for o in opaths])
+    y = np.concatenate([o["return"] for o in opaths]).reshape(-1, 1)
+    ostats, oth, _ = valuefn.regression_fit(vf_theta, vspec, x, y, mixfrac=0.1, maxiter=25)
+    assert list(vstats)[:6] == ["loss_before", "loss_after", "mse_before", "mse_after", "l2_before", "l2_after"]
+    for k in ("loss_before", "mse_before", "l2_before", "TargStdev", "PredStdevBefore", "EV_before"):
+        assert np.isclose(vstats[k], ostats[k], rtol=1e-4, atol=1e-6), (k, vstats[k], ostats[k])
+    assert vstats["loss_after"] < vstats["loss_before"]
+    assert np.isclose(vstats["loss_after"], ostats["loss_after"], rtol=2e-2)     # L-BFGS path on float32 vs float64
+
+    # ---- updater(paths) (trpo.py:72-140)
+    theta = agent.policy.get_flat()
+    spec = _oracle_spec(agent.policy)
+    cat = lambda k: np.concatenate([o[k] for o in opaths])
+    out = agent.updater(paths)
+    ostats, oinfo = natgrad.trpo_update(theta, spec, cat("observation"), cat("action"), cat("advantage"),
+                                        cat("prob"), 0.1, 0.01)
+    assert list(out) == ["surr_before", "surr_after", "kl_before", "kl_after", "ent_before", "ent_after"]
+    for k in out:
+        assert np.isclose(out[k], ostats[k], rtol=1e-4, atol=1e-6), (k, out[k], ostats[k])
+    assert relerr(agent.policy.get_flat(), oinfo["theta_new"]) < 1e-5
+    assert agent.updater.last_info["success"] == int(oinfo["success"])
+
+
+def test_ppo_lbfgs_updater_matches_oracle():
+    from modular_rl_b200 import agentzoo, spaces
+    from oracle import ppo_penalty
+    np.random.seed(1)
+    rng = np.random.default_rng(1)
+    ob_space = spaces.Box(-np.ones(5), np.ones(5))
+    agent = agentzoo.PpoLbfgsAgent(ob_space, spaces.Box(-np.ones(2), np.ones(2)),
+                                   dict(hid_sizes=[12, 12], timestep_limit=50, maxiter=10))
+    paths = _make_paths(rng, 30, 5, agent.policy, tmax=50)
+    adv = rng.standard_normal(sum(len(p["reward"]) for p in paths))
+    adv = (adv - adv.mean()) / adv.std()
+    k = 0
+    for p in paths:
+        p["advantage"] = adv[k:k + len(p["reward"])]
+        k += len(p["reward"])
+    theta = agent.policy.get_flat()
+    spec = _oracle_spec(agent.policy)
+    cat = lambda key: np.concatenate([p[key] for p in paths])
+    info = agent.updater(paths)
+    oinfo, oth, oklc, _ = ppo_penalty.ppo_lbfgs_update(theta, spec, cat("observation"), cat("action"),
+                                                       cat("advantage"), cat("prob"), maxiter=10)
+    assert set(info) == set(oinfo)
+    for key in ("surr_before", "kl_before", "ent_before"):
+        assert np.isclose(info[key], oinfo[key], rtol=1e-4, atol=1e-6)
+    assert info["surr_after"] < info["surr_before"]
+    assert np.isclose(info["surr_after"], oinfo["surr_after"], rtol=5e-2, atol=1e-3)   # optimiser path, f32 vs f64
+    assert agent.updater.kl_coeff == oklc
+
+
+def test_discount_and_filter_batch(golden):
+    from modular_rl_b200.filters import ZFilter
+    from modular_rl_b200.misc_utils import discount
+    y = discount(golden["disc_kat_x"], 0.99)                     # x.py:762 KAT through the scan kernel
+    assert np.allclose(y, golden["disc_kat_y"], rtol=1e-14)
+    for i in range(4):
+        assert np.allclose(discount(golden[f"disc{i}_x"], float(golden[f"disc{i}_g"])), golden[f"disc{i}_y"],
+                           rtol=1e-12, atol=1e-13)
+    assert np.allclose(discount(golden["disc2d_x"], 0.9), golden["disc2d_y"], rtol=1e-12, atol=1e-13)
+    X = golden["rs_x"]
+    a, b = ZFilter((3,), clip=5), ZFilter((3,), clip=5)
+    ya = np.array([a(x) for x in X])
+    yb = np.concatenate([b.filter_batch(X[:13]), np.array([b(x) for x in X[13:20]]), b.filter_batch(X[20:])])
+    assert np.allclose(ya, yb, rtol=1e-12, atol=1e-12) and a.rs.n == b.rs.n
+    assert np.allclose(a.rs.mean, b.rs.mean, rtol=1e-13) and np.allclose(a.rs.var, b.rs.var, rtol=1e-12)
+
+
+def test_run_pg_cartpole_learns():
+    """BASELINE config 1: CartPole-v0 TrpoAgent through run_pg.py's own flags; a functional check
+    (mean episode reward rises), not a throughput number."""
+    cmd = [sys.executable, os.path.join(ROOT, "run_pg.py"), "--env", "CartPole-v0", "--agent",
+           "modular_rl.agentzoo.TrpoAgent", "--n_iter", "12", "--timesteps_per_batch", "2000", "--seed", "0",
+           "--cg_damping", "0.1", "--lam", "0.97", "--outfile", "/tmp/mrl_test_a.h5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rews = [float(ln.split()[-1]) for ln in out.stdout.splitlines() if ln.startswith("EpRewMean")]
+    assert len(rews) == 12
+    assert max(rews[-3:]) > 2.0 * rews[0], rews
+    kls = [float(ln.split()[-1]) for ln in out.stdout.splitlines() if ln.startswith("pol_kl_after")]
+    assert all(0 < k < 0.03 for k in kls), kls
+
+
+def test_coverage_smoke_pendulum():
+    """coverage.sh:7 of the reference: one TRPO iteration on Pendulum with tiny settings."""
+    cmd = [sys.executable, os.path.join(ROOT, "run_pg.py"), "--snapshot_every=20", "--n_iter=1", "--cg_damping=0.1",
+           "--timesteps_per_batch=5", "--lam=0.97", "--agent=modular_rl.agentzoo.TrpoAgent", "--max_kl=0.01",
+           "--env=Pendulum", "--gamma=0.98", "--hid_sizes=10,5", "--outfile", "/tmp/mrl_test_b.h5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "pol_surr_after" in out.stdout and "vf_EV_after" in out.stdout
