@@ -88,7 +88,7 @@ def test_compute_advantage_fit_and_trpo_updater(kind):
     assert list(out) == ["surr_before", "surr_after", "kl_before", "kl_after", "ent_before", "ent_after"]
     for k in out:
         assert np.isclose(out[k], ostats[k], rtol=1e-4, atol=1e-6), (k, out[k], ostats[k])
-    assert relerr(agent.policy.get_flat(), oinfo["theta_new"]) < 1e-5
+    assert relerr(agent.policy.get_flat(), oinfo["theta_new"]) < 5e-5   # ~1200 timesteps: CG amplifies f32 rounding of the Fvp
     assert agent.updater.last_info["success"] == int(oinfo["success"])
 
 
