@@ -161,3 +161,15 @@ def test_coverage_smoke_pendulum():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "pol_surr_after" in out.stdout and "vf_EV_after" in out.stdout
+
+
+def test_multi_gpu_parity_two_ranks():
+    """Sharded batch over 2 GPUs == full batch (skipped on a 1-GPU box; the CPU-side algebra is
+    covered by tests/test_host_logic.py with gloo)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, (out.stdout[-3000:], out.stderr[-3000:])
