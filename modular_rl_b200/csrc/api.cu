@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -134,7 +135,7 @@ struct mrl_batch {
   unsigned long long version = 0;
   int pol_head = -1, pol_dout = 0, naux_pol = 0;
   bool has_baseline = false, has_adv32 = false, has_ret = false;
-  DevBuf Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
+  DevBuf XA, Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
       gather;
 };
 
@@ -165,7 +166,7 @@ extern "C" int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int wit
 extern "C" int mrl_batch_destroy(mrl_batch* b) {
   if (!b) return 0;
   cudaSetDevice(b->device);
-  DevBuf* bufs[] = {&b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
+  DevBuf* bufs[] = {&b->XA, &b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
                     &b->stage2, &b->baseline, &b->ret, &b->adv, &b->adv32, &b->stats, &b->gather};
   for (DevBuf* d : bufs) d->release();
   delete b;
@@ -198,6 +199,9 @@ extern "C" int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long l
   CKL(launch_pack_tiles(src, dtype, ld, b->ob_dim, b->d0p, N, b->Xt.as<float>(), b->d0p, 0, b->n_tiles, st), 1);
   CKL(launch_pack_rows(src, dtype, ld, b->ob_dim, N, b->Xr.as<float>(), b->d0r, (long long)b->n_tiles * MRL_TILE,
                        st), 1);
+  const long long n_mtiles = (b->n_tiles + 1) / 2;
+  CK(b->XA.reserve(l1tc_xa_floats(b->d0p / 8, n_mtiles) * 4));
+  CKL(launch_pack_xa(src, dtype, ld, b->ob_dim, N, b->XA.as<float>(), b->d0p / 8, n_mtiles, st), 1);
   return 0;
 }
 
@@ -224,7 +228,7 @@ extern "C" int mrl_batch_set_paths(mrl_batch* b, const long long* offsets, const
   if (b->with_time) {
     if (!(timestep_limit > 0)) return fail("mrl_batch_set_paths: timestep_limit must be > 0");
     CKL(launch_time_feature(b->offsets.as<long long>(), n_paths, b->N, timestep_limit, b->Xt.as<float>(), b->d0p,
-                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), st), 1);
+                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), b->XA.as<float>(), b->d0p / 8, st), 1);
   }
   return 0;
 }
@@ -541,7 +545,7 @@ extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, 
 struct mrl_net {
   int device = 0;
   NetGeom g;
-  DevBuf theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
+  DevBuf WBt, WBv, theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
       out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, scal, headout, stage;
   unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
   const mrl_batch* cache_batch = nullptr;
@@ -581,6 +585,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   R(n->theta, P * 4); R(n->theta_prev, P * 4); R(n->theta_trial, P * 4); R(n->vflat, P * 4);
   R(n->W1p, (size_t)n->g.d0p * n->g.n1p * 4); R(n->V1p, (size_t)n->g.d0p * n->g.n1p * 4);
   R(n->img, (size_t)n->g.img_floats * 4); R(n->imgv, (size_t)n->g.img_floats * 4);
+  R(n->WBt, l1tc_wb_floats(n->g) * 4); R(n->WBv, l1tc_wb_floats(n->g) * 4);
   R(n->out32, P * 4); R(n->out64, P * 8); R(n->g32, P * 4);
   R(n->cg_b, P * 8); R(n->cg_x, P * 8); R(n->cg_r, P * 8); R(n->cg_p, P * 8);
   R(n->p32, P * 4); R(n->x32, P * 4); R(n->fullstep, P * 8);
@@ -599,7 +604,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
+  DevBuf* bufs[] = {&n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->D1r, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->scal,
                     &n->headout, &n->stage};
@@ -627,6 +632,7 @@ void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st) {
 
 static int repack(mrl_net* n, cudaStream_t st) {
   CKP(PK_PACK, launch_pack_params(n->g, n->theta.as<float>(), n->W1p.as<float>(), n->img.as<float>(), st), 1);
+  CKP(PK_PACK, launch_pack_wb(n->g, n->theta.as<float>(), n->WBt.as<float>(), st), 1);
   n->params_version++;
   return 0;
 }
@@ -654,6 +660,13 @@ extern "C" int mrl_net_get_params(mrl_net* n, float* theta, int loc, void* strea
   CK(cudaMemcpyAsync(theta, n->theta.p, (size_t)n->g.P * 4, loc == MRL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (loc == MRL_HOST) CK(cudaStreamSynchronize(st));
   return 0;
+}
+
+// debugging aid only: MRL_L1_SIMT=1 routes layer 1 through the FP32 SIMT kernels instead of tcgen05
+static bool use_simt_l1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MRL_L1_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 // ------------------------------------------------------------------------ passes
@@ -705,7 +718,10 @@ static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_ca
   RET(reserve_ws(n, b, pl));
   // the batch tile has b->d0p feature rows; the net consumes the first g.d0p of them
   NetGeom gl = g;
-  CKP(PK_L1F, launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+  if (use_simt_l1())
+    CKP(PK_L1F, launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+  else
+    CKP(PK_L1F, launch_l1_forward_tc(gl, b->XA.as<float>(), b->d0p / 8, n->WBt.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
   MidFwdArgs a;
   a.img = n->img.as<float>();
   a.Zt = n->Z1.as<float>();
@@ -746,7 +762,12 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.Zt = nullptr;
   if (mode == MRL_MODE_FVP) {
     CKP(PK_PACK, launch_pack_params(g, v_dev, n->V1p.as<float>(), n->imgv.as<float>(), st), 1);
-    CKP(PK_L1F, launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+    if (use_simt_l1()) {
+      CKP(PK_L1F, launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+    } else {
+      CKP(PK_PACK, launch_pack_wb(g, v_dev, n->WBv.as<float>(), st), 1);
+      CKP(PK_L1F, launch_l1_forward_tc(g, b->XA.as<float>(), b->d0p / 8, n->WBv.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+    }
     a.imgv = n->imgv.as<float>();
     a.Zt = n->Z1.as<float>();
   }

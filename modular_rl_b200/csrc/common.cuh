@@ -101,6 +101,13 @@ __device__ __forceinline__ float dact_from_h(float h) {
   return h * (1.f - h);
 }
 
+// round-to-nearest TF32 (10-bit mantissa) kept in an fp32 container
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

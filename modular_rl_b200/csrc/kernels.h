@@ -17,7 +17,18 @@ cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncol
 cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols, long long N, float* dst,
                              int ldo, long long rows_out, cudaStream_t st);
 cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
-                                int d0p, int col, float* Xr, int d0r, int* tindex, cudaStream_t st);
+                                int d0p, int col, float* Xr, int d0r, int* tindex, float* XA, int xa_kgroups,
+                                cudaStream_t st);
+
+// ---- mlp_l1_tc.cu  (tcgen05 / TMEM layer-1 GEMMs, 3xTF32)
+int l1tc_nu(const NetGeom& g);
+size_t l1tc_wb_floats(const NetGeom& g);
+size_t l1tc_xa_floats(int xa_kgroups, long long n_mtiles);
+cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgroups, const float* WB, float* Zt,
+                                 int n_tiles, cudaStream_t st);
+cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, long long N, float* XA, int xa_kgroups,
+                           long long n_mtiles, cudaStream_t st);
+cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cudaStream_t st);
 
 // ---- mlp_mid.cu
 struct MidFwdArgs {

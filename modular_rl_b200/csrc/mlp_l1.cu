@@ -334,7 +334,8 @@ __global__ void pack_rows_kernel(const T* __restrict__ src, long long ld, int nc
 // Also writes the within-path index (int32) for the bit-exact integer contract.
 __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n_paths, long long N,
                                     double timestep_limit, float* __restrict__ Xt, int d0p, int col,
-                                    float* __restrict__ Xr, int d0r, int* __restrict__ tindex) {
+                                    float* __restrict__ Xr, int d0r, int* __restrict__ tindex,
+                                    float* __restrict__ XA, int xa_kgroups) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
   int lo = 0, hi = n_paths;  // offsets[lo] <= t < offsets[hi]
@@ -349,6 +350,14 @@ __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n
   Xt[((size_t)tile * d0p + col) * MRL_LDT + r] = f;
   Xr[(size_t)t * d0r + col] = f;
   if (tindex) tindex[t] = (int)k;
+  if (XA) {   // tensor-core operand copy: [mtile][kg][hi|lo][khalf][mgroup][8][4], see mlp_l1_tc.cu
+    const long long mt = t / 128;
+    const int m = (int)(t % 128);
+    const float h = tf32_rna(f);
+    float* base = XA + ((size_t)mt * xa_kgroups + (col >> 3)) * 2048 + ((col & 7) >> 2) * 512 + (m >> 3) * 32 + (m & 7) * 4 + (col & 3);
+    base[0] = h;
+    base[1024] = tf32_rna(f - h);
+  }
 }
 
 // ------------------------------------------------------------------------------------ launchers
@@ -426,8 +435,9 @@ cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols
 }
 
 cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
-                                int d0p, int col, float* Xr, int d0r, int* tindex, cudaStream_t st) {
+                                int d0p, int col, float* Xr, int d0r, int* tindex, float* XA, int xa_kgroups,
+                                cudaStream_t st) {
   time_feature_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(offsets, n_paths, N, limit, Xt, d0p, col, Xr,
-                                                                   d0r, tindex);
+                                                                   d0r, tindex, XA, xa_kgroups);
   return cudaGetLastError();
 }

@@ -1,0 +1,278 @@
+// Layer-1 GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM), split-precision 3xTF32.
+//
+//   l1_forward_tc_kernel : Z1[128 timesteps x NU] = X[128 x d0p] . B[d0p x NU]        (B = W1 or V1)
+//
+// FP32 parity (1e-5 relative, north_star) rules out plain TF32 (10-bit mantissa).  Every operand is
+// stored as hi = rna_tf32(x) and lo = rna_tf32(x - hi) - both exactly representable in TF32 - and
+// each K=8 step issues three MMAs  D += A_lo.B_hi ; D += A_hi.B_lo ; D += A_hi.B_hi  with FP32
+// accumulation in TMEM: per-product error ~2^-21, i.e. FP32-class results at 1/3 of the TF32 rate.
+//
+// Operands are pre-arranged in HBM in the UMMA canonical K-major / no-swizzle core-matrix order
+// (8 rows x 16 bytes per core matrix, SBO = 128 B between row groups, LBO between the two K halves),
+// so a pipeline stage is filled by two 1-D bulk async copies (UBLKCP) with no tensor map:
+//   A stage: [hi | lo] x [khalf 2][mgroup 16][8][4] floats (2 x 4 KB)  - one 128-timestep x 8-feature block
+//   B stage: [hi | lo] x [khalf 2][ngroup NU/8][8][4] floats
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter -> Z1 tile-major in HBM).
+// Two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Persistent grid.
+#include "common.cuh"
+#include "kernels.h"
+
+#define TC_STAGES 6
+#define TC_THREADS 192
+#define TC_M 128
+#define TC_WATCHDOG (1u << 27)
+
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > TC_WATCHDOG) __trap();   // a protocol bug becomes an error, never a hung GPU
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// XA: [mtile][kg][hi|lo][khalf][mgroup][8][4]   WB: [kg][hi|lo][khalf][ngroup][8][4]
+__global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const float* __restrict__ XA,
+                                                                      const float* __restrict__ WB,
+                                                                      float* __restrict__ Zt, int kgroups,
+                                                                      int xa_kgroups, int nu, int d1, int n_mtiles,
+                                                                      int n_tiles, int acc_cols) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [TC_STAGES]
+  uint64_t* empty = full + TC_STAGES;                           // [TC_STAGES]
+  uint64_t* tfull = empty + TC_STAGES;                          // [2]
+  uint64_t* tempty = tfull + 2;                                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  unsigned char* stages = smem_raw + 256;
+  const uint32_t bytesA = 2 * TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
+  const uint32_t stage_bytes = bytesA + bytesB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {   // TMEM: 2 accumulators of acc_cols columns each
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(2 * acc_cols)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---------------- producer
+      uint32_t it = 0;
+      for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+        const float* a_src = XA + (size_t)mt * xa_kgroups * (2 * TC_M * 8);
+        for (int kg = 0; kg < kgroups; ++kg, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait_guard(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+          unsigned char* st = stages + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          bulk_g2s(st, a_src + (size_t)kg * (2 * TC_M * 8), bytesA, &full[s]);
+          bulk_g2s(st + bytesA, WB + (size_t)kg * (2 * nu * 8), bytesB, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---------------- MMA issuer
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=TF32, K-major both
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
+      const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;   // bytes between the two K halves
+      uint32_t it = 0, tcount = 0;
+      for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        mbar_wait_guard(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int kg = 0; kg < kgroups; ++kg, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait_guard(&full[s], (it / TC_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
+          const uint64_t a_hi = umma_desc(sa, lboA, 128), a_lo = umma_desc(sa + bytesA / 2, lboA, 128);
+          const uint64_t b_hi = umma_desc(sa + bytesA, lboB, 128), b_lo = umma_desc(sa + bytesA + bytesB / 2, lboB, 128);
+          umma_tf32(d_tmem, a_lo, b_hi, idesc, kg > 0 ? 1u : 0u);   // small terms first
+          umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+          umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          tc_commit(&empty[s]);          // frees the stage when the three MMAs have read it
+        }
+        tc_commit(&tfull[acc]);          // accumulator complete
+      }
+    }
+  } else {             // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      mbar_wait_guard(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const int r = q * 32 + lane;                 // timestep row inside the 128-row tile
+      const int tile = 2 * mt + (r >> 6);
+      float* zt = Zt + ((size_t)tile * d1) * MRL_LDT + (r & 63);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+      for (int c0 = 0; c0 < nu; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        if (tile < n_tiles) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < d1) zt[(size_t)(c0 + j) * MRL_LDT] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * acc_cols)));
+  }
+}
+
+// ------------------------------------------------------------------------------------ operand packing
+// src row-major [N x ld] (float/double) -> XA.  One thread per (timestep, 4 consecutive features).
+template <typename T>
+__global__ void pack_xa_kernel(const T* __restrict__ src, long long ld, int ncols, long long N, float* __restrict__ XA,
+                               int xa_kgroups, long long rows_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int quads = xa_kgroups * 2;
+  if (i >= rows_out * quads) return;
+  const long long t = i / quads;
+  const int kq4 = (int)(i % quads);             // quad index: features 4*kq4 .. +3
+  const int kg = kq4 >> 1, khalf = kq4 & 1;
+  const long long mt = t / TC_M;
+  const int m = (int)(t % TC_M);
+  float hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * kq4 + j;
+    const float x = (t < N && c < ncols) ? (float)src[t * ld + c] : 0.f;
+    hi[j] = tf32_rna(x);
+    lo[j] = tf32_rna(x - hi[j]);
+  }
+  float* base = XA + ((size_t)mt * xa_kgroups + kg) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4;
+  *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+// one feature column (e.g. the time feature) rewritten in place from a flat float array
+__global__ void pack_xa_column_kernel(const float* __restrict__ col, long long N, float* __restrict__ XA, int xa_kgroups,
+                                      int c) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const int kg = c >> 3, khalf = (c & 7) >> 2, kq = c & 3;
+  const long long mt = t / TC_M;
+  const int m = (int)(t % TC_M);
+  const float x = col[t], h = tf32_rna(x);
+  float* base = XA + ((size_t)mt * xa_kgroups + kg) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4 + kq;
+  base[0] = h;
+  base[TC_M * 8] = tf32_rna(x - h);
+}
+
+// theta (flat) layer-1 kernel [d0 x d1] -> WB [kg][hi|lo][khalf][ngroup][8][4]
+__global__ void pack_wb_kernel(NetGeom g, const float* __restrict__ theta, float* __restrict__ WB, int nu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = g.d0p * nu;
+  if (i >= total) return;
+  const int k = i / nu, n = i % nu;
+  const float x = (k < g.d[0] && n < g.d[1]) ? theta[g.off_flat_W[1] + k * g.d[1] + n] : 0.f;
+  const float h = tf32_rna(x);
+  const int kg = k >> 3, khalf = (k & 7) >> 2, kq = k & 3;
+  float* base = WB + (size_t)kg * (2 * nu * 8) + khalf * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4 + kq;
+  base[0] = h;
+  base[nu * 8] = tf32_rna(x - h);
+}
+
+// ------------------------------------------------------------------------------------ launchers
+int l1tc_nu(const NetGeom& g) { return round_up(g.d[1], 16); }
+size_t l1tc_wb_floats(const NetGeom& g) { return (size_t)g.d0p * l1tc_nu(g) * 2; }
+size_t l1tc_xa_floats(int xa_kgroups, long long n_mtiles) { return (size_t)n_mtiles * xa_kgroups * 2 * TC_M * 8; }
+
+cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgroups, const float* WB, float* Zt,
+                                 int n_tiles, cudaStream_t st) {
+  const int nu = l1tc_nu(g);
+  const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
+  const size_t smem = 256 + (size_t)TC_STAGES * (2 * TC_M * 8 * 4 + 2 * nu * 8 * 4);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(l1_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_mtiles = (n_tiles + 1) / 2;
+  const int grid = n_mtiles < sms ? n_mtiles : sms;
+  l1_forward_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XA, WB, Zt, g.d0p / 8, xa_kgroups, nu, g.d[1], n_mtiles, n_tiles,
+                                                       acc_cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, long long N, float* XA, int xa_kgroups,
+                           long long n_mtiles, cudaStream_t st) {
+  const long long rows_out = n_mtiles * TC_M;
+  const long long total = rows_out * xa_kgroups * 2;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == 1) pack_xa_kernel<double><<<blocks, 256, 0, st>>>((const double*)src, ld, ncols, N, XA, xa_kgroups, rows_out);
+  else pack_xa_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, ld, ncols, N, XA, xa_kgroups, rows_out);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_xa_column(const float* col, long long N, float* XA, int xa_kgroups, int c, cudaStream_t st) {
+  pack_xa_column_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(col, N, XA, xa_kgroups, c);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cudaStream_t st) {
+  const int nu = l1tc_nu(g);
+  const int total = g.d0p * nu;
+  pack_wb_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, theta, WB, nu);
+  return cudaGetLastError();
+}
