@@ -135,7 +135,7 @@ struct mrl_batch {
   unsigned long long version = 0;
   int pol_head = -1, pol_dout = 0, naux_pol = 0;
   bool has_baseline = false, has_adv32 = false, has_ret = false;
-  DevBuf XA, Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
+  DevBuf XG, XA, Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
       gather;
 };
 
@@ -166,7 +166,7 @@ extern "C" int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int wit
 extern "C" int mrl_batch_destroy(mrl_batch* b) {
   if (!b) return 0;
   cudaSetDevice(b->device);
-  DevBuf* bufs[] = {&b->XA, &b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
+  DevBuf* bufs[] = {&b->XG, &b->XA, &b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
                     &b->stage2, &b->baseline, &b->ret, &b->adv, &b->adv32, &b->stats, &b->gather};
   for (DevBuf* d : bufs) d->release();
   delete b;
@@ -202,6 +202,9 @@ extern "C" int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long l
   const long long n_mtiles = (b->n_tiles + 1) / 2;
   CK(b->XA.reserve(l1tc_xa_floats(b->d0p / 8, n_mtiles) * 4));
   CKL(launch_pack_xa(src, dtype, ld, b->ob_dim, N, b->XA.as<float>(), b->d0p / 8, n_mtiles, st), 1);
+  const int xg_ftiles = (b->xdim + 127) / 128;
+  CK(b->XG.reserve(l1tc_xg_floats(xg_ftiles, b->n_tiles) * 4));
+  CKL(launch_pack_xg(src, dtype, ld, b->ob_dim, N, b->XG.as<float>(), xg_ftiles, b->n_tiles, st), 1);
   return 0;
 }
 
@@ -228,7 +231,8 @@ extern "C" int mrl_batch_set_paths(mrl_batch* b, const long long* offsets, const
   if (b->with_time) {
     if (!(timestep_limit > 0)) return fail("mrl_batch_set_paths: timestep_limit must be > 0");
     CKL(launch_time_feature(b->offsets.as<long long>(), n_paths, b->N, timestep_limit, b->Xt.as<float>(), b->d0p,
-                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), b->XA.as<float>(), b->d0p / 8, st), 1);
+                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), b->XA.as<float>(), b->d0p / 8,
+                            b->XG.as<float>(), (b->xdim + 127) / 128, st), 1);
   }
   return 0;
 }
@@ -545,7 +549,7 @@ extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, 
 struct mrl_net {
   int device = 0;
   NetGeom g;
-  DevBuf WBt, WBv, theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
+  DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
       out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, scal, headout, stage;
   unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
   const mrl_batch* cache_batch = nullptr;
@@ -572,6 +576,10 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   const int d = dims[n_layers];
   const int naux = head == MRL_GAUSS ? 1 + 3 * d : (head == MRL_CATEGORICAL ? 2 + d : 1);
   mrl_build_geom(&n->g, n_layers, dims, head, activation, naux);
+  if (!l1tc_supported(n->g)) {
+    delete n;
+    return fail("mrl_net_create: input dim %d x first hidden width %d exceeds the TMEM budget of the layer-1 tensor-core kernels", dims[0], dims[1]);
+  }
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   const size_t need = mid_backward_smem(n->g, head == MRL_VALUE ? MRL_MODE_GRAD : MRL_MODE_FVP) + 2048;
@@ -604,7 +612,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
+  DevBuf* bufs[] = {&n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->D1r, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->scal,
                     &n->headout, &n->stage};
@@ -704,6 +712,7 @@ static int reserve_ws(mrl_net* n, const mrl_batch* b, const Plan& pl) {
   CK(n->Z1.reserve((size_t)b->n_tiles * g.d[1] * MRL_LDT * 4));
   CK(n->cache.reserve((size_t)b->n_tiles * g.act_rows * MRL_LDT * 4));
   CK(n->D1r.reserve((size_t)b->n_tiles * MRL_TILE * g.n1p * 4));
+  CK(n->DG.reserve(l1tc_dg_floats(g, b->n_tiles) * 4));
   CK(n->part1.reserve((size_t)pl.n_slabs * g.d[0] * g.n1p * 4));
   CK(n->partm.reserve((size_t)pl.n_slabs * g.pmid * 4));
   CK(n->loss_part.reserve((size_t)pl.n_slabs * 4 * 8));
@@ -774,7 +783,9 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.aux = mode == MRL_MODE_GRAD ? aux_of(n, b) : nullptr;
   a.cache = n->cache.as<float>();
   a.coef = coef_dev;
-  a.D1r = n->D1r.as<float>();
+  a.D1r = use_simt_l1() ? n->D1r.as<float>() : nullptr;
+  a.DG = use_simt_l1() ? nullptr : n->DG.as<float>();
+  a.nu = l1tc_nu(g);
   a.partm = n->partm.as<float>();
   a.N = b->N;
   a.n_tiles = b->n_tiles;
@@ -782,8 +793,12 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.mode = mode;
   a.reverse_kl = reverse_kl;
   CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
-  CKP(PK_L1G, launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
-                     b->n_tiles, pl.n_slabs, st), 1);
+  if (use_simt_l1())
+    CKP(PK_L1G, launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
+                               b->n_tiles, pl.n_slabs, st), 1);
+  else
+    CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
+                                  pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
   const int world = world_of(n);
   // terms that are not sums over timesteps are divided by `world` so that the all-reduce restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;

@@ -18,17 +18,24 @@ cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols
                              int ldo, long long rows_out, cudaStream_t st);
 cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
                                 int d0p, int col, float* Xr, int d0r, int* tindex, float* XA, int xa_kgroups,
-                                cudaStream_t st);
+                                float* XG, int xg_ftiles, cudaStream_t st);
 
 // ---- mlp_l1_tc.cu  (tcgen05 / TMEM layer-1 GEMMs, 3xTF32)
 int l1tc_nu(const NetGeom& g);
 size_t l1tc_wb_floats(const NetGeom& g);
+bool l1tc_supported(const NetGeom& g);
 size_t l1tc_xa_floats(int xa_kgroups, long long n_mtiles);
 cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgroups, const float* WB, float* Zt,
                                  int n_tiles, cudaStream_t st);
 cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, long long N, float* XA, int xa_kgroups,
                            long long n_mtiles, cudaStream_t st);
 cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cudaStream_t st);
+size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles);
+size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles);
+cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, long long N, float* XG, int xg_ftiles,
+                           long long n_tiles, cudaStream_t st);
+cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,
+                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st);
 
 // ---- mlp_mid.cu
 struct MidFwdArgs {
@@ -48,7 +55,9 @@ struct MidBwdArgs {
   const float* aux;
   const float* cache;
   const double* coef;  // device: {c_surr, c_kl} (gradient mode)
-  float* D1r;          // out: delta_1 row-major [n_tiles*64][n1p]
+  float* D1r;          // out: delta_1 row-major [n_tiles*64][n1p]   (SIMT layer-1 gradient; may be null)
+  float* DG;           // out: delta_1 as the tcgen05 B operand [tg][hi|lo][khalf][ngroup][8][4] (may be null)
+  int nu;              // padded layer-1 width of DG
   float* partm;        // out: [n_slabs][pmid]
   long long N;
   int n_tiles, slab_tiles, mode, reverse_kl;

@@ -335,7 +335,8 @@ __global__ void pack_rows_kernel(const T* __restrict__ src, long long ld, int nc
 __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n_paths, long long N,
                                     double timestep_limit, float* __restrict__ Xt, int d0p, int col,
                                     float* __restrict__ Xr, int d0r, int* __restrict__ tindex,
-                                    float* __restrict__ XA, int xa_kgroups) {
+                                    float* __restrict__ XA, int xa_kgroups, float* __restrict__ XG,
+                                    int xg_ftiles) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
   int lo = 0, hi = n_paths;  // offsets[lo] <= t < offsets[hi]
@@ -357,6 +358,12 @@ __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n
     float* base = XA + ((size_t)mt * xa_kgroups + (col >> 3)) * 2048 + ((col & 7) >> 2) * 512 + (m >> 3) * 32 + (m & 7) * 4 + (col & 3);
     base[0] = h;
     base[1024] = tf32_rna(f - h);
+    // gradient operand copy: [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps]
+    const int fm = col % 128;
+    float* g = XG + ((size_t)(t >> 3) * xg_ftiles + col / 128) * 2048 + (int)((t & 7) >> 2) * 512 + (fm >> 3) * 32 +
+               (fm & 7) * 4 + (int)(t & 3);
+    g[0] = h;
+    g[1024] = tf32_rna(f - h);
   }
 }
 
@@ -436,8 +443,8 @@ cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols
 
 cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
                                 int d0p, int col, float* Xr, int d0r, int* tindex, float* XA, int xa_kgroups,
-                                cudaStream_t st) {
+                                float* XG, int xg_ftiles, cudaStream_t st) {
   time_feature_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(offsets, n_paths, N, limit, Xt, d0p, col, Xr,
-                                                                   d0r, tindex, XA, xa_kgroups);
+                                                                   d0r, tindex, XA, xa_kgroups, XG, xg_ftiles);
   return cudaGetLastError();
 }

@@ -178,6 +178,129 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
   }
 }
 
+// ------------------------------------------------------------------------------------
+// part1[slab][f][n] = sum_{t in slab} X[t][f] * delta1[t][n]  on the tensor cores:
+// D[128 features x NU] += A[128 x 8 timesteps] . B[NU x 8 timesteps]^T, K = timesteps.
+//   XG: [tg = t/8][ftile][hi|lo][khalf][fgroup 16][8 features][4 timesteps]
+//   DG: [tg][hi|lo][khalf][ngroup NU/8][8][4 timesteps]       (written by mid_backward_kernel)
+// One CTA accumulates a whole slab (<= 1024 timesteps) for all feature tiles in TMEM (ftiles x
+// acc_cols columns), then the epilogue warps store the fp32 partial that reduce_partials_kernel sums
+// in fp64.  Same warp roles and stage ring as the forward kernel.
+__global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* __restrict__ XG,
+                                                                   const float* __restrict__ DG,
+                                                                   float* __restrict__ part1, int ftiles,
+                                                                   int xg_ftiles, int nu, int d0, int n1p,
+                                                                   int slab_tiles, int n_tiles, int n_slabs,
+                                                                   int acc_cols, int tmem_cols, int nstages) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tfull = empty + TC_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  unsigned char* stages = smem_raw + 256;
+  const uint32_t bytesA1 = 2 * TC_M * 8 * 4;                 // one feature tile, hi + lo
+  const uint32_t bytesA = ftiles * bytesA1, bytesB = 2 * nu * 8 * 4;
+  const uint32_t stage_bytes = bytesA + bytesB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tempty[0], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
+        for (int tg = t0 * 8; tg < t1 * 8; ++tg, ++it) {
+          const int s = it % nstages;
+          mbar_wait_guard(&empty[s], ((it / nstages) & 1) ^ 1);
+          unsigned char* st = stages + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          bulk_g2s(st, XG + (size_t)tg * xg_ftiles * (2 * TC_M * 8), bytesA, &full[s]);
+          bulk_g2s(st + bytesA, DG + (size_t)tg * (2 * nu * 8), bytesB, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
+      const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;
+      uint32_t it = 0, scount = 0;
+      for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
+        const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
+        mbar_wait_guard(&tempty[0], (scount & 1) ^ 1);
+        tc_fence_after();
+        for (int tg = t0 * 8; tg < t1 * 8; ++tg, ++it) {
+          const int s = it % nstages;
+          mbar_wait_guard(&full[s], (it / nstages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
+          const uint64_t b_hi = umma_desc(sa + bytesA, lboB, 128), b_lo = umma_desc(sa + bytesA + bytesB / 2, lboB, 128);
+          const uint32_t accf = tg > t0 * 8 ? 1u : 0u;
+          for (int ft = 0; ft < ftiles; ++ft) {
+            const uint32_t ab = sa + ft * bytesA1;
+            const uint64_t a_hi = umma_desc(ab, lboA, 128), a_lo = umma_desc(ab + bytesA1 / 2, lboA, 128);
+            const uint32_t d_tmem = tmem_base + ft * acc_cols;
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, accf);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tfull[0]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t scount = 0;
+    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
+      mbar_wait_guard(&tfull[0], scount & 1);
+      tc_fence_after();
+      for (int ft = 0; ft < ftiles; ++ft) {
+        const int f = ft * TC_M + q * 32 + lane;
+        float* dst = part1 + ((size_t)slab * d0 + f) * n1p;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ft * acc_cols;
+        for (int c0 = 0; c0 < nu; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          if (f < d0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (c0 + j < n1p)
+                *reinterpret_cast<float4*>(dst + c0 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+  }
+}
+
 // ------------------------------------------------------------------------------------ operand packing
 // src row-major [N x ld] (float/double) -> XA.  One thread per (timestep, 4 consecutive features).
 template <typename T>
@@ -215,6 +338,31 @@ __global__ void pack_xa_column_kernel(const float* __restrict__ col, long long N
   float* base = XA + ((size_t)mt * xa_kgroups + kg) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4 + kq;
   base[0] = h;
   base[TC_M * 8] = tf32_rna(x - h);
+}
+
+// src row-major [N x ld] -> XG [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps].
+// One thread per (4 consecutive timesteps, feature).
+template <typename T>
+__global__ void pack_xg_kernel(const T* __restrict__ src, long long ld, int ncols, long long N, float* __restrict__ XG,
+                               int xg_ftiles, long long n_tquads) {
+  const int fpad = xg_ftiles * TC_M;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tquads * fpad) return;
+  const long long tq = i / fpad;
+  const int f = (int)(i % fpad);
+  float hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long t = tq * 4 + j;
+    const float x = (t < N && f < ncols) ? (float)src[t * ld + f] : 0.f;
+    hi[j] = tf32_rna(x);
+    lo[j] = tf32_rna(x - hi[j]);
+  }
+  const long long tg = tq >> 1;
+  const int khalf = (int)(tq & 1), ft = f / TC_M, fm = f % TC_M;
+  float* base = XG + ((size_t)tg * xg_ftiles + ft) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (fm >> 3) * 32 + (fm & 7) * 4;
+  *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // theta (flat) layer-1 kernel [d0 x d1] -> WB [kg][hi|lo][khalf][ngroup][8][4]
@@ -275,4 +423,55 @@ cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cuda
   const int total = g.d0p * nu;
   pack_wb_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, theta, WB, nu);
   return cudaGetLastError();
+}
+
+size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles) { return (size_t)n_tiles * 8 * xg_ftiles * 2 * TC_M * 8; }
+size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles) { return (size_t)n_tiles * 8 * 2 * l1tc_nu(g) * 8; }
+
+cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, long long N, float* XG, int xg_ftiles,
+                           long long n_tiles, cudaStream_t st) {
+  const long long n_tquads = n_tiles * 16;
+  const long long total = n_tquads * xg_ftiles * TC_M;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == 1) pack_xg_kernel<double><<<blocks, 256, 0, st>>>((const double*)src, ld, ncols, N, XG, xg_ftiles, n_tquads);
+  else pack_xg_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, ld, ncols, N, XG, xg_ftiles, n_tquads);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,
+                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st) {
+  const int nu = l1tc_nu(g);
+  const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
+  const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
+  int tmem_cols = 32;
+  while (tmem_cols < ftiles * acc_cols) tmem_cols *= 2;
+  if (tmem_cols > 512) return cudaErrorInvalidConfiguration;
+  const size_t stage_bytes = (size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4;
+  int nstages = (int)((227 * 1024 - 256) / stage_bytes);
+  if (nstages > TC_STAGES) nstages = TC_STAGES;
+  if (nstages < 2) return cudaErrorInvalidConfiguration;
+  const size_t smem = 256 + (size_t)nstages * stage_bytes;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(l1_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n_slabs < sms ? n_slabs : sms;
+  l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
+                                                    n_tiles, n_slabs, acc_cols, tmem_cols, nstages);
+  return cudaGetLastError();
+}
+
+// nets the tensor-core layer-1 path can hold: TMEM (512 columns) and shared memory (>= 2 stages)
+bool l1tc_supported(const NetGeom& g) {
+  const int nu = l1tc_nu(g);
+  const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
+  const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
+  if (nu > 256 || ftiles * acc_cols > 512) return false;
+  const size_t stage_bytes = (size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4;
+  return 2 * stage_bytes + 256 <= 227 * 1024;
 }

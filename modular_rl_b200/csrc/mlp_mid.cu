@@ -497,10 +497,25 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
       const float* D1 = E;  // off_act[1] == 0
       const int n1 = g.d[1];
       for (int job = ln.warp; job < ((n1 + 7) >> 3); job += NW) bias_job(job, ln, D1, n1, G + g.off_b[1]);
-      float* out = a.D1r + (size_t)tile * MRL_TILE * g.n1p;
-      for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_MID_THREADS) {
-        const int r = i / g.n1p, c = i % g.n1p;
-        out[i] = (c < n1) ? D1[c * MRL_LDT + r] : 0.f;
+      if (a.D1r) {
+        float* out = a.D1r + (size_t)tile * MRL_TILE * g.n1p;
+        for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_MID_THREADS) {
+          const int r = i / g.n1p, c = i % g.n1p;
+          out[i] = (c < n1) ? D1[c * MRL_LDT + r] : 0.f;
+        }
+      }
+      if (a.DG) {   // split-precision tensor-core operand: 4 consecutive timesteps of one column per thread
+        const int nu = a.nu;
+        for (int i = tid; i < 16 * nu; i += MRL_MID_THREADS) {
+          const int tq = i / nu, n = i % nu;       // timesteps 4*tq .. +3 of this tile
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < n1) v = *reinterpret_cast<const float4*>(D1 + n * MRL_LDT + 4 * tq);
+          const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          const float4 l = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+          float* base = a.DG + ((size_t)tile * 8 + (tq >> 1)) * (2 * nu * 8) + (tq & 1) * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4;
+          *reinterpret_cast<float4*>(base) = h;
+          *reinterpret_cast<float4*>(base + nu * 8) = l;
+        }
       }
     }
     __syncthreads();
