@@ -3,9 +3,9 @@
 // One CTA owns a slab of up to 16 tiles (1024 timesteps).  All weights of layers 2..L (plus
 // transposes and the tangent's weights for the R-op) live in shared memory for the CTA's
 // lifetime; per tile the activations of all layers are held feature-major in shared memory
-// ([feature][68]), every GEMM is a register-tiled SIMT FP32 product (4x4 per thread,
-// 32x16 per warp, both operands read with conflict-free broadcast LDS.128), and weight
-// gradients accumulate in shared memory until the slab is flushed as one fp32 partial.
+// ([feature][68]); every GEMM is a set of 32x16 warp tiles computed with mma.sync TF32 in
+// split precision (3xTF32, FP32-class accuracy), and weight gradients accumulate in shared
+// memory until the slab is flushed as one fp32 partial.
 //
 //   mid_forward_kernel : h1 = act(Z1+b1), ..., head -> surr/kl/ent (or MSE) sums, activation cache
 //                        trpo.py:37-42,60-63 ; core.py:339-365,402-438 ; core.py:613-617
@@ -17,6 +17,9 @@
 #define LOG_2PI 1.8378770664093453f
 #define LOG_2PIE 2.8378770664093453f
 #define MAX_DOUT 64
+#ifndef MRL_BWD_THREADS
+#define MRL_BWD_THREADS 512   // reverse-sweep kernel: 16 warps hide the LDS/MMA latencies of the small tiles
+#endif
 
 // g(u) = u - log1p(u) = u^2/2 - u^3/3 + ...  evaluated without the O(u) cancellation.  Both KL
 // formulas reduce to sums of g(.) of a relative deviation, which is what keeps a float32 per-row KL
@@ -42,95 +45,159 @@ struct Lane {
   }
 };
 
-// acc[i][j] += sum_k A[k][r+i] * B[k][c+j]
-__device__ __forceinline__ void gemm_acc(float (&acc)[4][4], const float* __restrict__ A,
-                                         const float* __restrict__ B, int K, int ldb, int r, int c) {
-  const float* a = A + r;
-  const float* b = B + c;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 av = *reinterpret_cast<const float4*>(a + k * MRL_LDT);
-    const float4 bv = *reinterpret_cast<const float4*>(b + k * ldb);
-    acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
-    acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
-    acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
-    acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
-    acc[2][0] = fmaf(av.z, bv.x, acc[2][0]); acc[2][1] = fmaf(av.z, bv.y, acc[2][1]);
-    acc[2][2] = fmaf(av.z, bv.z, acc[2][2]); acc[2][3] = fmaf(av.z, bv.w, acc[2][3]);
-    acc[3][0] = fmaf(av.w, bv.x, acc[3][0]); acc[3][1] = fmaf(av.w, bv.y, acc[3][1]);
-    acc[3][2] = fmaf(av.w, bv.z, acc[3][2]); acc[3][3] = fmaf(av.w, bv.w, acc[3][3]);
+// ---- warp-level tensor-core GEMM pieces (mma.sync m16n8k8 TF32, split-precision 3xTF32) ----------
+// The fused chain cannot feed tcgen05: its operands would need the UMMA core-matrix layout in shared
+// memory with separate hi/lo copies of every activation and weight (2x the 219 KB this kernel already
+// uses at Humanoid sizes).  mma.sync takes fragments from registers, so the split x = hi + lo is done
+// on the fly after a plain LDS and the shared-memory layouts stay as they are.  hi = rna_tf32(x),
+// lo = x - hi (exact in fp32; the tensor core drops its low 13 bits, a 2^-21 relative effect);
+// D += lo.hi + hi.lo + hi.hi keeps FP32-class accuracy (north_star: 1e-5) at 1/3 of the TF32 rate,
+// with ~3x fewer issued instructions than the FFMA formulation (the chain is issue-bound).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  // round-to-nearest TF32 by integer arithmetic on the sign-magnitude bits (cvt.rna.tf32 costs ~4
+  // instructions on sm_100a): +half-ulp then truncate.  hi must be exact for the subtraction; for lo the
+  // tensor core's own truncation of the low 13 bits completes the rounding.
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// 2x2 mma tiles, three passes (lo.hi, hi.lo, hi.hi) so that consecutive MMAs hit different accumulators
+__device__ __forceinline__ void mma3_2x2(float (&acc)[2][2][4], const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4],
+                                         const uint32_t (&bh)[2][2], const uint32_t (&bl)[2][2]) {
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+}
+
+// acc[mi][ni] += A^T-tile . B-tile over k in [0,K): A_T[k][r] feature-major activations (ld = MRL_LDT),
+// B[k][c] row-major weights (ld = ldb).  Warp tile 32 rows x 16 cols = 2 x 2 mma tiles.
+template <bool TAIL>
+__device__ __forceinline__ void mma_fwd_step(float (&acc)[2][2][4], const float* __restrict__ a, const float* __restrict__ b0,
+                                             const float* __restrict__ b1, int ldb4, int krem) {
+  // a -> A_T[k0 + t][r0 + g], b0/b1 -> B[k0 + t][c], ldb4 = 4 * ldb ; rows k0+t and k0+t+4
+  const bool va = !TAIL || krem > 0, vb = !TAIL || krem > 4;   // krem = K - (k0 + t)
+  uint32_t bh[2][2], bl[2][2], ah[2][4], al[2][4];
+  split_tf32(va ? b0[0] : 0.f, bh[0][0], bl[0][0]);
+  split_tf32(vb ? b0[ldb4] : 0.f, bh[0][1], bl[0][1]);
+  split_tf32(va ? b1[0] : 0.f, bh[1][0], bl[1][0]);
+  split_tf32(vb ? b1[ldb4] : 0.f, bh[1][1], bl[1][1]);
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    split_tf32(va ? a[16 * mi] : 0.f, ah[mi][0], al[mi][0]);
+    split_tf32(va ? a[16 * mi + 8] : 0.f, ah[mi][1], al[mi][1]);
+    split_tf32(vb ? a[4 * MRL_LDT + 16 * mi] : 0.f, ah[mi][2], al[mi][2]);
+    split_tf32(vb ? a[4 * MRL_LDT + 16 * mi + 8] : 0.f, ah[mi][3], al[mi][3]);
   }
+  mma3_2x2(acc, ah, al, bh, bl);
+}
+__device__ __forceinline__ void mma_fwd_acc(float (&acc)[2][2][4], const float* __restrict__ A,
+                                            const float* __restrict__ B, int K, int ldb, int r0, int c0,
+                                            int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* a = A + t * MRL_LDT + r0 + g;
+  const float* b0 = B + t * ldb + min(c0 + g, ldb - 1);
+  const float* b1 = B + t * ldb + min(c0 + 8 + g, ldb - 1);
+  const int ldb4 = 4 * ldb, ldb8 = 8 * ldb;
+  int k0 = 0;
+#pragma unroll 2
+  for (; k0 + 8 <= K; k0 += 8) {
+    mma_fwd_step<false>(acc, a, b0, b1, ldb4, 8);
+    a += 8 * MRL_LDT; b0 += ldb8; b1 += ldb8;
+  }
+  if (k0 < K) mma_fwd_step<true>(acc, a, b0, b1, ldb4, K - k0 - t);
 }
 
 // One warp job of  OUT[c][r] = epi(c, r, sum_k A1[k][r] B1[k][c] (+ sum_k A2[k][r] B2[k][c])).
-// job -> 32 rows x 16 cols; epi receives 4 consecutive rows of one column.
+// job -> 32 rows x 16 cols; epi(c, r, value) is called once per output element.
 template <class Epi>
 __device__ __forceinline__ void fwd_job(int job, const Lane& ln, const float* A1, const float* B1, int K1,
                                         const float* A2, const float* B2, int K2, int ldb, int n_out,
                                         Epi epi) {
-  const int rj = job & 1, cj = job >> 1;
-  const int r = rj * 32 + 4 * ln.rg;
-  const int c = cj * 16 + 4 * ln.cg;
-  const int cc = min(c, ldb - 4);
-  float acc[4][4];
+  const int r0 = (job & 1) * 32, c0 = (job >> 1) * 16;
+  float acc[2][2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  gemm_acc(acc, A1, B1, K1, ldb, r, cc);
-  if (A2 != nullptr) gemm_acc(acc, A2, B2, K2, ldb, r, cc);
-  if (c == cc) {
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (c + j < n_out) epi(c + j, r, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
-  }
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  mma_fwd_acc(acc, A1, B1, K1, ldb, r0, c0, ln.lane);
+  if (A2 != nullptr) mma_fwd_acc(acc, A2, B2, K2, ldb, r0, c0, ln.lane);
+  const int g = ln.lane >> 2, t = ln.lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      const int r = r0 + 16 * mi + g, c = c0 + 8 * ni + 2 * t;
+      if (c < n_out) { epi(c, r, acc[mi][ni][0]); epi(c, r + 8, acc[mi][ni][2]); }
+      if (c + 1 < n_out) { epi(c + 1, r, acc[mi][ni][1]); epi(c + 1, r + 8, acc[mi][ni][3]); }
+    }
 }
 __device__ __forceinline__ int fwd_jobs(int n_out) { return 2 * ((n_out + 15) >> 4); }
 
-// One warp job of  G[m][n] += sum_r A[m][r] * D[n][r]   (32 m x 16 n per job)
+// One warp job of  G[m][n] += sum_r A[m][r] * D[n][r]   (32 m x 16 n per job, K = the 64 timesteps)
 __device__ __forceinline__ void grad_job(int job, int n_nblk, const Lane& ln, const float* __restrict__ A,
                                          int M, const float* __restrict__ D, int Nn, float* G, int ldg) {
   const int m0 = (job / n_nblk) * 32, n0 = (job % n_nblk) * 16;
-  const int mg = ln.lane & 7, ng = ln.lane >> 3;
-  const float* ap[4];
-  const float* dp[4];
+  const int g = ln.lane >> 2, t = ln.lane & 3;
+  const float* ap[4];   // rows m0+g, +8, +16, +24 (clamped; out-of-range rows are never stored)
+  const float* dp[2];   // rows n0+g, +8
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    ap[q] = A + min(m0 + mg + 8 * q, M - 1) * MRL_LDT;
-    dp[q] = D + min(n0 + ng + 4 * q, Nn - 1) * MRL_LDT;
-  }
-  float acc[4][4];
+  for (int q = 0; q < 4; ++q) ap[q] = A + min(m0 + g + 8 * q, M - 1) * MRL_LDT + t;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int q = 0; q < 2; ++q) dp[q] = D + min(n0 + g + 8 * q, Nn - 1) * MRL_LDT + t;
+  float acc[2][2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
 #pragma unroll 2
-  for (int k = 0; k < MRL_TILE; k += 4) {
-    float4 a[4], d[4];
+  for (int k0 = 0; k0 < MRL_TILE; k0 += 8) {
+    uint32_t bh[2][2], bl[2][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      a[q] = *reinterpret_cast<const float4*>(ap[q] + k);
-      d[q] = *reinterpret_cast<const float4*>(dp[q] + k);
+    for (int ni = 0; ni < 2; ++ni) {
+      split_tf32(dp[ni][k0], bh[ni][0], bl[ni][0]);
+      split_tf32(dp[ni][k0 + 4], bh[ni][1], bl[ni][1]);
     }
+    uint32_t ah[2][4], al[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int mi = 0; mi < 2; ++mi) {
+      split_tf32(ap[2 * mi][k0], ah[mi][0], al[mi][0]);
+      split_tf32(ap[2 * mi + 1][k0], ah[mi][1], al[mi][1]);
+      split_tf32(ap[2 * mi][k0 + 4], ah[mi][2], al[mi][2]);
+      split_tf32(ap[2 * mi + 1][k0 + 4], ah[mi][3], al[mi][3]);
+    }
+    mma3_2x2(acc, ah, al, bh, bl);
+  }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[i][j] = fmaf(a[i].x, d[j].x, acc[i][j]);
-        acc[i][j] = fmaf(a[i].y, d[j].y, acc[i][j]);
-        acc[i][j] = fmaf(a[i].z, d[j].z, acc[i][j]);
-        acc[i][j] = fmaf(a[i].w, d[j].w, acc[i][j]);
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      const int m = m0 + 16 * mi + g, n = n0 + 8 * ni + 2 * t;
+      if (m < M) {
+        if (n < Nn) G[m * ldg + n] += acc[mi][ni][0];
+        if (n + 1 < Nn) G[m * ldg + n + 1] += acc[mi][ni][1];
       }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + mg + 8 * i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + ng + 4 * j;
-      if (m < M && n < Nn) G[m * ldg + n] += acc[i][j];
+      if (m + 8 < M) {
+        if (n < Nn) G[(m + 8) * ldg + n] += acc[mi][ni][2];
+        if (n + 1 < Nn) G[(m + 8) * ldg + n + 1] += acc[mi][ni][3];
+      }
     }
-  }
 }
 
 // gb[j] += sum_r D[j][r] for 8 features per job
@@ -142,6 +209,13 @@ __device__ __forceinline__ void bias_job(int job, const Lane& ln, const float* _
     s = warp_sum(s);
     if (ln.lane == 0) gb[j] += s;
   }
+}
+
+// pull the next tile's lines into L2 while this tile computes (the working set is far larger than L2)
+__device__ __forceinline__ void prefetch_l2(const float* src, int nfloats) {
+  const char* p = reinterpret_cast<const char*>(src);
+  for (int off = threadIdx.x * 128; off < nfloats * 4; off += blockDim.x * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 
 __device__ __forceinline__ void copy_f4(float* dst, const float* src, int nfloats) {
@@ -203,15 +277,9 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom
       const bool last = (l == L);
       for (int job = ln.warp; job < nj; job += MRL_MID_THREADS / 32) {
         fwd_job(job, ln, A, W, g.d[l - 1], nullptr, nullptr, 0, g.ldw[l], g.d[l],
-                [&](int c, int r, float4 v) {
-                  const float bb = b[c];
-                  if (last) {
-                    v.x += bb; v.y += bb; v.z += bb; v.w += bb;
-                  } else {
-                    v.x = act_fn<ACT>(v.x + bb); v.y = act_fn<ACT>(v.y + bb);
-                    v.z = act_fn<ACT>(v.z + bb); v.w = act_fn<ACT>(v.w + bb);
-                  }
-                  *reinterpret_cast<float4*>(O + c * MRL_LDT + r) = v;
+                [&](int c, int r, float v) {
+                  v += b[c];
+                  O[c * MRL_LDT + r] = last ? v : act_fn<ACT>(v);
                 });
       }
       __syncthreads();
@@ -307,7 +375,7 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom
 
 // =====================================================================================
 template <int HEAD, int ACT, int MODE>
-__global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeom g, MidBwdArgs a) {
+__global__ void __launch_bounds__(MRL_BWD_THREADS, 1) mid_backward_kernel(NetGeom g, MidBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* img = smem;
   float* imgv = img + g.img_floats;
@@ -322,11 +390,11 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
   const int L = g.L, dL = g.d[L];
   const int slab = blockIdx.x;
   const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
-  constexpr int NW = MRL_MID_THREADS / 32;
+  constexpr int NW = MRL_BWD_THREADS / 32;
 
   copy_f4(img, a.img, g.img_floats);
   if (MODE == MRL_MODE_FVP) copy_f4(imgv, a.imgv, g.bw_floats);
-  for (int i = tid; i < g.bw_floats + gl_floats; i += MRL_MID_THREADS) G[i] = 0.f;
+  for (int i = tid; i < g.bw_floats + gl_floats; i += MRL_BWD_THREADS) G[i] = 0.f;
   __syncthreads();
   if (HEAD == MRL_HEAD_GAUSS && tid < dL) {
     const float ls = img[g.off_pm_logstd + tid];
@@ -343,6 +411,10 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
   for (int tile = t0; tile < t1; ++tile) {
     const int nvalid = (int)min((long long)MRL_TILE, a.N - (long long)tile * MRL_TILE);
     copy_f4(H, a.cache + (size_t)tile * g.act_rows * MRL_LDT, g.act_rows * MRL_LDT);
+    if (tile + 1 < t1) {
+      prefetch_l2(a.cache + (size_t)(tile + 1) * g.act_rows * MRL_LDT, g.act_rows * MRL_LDT);
+      if (MODE == MRL_MODE_FVP) prefetch_l2(a.Zt + (size_t)(tile + 1) * g.d[1] * MRL_LDT, g.d[1] * MRL_LDT);
+    }
     if (MODE == MRL_MODE_FVP) {
       // R-forward, layer 1: Rh1 = act'(h1) * (x.V1 + vb1).  Same thread wrote H[i] just above.
       const float4* zs = reinterpret_cast<const float4*>(a.Zt + (size_t)tile * g.d[1] * MRL_LDT);
@@ -350,7 +422,7 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
       float4* dst = reinterpret_cast<float4*>(E);
       const float* vb1 = imgv + g.off_b[1];
       const int n4 = g.d[1] * (MRL_LDT / 4);
-      for (int i = tid; i < n4; i += MRL_MID_THREADS) {
+      for (int i = tid; i < n4; i += MRL_BWD_THREADS) {
         float4 z = zs[i];
         const float b = vb1[i / (MRL_LDT / 4)];
         if (L > 1) {
@@ -377,15 +449,10 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
         const bool last = (l == L);
         for (int job = ln.warp; job < nj; job += NW) {
           fwd_job(job, ln, RA, W, g.d[l - 1], HA, V, g.d[l - 1], g.ldw[l], g.d[l],
-                  [&](int c, int r, float4 v) {
-                    const float bb = vb[c];
-                    v.x += bb; v.y += bb; v.z += bb; v.w += bb;
-                    if (!last) {
-                      const float4 h = *reinterpret_cast<const float4*>(Hl + c * MRL_LDT + r);
-                      v.x *= dact_from_h<ACT>(h.x); v.y *= dact_from_h<ACT>(h.y);
-                      v.z *= dact_from_h<ACT>(h.z); v.w *= dact_from_h<ACT>(h.w);
-                    }
-                    *reinterpret_cast<float4*>(O + c * MRL_LDT + r) = v;
+                  [&](int c, int r, float v) {
+                    v += vb[c];
+                    if (!last) v *= dact_from_h<ACT>(Hl[c * MRL_LDT + r]);
+                    O[c * MRL_LDT + r] = v;
                   });
         }
         __syncthreads();
@@ -479,11 +546,8 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
       const float* WT = img + g.off_WT[l];
       for (int job = ln.warp; job < n_delta + n_grad + n_bias; job += NW) {
         if (job < n_delta) {       // delta_{l-1} = (delta_l W_l^T) * act'(h_{l-1})
-          fwd_job(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, [&](int c, int r, float4 v) {
-            const float4 h = *reinterpret_cast<const float4*>(Hp + c * MRL_LDT + r);
-            v.x *= dact_from_h<ACT>(h.x); v.y *= dact_from_h<ACT>(h.y);
-            v.z *= dact_from_h<ACT>(h.z); v.w *= dact_from_h<ACT>(h.w);
-            *reinterpret_cast<float4*>(Ep + c * MRL_LDT + r) = v;
+          fwd_job(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, [&](int c, int r, float v) {
+            Ep[c * MRL_LDT + r] = v * dact_from_h<ACT>(Hp[c * MRL_LDT + r]);
           });
         } else if (job < n_delta + n_grad) {
           grad_job(job - n_delta, n_nblk, ln, Hp, M, D, Nn, G + g.off_W[l], g.ldw[l]);
@@ -499,14 +563,14 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_backward_kernel(NetGeo
       for (int job = ln.warp; job < ((n1 + 7) >> 3); job += NW) bias_job(job, ln, D1, n1, G + g.off_b[1]);
       if (a.D1r) {
         float* out = a.D1r + (size_t)tile * MRL_TILE * g.n1p;
-        for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_MID_THREADS) {
+        for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_BWD_THREADS) {
           const int r = i / g.n1p, c = i % g.n1p;
           out[i] = (c < n1) ? D1[c * MRL_LDT + r] : 0.f;
         }
       }
       if (a.DG) {   // split-precision tensor-core operand: 4 consecutive timesteps of one column per thread
         const int nu = a.nu;
-        for (int i = tid; i < 16 * nu; i += MRL_MID_THREADS) {
+        for (int i = tid; i < 16 * nu; i += MRL_BWD_THREADS) {
           const int tq = i / nu, n = i % nu;       // timesteps 4*tq .. +3 of this tile
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (n < n1) v = *reinterpret_cast<const float4*>(D1 + n * MRL_LDT + 4 * tq);
@@ -555,7 +619,7 @@ static cudaError_t launch_bwd_t(const NetGeom& g, const MidBwdArgs& a, int n_sla
   cudaError_t e = cudaFuncSetAttribute(mid_backward_kernel<HEAD, ACT, MODE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  mid_backward_kernel<HEAD, ACT, MODE><<<n_slabs, MRL_MID_THREADS, sm, st>>>(g, a);
+  mid_backward_kernel<HEAD, ACT, MODE><<<n_slabs, MRL_BWD_THREADS, sm, st>>>(g, a);
   return cudaGetLastError();
 }
 
