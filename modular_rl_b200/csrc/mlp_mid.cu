@@ -65,45 +65,49 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// 2x2 mma tiles, three passes (lo.hi, hi.lo, hi.hi) so that consecutive MMAs hit different accumulators
-__device__ __forceinline__ void mma3_2x2(float (&acc)[2][2][4], const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4],
-                                         const uint32_t (&bh)[2][2], const uint32_t (&bl)[2][2]) {
+// MT x 2 mma tiles, three passes (lo.hi, hi.lo, hi.hi) so that consecutive MMAs hit different accumulators
+template <int MT>
+__device__ __forceinline__ void mma3_tiles(float (&acc)[MT][2][4], const uint32_t (&ah)[MT][4],
+                                           const uint32_t (&al)[MT][4], const uint32_t (&bh)[2][2],
+                                           const uint32_t (&bl)[2][2]) {
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], al[mi], bh[ni]);
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
 }
 
 // acc[mi][ni] += A^T-tile . B-tile over k in [0,K): A_T[k][r] feature-major activations (ld = MRL_LDT),
-// B[k][c] row-major weights (ld = ldb).  Warp tile 32 rows x 16 cols = 2 x 2 mma tiles.
-template <bool TAIL>
-__device__ __forceinline__ void mma_fwd_step(float (&acc)[2][2][4], const float* __restrict__ a, const float* __restrict__ b0,
-                                             const float* __restrict__ b1, int ldb4, int krem) {
+// B[k][c] row-major weights (ld = ldb).  Warp tile (16*MT) rows x 16 cols = MT x 2 mma tiles.
+template <int MT, bool TAIL>
+__device__ __forceinline__ void mma_fwd_step(float (&acc)[MT][2][4], const float* __restrict__ a,
+                                             const float* __restrict__ b0, const float* __restrict__ b1, int ldb4,
+                                             int krem) {
   // a -> A_T[k0 + t][r0 + g], b0/b1 -> B[k0 + t][c], ldb4 = 4 * ldb ; rows k0+t and k0+t+4
   const bool va = !TAIL || krem > 0, vb = !TAIL || krem > 4;   // krem = K - (k0 + t)
-  uint32_t bh[2][2], bl[2][2], ah[2][4], al[2][4];
+  uint32_t bh[2][2], bl[2][2], ah[MT][4], al[MT][4];
   split_tf32(va ? b0[0] : 0.f, bh[0][0], bl[0][0]);
   split_tf32(vb ? b0[ldb4] : 0.f, bh[0][1], bl[0][1]);
   split_tf32(va ? b1[0] : 0.f, bh[1][0], bl[1][0]);
   split_tf32(vb ? b1[ldb4] : 0.f, bh[1][1], bl[1][1]);
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi) {
+  for (int mi = 0; mi < MT; ++mi) {
     split_tf32(va ? a[16 * mi] : 0.f, ah[mi][0], al[mi][0]);
     split_tf32(va ? a[16 * mi + 8] : 0.f, ah[mi][1], al[mi][1]);
     split_tf32(vb ? a[4 * MRL_LDT + 16 * mi] : 0.f, ah[mi][2], al[mi][2]);
     split_tf32(vb ? a[4 * MRL_LDT + 16 * mi + 8] : 0.f, ah[mi][3], al[mi][3]);
   }
-  mma3_2x2(acc, ah, al, bh, bl);
+  mma3_tiles<MT>(acc, ah, al, bh, bl);
 }
-__device__ __forceinline__ void mma_fwd_acc(float (&acc)[2][2][4], const float* __restrict__ A,
+template <int MT>
+__device__ __forceinline__ void mma_fwd_acc(float (&acc)[MT][2][4], const float* __restrict__ A,
                                             const float* __restrict__ B, int K, int ldb, int r0, int c0,
                                             int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -114,31 +118,33 @@ __device__ __forceinline__ void mma_fwd_acc(float (&acc)[2][2][4], const float* 
   int k0 = 0;
 #pragma unroll 2
   for (; k0 + 8 <= K; k0 += 8) {
-    mma_fwd_step<false>(acc, a, b0, b1, ldb4, 8);
+    mma_fwd_step<MT, false>(acc, a, b0, b1, ldb4, 8);
     a += 8 * MRL_LDT; b0 += ldb8; b1 += ldb8;
   }
-  if (k0 < K) mma_fwd_step<true>(acc, a, b0, b1, ldb4, K - k0 - t);
+  if (k0 < K) mma_fwd_step<MT, true>(acc, a, b0, b1, ldb4, K - k0 - t);
 }
 
 // One warp job of  OUT[c][r] = epi(c, r, sum_k A1[k][r] B1[k][c] (+ sum_k A2[k][r] B2[k][c])).
-// job -> 32 rows x 16 cols; epi(c, r, value) is called once per output element.
-template <class Epi>
+// job -> (16*MT) rows x 16 cols; epi(c, r, value) is called once per output element.  MT = 1 doubles
+// the number of jobs of a phase that would otherwise leave warps idle.
+template <int MT, class Epi>
 __device__ __forceinline__ void fwd_job(int job, const Lane& ln, const float* A1, const float* B1, int K1,
                                         const float* A2, const float* B2, int K2, int ldb, int n_out,
                                         Epi epi) {
-  const int r0 = (job & 1) * 32, c0 = (job >> 1) * 16;
-  float acc[2][2][4];
+  constexpr int RB = MRL_TILE / (16 * MT);
+  const int r0 = (job % RB) * 16 * MT, c0 = (job / RB) * 16;
+  float acc[MT][2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-  mma_fwd_acc(acc, A1, B1, K1, ldb, r0, c0, ln.lane);
-  if (A2 != nullptr) mma_fwd_acc(acc, A2, B2, K2, ldb, r0, c0, ln.lane);
+  mma_fwd_acc<MT>(acc, A1, B1, K1, ldb, r0, c0, ln.lane);
+  if (A2 != nullptr) mma_fwd_acc<MT>(acc, A2, B2, K2, ldb, r0, c0, ln.lane);
   const int g = ln.lane >> 2, t = ln.lane & 3;
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) {
       const int r = r0 + 16 * mi + g, c = c0 + 8 * ni + 2 * t;
@@ -146,22 +152,25 @@ __device__ __forceinline__ void fwd_job(int job, const Lane& ln, const float* A1
       if (c + 1 < n_out) { epi(c + 1, r, acc[mi][ni][1]); epi(c + 1, r + 8, acc[mi][ni][3]); }
     }
 }
-__device__ __forceinline__ int fwd_jobs(int n_out) { return 2 * ((n_out + 15) >> 4); }
+__device__ __forceinline__ int fwd_jobs(int n_out, int mt) { return (MRL_TILE / (16 * mt)) * ((n_out + 15) >> 4); }
+// 16-row jobs when 32-row jobs would not give every warp work
+__device__ __forceinline__ int pick_mt(int n_out, int nwarps) { return fwd_jobs(n_out, 2) < nwarps ? 1 : 2; }
 
-// One warp job of  G[m][n] += sum_r A[m][r] * D[n][r]   (32 m x 16 n per job, K = the 64 timesteps)
+// One warp job of  G[m][n] += sum_r A[m][r] * D[n][r]   ((16*MT) m x 16 n per job, K = the 64 timesteps)
+template <int MT>
 __device__ __forceinline__ void grad_job(int job, int n_nblk, const Lane& ln, const float* __restrict__ A,
                                          int M, const float* __restrict__ D, int Nn, float* G, int ldg) {
-  const int m0 = (job / n_nblk) * 32, n0 = (job % n_nblk) * 16;
+  const int m0 = (job / n_nblk) * 16 * MT, n0 = (job % n_nblk) * 16;
   const int g = ln.lane >> 2, t = ln.lane & 3;
-  const float* ap[4];   // rows m0+g, +8, +16, +24 (clamped; out-of-range rows are never stored)
-  const float* dp[2];   // rows n0+g, +8
+  const float* ap[2 * MT];   // rows m0+g, +8, ... (clamped; out-of-range rows are never stored)
+  const float* dp[2];        // rows n0+g, +8
 #pragma unroll
-  for (int q = 0; q < 4; ++q) ap[q] = A + min(m0 + g + 8 * q, M - 1) * MRL_LDT + t;
+  for (int q = 0; q < 2 * MT; ++q) ap[q] = A + min(m0 + g + 8 * q, M - 1) * MRL_LDT + t;
 #pragma unroll
   for (int q = 0; q < 2; ++q) dp[q] = D + min(n0 + g + 8 * q, Nn - 1) * MRL_LDT + t;
-  float acc[2][2][4];
+  float acc[MT][2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -174,18 +183,18 @@ __device__ __forceinline__ void grad_job(int job, int n_nblk, const Lane& ln, co
       split_tf32(dp[ni][k0], bh[ni][0], bl[ni][0]);
       split_tf32(dp[ni][k0 + 4], bh[ni][1], bl[ni][1]);
     }
-    uint32_t ah[2][4], al[2][4];
+    uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
+    for (int mi = 0; mi < MT; ++mi) {
       split_tf32(ap[2 * mi][k0], ah[mi][0], al[mi][0]);
       split_tf32(ap[2 * mi + 1][k0], ah[mi][1], al[mi][1]);
       split_tf32(ap[2 * mi][k0 + 4], ah[mi][2], al[mi][2]);
       split_tf32(ap[2 * mi + 1][k0 + 4], ah[mi][3], al[mi][3]);
     }
-    mma3_2x2(acc, ah, al, bh, bl);
+    mma3_tiles<MT>(acc, ah, al, bh, bl);
   }
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
+  for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) {
       const int m = m0 + 16 * mi + g, n = n0 + 8 * ni + 2 * t;
@@ -273,14 +282,16 @@ __global__ void __launch_bounds__(MRL_MID_THREADS, 1) mid_forward_kernel(NetGeom
       float* O = act + g.off_act[l] * MRL_LDT;
       const float* W = img + g.off_W[l];
       const float* b = img + g.off_b[l];
-      const int nj = fwd_jobs(g.d[l]);
       const bool last = (l == L);
+      auto epi = [&](int c, int r, float v) {
+        v += b[c];
+        O[c * MRL_LDT + r] = last ? v : act_fn<ACT>(v);
+      };
+      const int mt = pick_mt(g.d[l], MRL_MID_THREADS / 32);
+      const int nj = fwd_jobs(g.d[l], mt);
       for (int job = ln.warp; job < nj; job += MRL_MID_THREADS / 32) {
-        fwd_job(job, ln, A, W, g.d[l - 1], nullptr, nullptr, 0, g.ldw[l], g.d[l],
-                [&](int c, int r, float v) {
-                  v += b[c];
-                  O[c * MRL_LDT + r] = last ? v : act_fn<ACT>(v);
-                });
+        if (mt == 1) fwd_job<1>(job, ln, A, W, g.d[l - 1], nullptr, nullptr, 0, g.ldw[l], g.d[l], epi);
+        else fwd_job<2>(job, ln, A, W, g.d[l - 1], nullptr, nullptr, 0, g.ldw[l], g.d[l], epi);
       }
       __syncthreads();
     }
@@ -445,21 +456,26 @@ __global__ void __launch_bounds__(MRL_BWD_THREADS, 1) mid_backward_kernel(NetGeo
         const float* W = img + g.off_W[l];
         const float* V = imgv + g.off_W[l];
         const float* vb = imgv + g.off_b[l];
-        const int nj = fwd_jobs(g.d[l]);
         const bool last = (l == L);
+        const bool fold = last && HEAD == MRL_HEAD_GAUSS;   // Fisher metric of DiagGauss folded into the epilogue
+        auto epi = [&](int c, int r, float v) {
+          v += vb[c];
+          if (!last) v *= dact_from_h<ACT>(Hl[c * MRL_LDT + r]);
+          if (fold) v = (r < nvalid) ? v * ivar[c] : 0.f;
+          O[c * MRL_LDT + r] = v;
+        };
+        const int mt = pick_mt(g.d[l], NW);
+        const int nj = fwd_jobs(g.d[l], mt);
         for (int job = ln.warp; job < nj; job += NW) {
-          fwd_job(job, ln, RA, W, g.d[l - 1], HA, V, g.d[l - 1], g.ldw[l], g.d[l],
-                  [&](int c, int r, float v) {
-                    v += vb[c];
-                    if (!last) v *= dact_from_h<ACT>(Hl[c * MRL_LDT + r]);
-                    O[c * MRL_LDT + r] = v;
-                  });
+          if (mt == 1) fwd_job<1>(job, ln, RA, W, g.d[l - 1], HA, V, g.d[l - 1], g.ldw[l], g.d[l], epi);
+          else fwd_job<2>(job, ln, RA, W, g.d[l - 1], HA, V, g.d[l - 1], g.ldw[l], g.d[l], epi);
         }
         __syncthreads();
       }
     }
     // ---- head: delta_L (un-normalised; 1/N is applied by the slab reduce)
-    if (tid < MRL_TILE) {
+    const bool head_folded = (MODE == MRL_MODE_FVP && HEAD == MRL_HEAD_GAUSS && L > 1);
+    if (!head_folded && tid < MRL_TILE) {
       const int r = tid;
       const bool valid = r < nvalid;
       const float* aux = a.aux ? a.aux + (size_t)tile * g.naux * MRL_LDT + r : nullptr;
@@ -532,25 +548,28 @@ __global__ void __launch_bounds__(MRL_BWD_THREADS, 1) mid_backward_kernel(NetGeo
         }
       }
     }
-    __syncthreads();
+    if (!head_folded) __syncthreads();
     // ---- reverse sweep: layers L..2 (weights in shared memory)
     for (int l = L; l >= 2; --l) {
       const float* D = E + g.off_act[l] * MRL_LDT;
       const float* Hp = H + g.off_act[l - 1] * MRL_LDT;
       float* Ep = E + g.off_act[l - 1] * MRL_LDT;
       const int M = g.d[l - 1], Nn = g.d[l];
-      const int n_delta = fwd_jobs(M);
       const int n_nblk = (Nn + 15) >> 4;
-      const int n_grad = ((M + 31) >> 5) * n_nblk;
       const int n_bias = (Nn + 7) >> 3;
+      // 16-row / 16-feature jobs when the 32-wide ones would leave warps without work
+      const int mt = (fwd_jobs(M, 2) + ((M + 31) >> 5) * n_nblk + n_bias) < NW ? 1 : 2;
+      const int n_delta = fwd_jobs(M, mt);
+      const int n_grad = ((M + 16 * mt - 1) / (16 * mt)) * n_nblk;
       const float* WT = img + g.off_WT[l];
+      auto epi = [&](int c, int r, float v) { Ep[c * MRL_LDT + r] = v * dact_from_h<ACT>(Hp[c * MRL_LDT + r]); };
       for (int job = ln.warp; job < n_delta + n_grad + n_bias; job += NW) {
         if (job < n_delta) {       // delta_{l-1} = (delta_l W_l^T) * act'(h_{l-1})
-          fwd_job(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, [&](int c, int r, float v) {
-            Ep[c * MRL_LDT + r] = v * dact_from_h<ACT>(Hp[c * MRL_LDT + r]);
-          });
+          if (mt == 1) fwd_job<1>(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, epi);
+          else fwd_job<2>(job, ln, D, WT, Nn, nullptr, nullptr, 0, g.ldt[l], M, epi);
         } else if (job < n_delta + n_grad) {
-          grad_job(job - n_delta, n_nblk, ln, Hp, M, D, Nn, G + g.off_W[l], g.ldw[l]);
+          if (mt == 1) grad_job<1>(job - n_delta, n_nblk, ln, Hp, M, D, Nn, G + g.off_W[l], g.ldw[l]);
+          else grad_job<2>(job - n_delta, n_nblk, ln, Hp, M, D, Nn, G + g.off_W[l], g.ldw[l]);
         } else {
           bias_job(job - n_delta - n_grad, ln, D, Nn, G + g.off_b[l]);
         }
