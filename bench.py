@@ -299,11 +299,24 @@ def main():
             kernels[name] = ent
         top = max((k for k in kernels if k in flops), key=lambda k: kernels[k]["ms_per_step"])
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tr["workload"] == wl.name and tr["timesteps"] == n_local and top in tr["kernels"]:
+                traffic = tr["kernels"][top]["read"] + tr["kernels"][top]["write"]
+        except Exception:
+            pass
+        pipes = {"mid_backward_fvp": "mma.sync TF32 x3 split precision (FP32-class accuracy) + FP32 epilogues",
+                 "mid_backward_grad": "mma.sync TF32 x3 split precision + FP32 heads",
+                 "mid_forward": "mma.sync TF32 x3 split precision + FP32 heads",
+                 "l1_forward": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, HBM-bound",
+                 "l1_grad": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, HBM-bound"}
         roof = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["algo_tflops"], "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": kernels[top]["algo_tflops"] / peak_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": kernels[top]["algo_tflops"] / peak_tf, "traffic": traffic,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
                                 "fallback 1.4 PFLOP/s sustained (of fallback)"),
-                "pipe": "fp32-fma (SIMT; no tensor-core path yet)", "fp32_fma_peak_tflops": fp32.value,
+                "pipe": pipes.get(top, ""), "flops_counted": "algorithmic FP32 flops; each costs 3 TF32 MMAs",
+                "fp32_fma_peak_tflops": fp32.value,
                 "frac_of_fp32_fma_peak": kernels[top]["algo_tflops"] / fp32.value,
                 "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
         cpu = None
