@@ -55,8 +55,10 @@ struct Lane {
 // with ~3x fewer issued instructions than the FFMA formulation (the chain is issue-bound).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   // round-to-nearest TF32 by integer arithmetic on the sign-magnitude bits (cvt.rna.tf32 costs ~4
-  // instructions on sm_100a): +half-ulp then truncate.  hi must be exact for the subtraction; for lo the
-  // tensor core's own truncation of the low 13 bits completes the rounding.
+  // instructions on sm_100a): add half an ulp, then truncate.  hi must be exact for the subtraction;
+  // for lo the tensor core's own truncation of the low 13 bits completes the rounding.  Rounding (not
+  // truncating) hi matters: with a truncated hi the dropped lo.lo term is one-signed, a 2e-7 relative
+  // bias that the CG solve amplifies (measured on the ill-conditioned golden case).
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
 }
@@ -593,8 +595,10 @@ __global__ void __launch_bounds__(MRL_BWD_THREADS, 1) mid_backward_kernel(NetGeo
           const int tq = i / nu, n = i % nu;       // timesteps 4*tq .. +3 of this tile
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (n < n1) v = *reinterpret_cast<const float4*>(D1 + n * MRL_LDT + 4 * tq);
-          const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-          const float4 l = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+          uint32_t hx, hy, hz, hw, lx, ly, lz, lw;   // integer split (see split_tf32); UMMA reads the top 19 bits
+          split_tf32(v.x, hx, lx); split_tf32(v.y, hy, ly); split_tf32(v.z, hz, lz); split_tf32(v.w, hw, lw);
+          const float4 h = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
+          const float4 l = make_float4(__uint_as_float(lx), __uint_as_float(ly), __uint_as_float(lz), __uint_as_float(lw));
           float* base = a.DG + ((size_t)tile * 8 + (tq >> 1)) * (2 * nu * 8) + (tq & 1) * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4;
           *reinterpret_cast<float4*>(base) = h;
           *reinterpret_cast<float4*>(base + nu * 8) = l;
