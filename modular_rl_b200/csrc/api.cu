@@ -128,14 +128,14 @@ static size_t dtype_size(int dt) { return (dt == MRL_F32 || dt == MRL_I32) ? 4 :
 
 // ======================================================================== batch
 struct mrl_batch {
-  int device = 0, ob_dim = 0, with_time = 0, xdim = 0, d0p = 0, d0r = 0;
+  int device = 0, ob_dim = 0, with_time = 0, xdim = 0, d0p = 0;
   long long N = 0, Nglobal = 0;
   int n_tiles = 0, n_paths = 0;
   double timestep_limit = 1.0;
   unsigned long long version = 0;
   int pol_head = -1, pol_dout = 0, naux_pol = 0;
   bool has_baseline = false, has_adv32 = false, has_ret = false;
-  DevBuf XG, XA, Xt, Xr, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
+  DevBuf XG, XA, aux_pol, aux_vf, offsets, terminated, tindex, stage, stage2, baseline, ret, adv, adv32, stats,
       gather;
 };
 
@@ -159,14 +159,13 @@ extern "C" int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int wit
   b->with_time = with_time_feature ? 1 : 0;
   b->xdim = ob_dim + b->with_time;
   b->d0p = round_up(b->xdim, 8);
-  b->d0r = round_up(b->xdim, 4);
   *out = b;
   return 0;
 }
 extern "C" int mrl_batch_destroy(mrl_batch* b) {
   if (!b) return 0;
   cudaSetDevice(b->device);
-  DevBuf* bufs[] = {&b->XG, &b->XA, &b->Xt, &b->Xr, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
+  DevBuf* bufs[] = {&b->XG, &b->XA, &b->aux_pol, &b->aux_vf, &b->offsets, &b->terminated, &b->tindex, &b->stage,
                     &b->stage2, &b->baseline, &b->ret, &b->adv, &b->adv32, &b->stats, &b->gather};
   for (DevBuf* d : bufs) d->release();
   delete b;
@@ -194,11 +193,6 @@ extern "C" int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long l
   b->pol_head = -1;
   const void* src;
   RET(stage_in(b->stage, ob, (size_t)N * ld * dtype_size(dtype), loc, st, &src));
-  CK(b->Xt.reserve((size_t)b->n_tiles * b->d0p * MRL_LDT * 4));
-  CK(b->Xr.reserve((size_t)b->n_tiles * MRL_TILE * b->d0r * 4));
-  CKL(launch_pack_tiles(src, dtype, ld, b->ob_dim, b->d0p, N, b->Xt.as<float>(), b->d0p, 0, b->n_tiles, st), 1);
-  CKL(launch_pack_rows(src, dtype, ld, b->ob_dim, N, b->Xr.as<float>(), b->d0r, (long long)b->n_tiles * MRL_TILE,
-                       st), 1);
   const long long n_mtiles = (b->n_tiles + 1) / 2;
   CK(b->XA.reserve(l1tc_xa_floats(b->d0p / 8, n_mtiles) * 4));
   CKL(launch_pack_xa(src, dtype, ld, b->ob_dim, N, b->XA.as<float>(), b->d0p / 8, n_mtiles, st), 1);
@@ -230,9 +224,8 @@ extern "C" int mrl_batch_set_paths(mrl_batch* b, const long long* offsets, const
   CK(b->tindex.reserve((size_t)b->N * 4));
   if (b->with_time) {
     if (!(timestep_limit > 0)) return fail("mrl_batch_set_paths: timestep_limit must be > 0");
-    CKL(launch_time_feature(b->offsets.as<long long>(), n_paths, b->N, timestep_limit, b->Xt.as<float>(), b->d0p,
-                            b->ob_dim, b->Xr.as<float>(), b->d0r, b->tindex.as<int>(), b->XA.as<float>(), b->d0p / 8,
-                            b->XG.as<float>(), (b->xdim + 127) / 128, st), 1);
+    CKL(launch_time_feature(b->offsets.as<long long>(), n_paths, b->N, timestep_limit, b->ob_dim, b->tindex.as<int>(),
+                            b->XA.as<float>(), b->d0p / 8, b->XG.as<float>(), (b->xdim + 127) / 128, st), 1);
   }
   return 0;
 }
@@ -549,7 +542,7 @@ extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, 
 struct mrl_net {
   int device = 0;
   NetGeom g;
-  DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, W1p, img, V1p, imgv, vflat, Z1, cache, D1r, part1, partm, loss_part, out32,
+  DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, img, imgv, vflat, Z1, cache, part1, partm, loss_part, out32,
       out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, scal, headout, stage;
   unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
   const mrl_batch* cache_batch = nullptr;
@@ -591,7 +584,6 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   cudaError_t e = cudaSuccess;
   auto R = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.reserve(bytes); };
   R(n->theta, P * 4); R(n->theta_prev, P * 4); R(n->theta_trial, P * 4); R(n->vflat, P * 4);
-  R(n->W1p, (size_t)n->g.d0p * n->g.n1p * 4); R(n->V1p, (size_t)n->g.d0p * n->g.n1p * 4);
   R(n->img, (size_t)n->g.img_floats * 4); R(n->imgv, (size_t)n->g.img_floats * 4);
   R(n->WBt, l1tc_wb_floats(n->g) * 4); R(n->WBv, l1tc_wb_floats(n->g) * 4);
   R(n->out32, P * 4); R(n->out64, P * 8); R(n->g32, P * 4);
@@ -612,8 +604,8 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->W1p, &n->img, &n->V1p, &n->imgv, &n->vflat,
-                    &n->Z1, &n->cache, &n->D1r, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
+  DevBuf* bufs[] = {&n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
+                    &n->Z1, &n->cache, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->scal,
                     &n->headout, &n->stage};
   for (DevBuf* d : bufs) d->release();
@@ -639,8 +631,7 @@ void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st) {
 }
 
 static int repack(mrl_net* n, cudaStream_t st) {
-  CKP(PK_PACK, launch_pack_params(n->g, n->theta.as<float>(), n->W1p.as<float>(), n->img.as<float>(), st), 1);
-  CKP(PK_PACK, launch_pack_wb(n->g, n->theta.as<float>(), n->WBt.as<float>(), st), 1);
+  CKP(PK_PACK, launch_pack_params(n->g, n->theta.as<float>(), n->img.as<float>(), n->WBt.as<float>(), st), 1);
   n->params_version++;
   return 0;
 }
@@ -670,20 +661,28 @@ extern "C" int mrl_net_get_params(mrl_net* n, float* theta, int loc, void* strea
   return 0;
 }
 
-// debugging aid only: MRL_L1_SIMT=1 routes layer 1 through the FP32 SIMT kernels instead of tcgen05
-static bool use_simt_l1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MRL_L1_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 // ------------------------------------------------------------------------ passes
 struct Plan { int slab_tiles, n_slabs; };
 static Plan plan_for(const mrl_batch* b) {
+  // One CTA per slab; a slab is <= MRL_MAX_SLAB_TILES tiles (fp32 accumulation span).  Small batches get
+  // one wave of CTAs; large ones the slab size with the fewest tile-rounds on this GPU's SM count.
+  static int sms = 0;
+  if (sms == 0) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device) != cudaSuccess || sms <= 0) sms = 148;
+  }
   Plan p;
-  p.slab_tiles = (b->n_tiles + 295) / 296;
+  if (b->n_tiles <= sms * MRL_MAX_SLAB_TILES) {
+    p.slab_tiles = (b->n_tiles + sms - 1) / sms;
+  } else {
+    long long best = -1;
+    p.slab_tiles = MRL_MAX_SLAB_TILES;
+    for (int s = MRL_MAX_SLAB_TILES; s >= 8; --s) {
+      const long long slabs = (b->n_tiles + s - 1) / s;
+      const long long rounds = (slabs + sms - 1) / sms * s;
+      if (best < 0 || rounds < best) { best = rounds; p.slab_tiles = s; }
+    }
+  }
   if (p.slab_tiles < 1) p.slab_tiles = 1;
-  if (p.slab_tiles > MRL_MAX_SLAB_TILES) p.slab_tiles = MRL_MAX_SLAB_TILES;
   p.n_slabs = (b->n_tiles + p.slab_tiles - 1) / p.slab_tiles;
   return p;
 }
@@ -711,7 +710,6 @@ static int reserve_ws(mrl_net* n, const mrl_batch* b, const Plan& pl) {
   const NetGeom& g = n->g;
   CK(n->Z1.reserve((size_t)b->n_tiles * g.d[1] * MRL_LDT * 4));
   CK(n->cache.reserve((size_t)b->n_tiles * g.act_rows * MRL_LDT * 4));
-  CK(n->D1r.reserve((size_t)b->n_tiles * MRL_TILE * g.n1p * 4));
   CK(n->DG.reserve(l1tc_dg_floats(g, b->n_tiles) * 4));
   CK(n->part1.reserve((size_t)pl.n_slabs * g.d[0] * g.n1p * 4));
   CK(n->partm.reserve((size_t)pl.n_slabs * g.pmid * 4));
@@ -727,10 +725,7 @@ static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_ca
   RET(reserve_ws(n, b, pl));
   // the batch tile has b->d0p feature rows; the net consumes the first g.d0p of them
   NetGeom gl = g;
-  if (use_simt_l1())
-    CKP(PK_L1F, launch_l1_forward_strided(gl, b->Xt.as<float>(), b->d0p, n->W1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
-  else
-    CKP(PK_L1F, launch_l1_forward_tc(gl, b->XA.as<float>(), b->d0p / 8, n->WBt.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
+  CKP(PK_L1F, launch_l1_forward_tc(gl, b->XA.as<float>(), b->d0p / 8, n->WBt.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
   MidFwdArgs a;
   a.img = n->img.as<float>();
   a.Zt = n->Z1.as<float>();
@@ -770,21 +765,15 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.imgv = nullptr;
   a.Zt = nullptr;
   if (mode == MRL_MODE_FVP) {
-    CKP(PK_PACK, launch_pack_params(g, v_dev, n->V1p.as<float>(), n->imgv.as<float>(), st), 1);
-    if (use_simt_l1()) {
-      CKP(PK_L1F, launch_l1_forward_strided(g, b->Xt.as<float>(), b->d0p, n->V1p.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
-    } else {
-      CKP(PK_PACK, launch_pack_wb(g, v_dev, n->WBv.as<float>(), st), 1);
-      CKP(PK_L1F, launch_l1_forward_tc(g, b->XA.as<float>(), b->d0p / 8, n->WBv.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
-    }
+    CKP(PK_PACK, launch_pack_params(g, v_dev, n->imgv.as<float>(), n->WBv.as<float>(), st), 1);
+    CKP(PK_L1F, launch_l1_forward_tc(g, b->XA.as<float>(), b->d0p / 8, n->WBv.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
     a.imgv = n->imgv.as<float>();
     a.Zt = n->Z1.as<float>();
   }
   a.aux = mode == MRL_MODE_GRAD ? aux_of(n, b) : nullptr;
   a.cache = n->cache.as<float>();
   a.coef = coef_dev;
-  a.D1r = use_simt_l1() ? n->D1r.as<float>() : nullptr;
-  a.DG = use_simt_l1() ? nullptr : n->DG.as<float>();
+  a.DG = n->DG.as<float>();
   a.nu = l1tc_nu(g);
   a.partm = n->partm.as<float>();
   a.N = b->N;
@@ -793,12 +782,8 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.mode = mode;
   a.reverse_kl = reverse_kl;
   CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
-  if (use_simt_l1())
-    CKP(PK_L1G, launch_l1_grad(g, b->Xr.as<float>(), b->d0r, n->D1r.as<float>(), n->part1.as<float>(), pl.slab_tiles,
-                               b->n_tiles, pl.n_slabs, st), 1);
-  else
-    CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
-                                  pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
+  CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
+                                pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
   const int world = world_of(n);
   // terms that are not sums over timesteps are divided by `world` so that the all-reduce restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;

@@ -1,0 +1,236 @@
+// Parameter packing, batch repacking and the fp64 slab reduce.
+//
+// theta (the reference's flat vector, core.py:518-557) is expanded once per set_params into the
+// shared-memory image the fused chain loads ([biases | logstd | W2..WL | W2^T..WL^T]) and into the
+// split-precision tensor-core operand of layer 1 (see mlp_l1_tc.cu).  Side inputs of the batch
+// (advantages, actions, old probabilities, value targets) are repacked into the tile-major layout.
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------
+// theta (flat, reference order) -> the shared-memory image and the layer-1 tensor-core operand
+// WB [kg][hi|lo][khalf][ngroup][8][4] (K-major UMMA core-matrix order, hi = rna_tf32(x), lo = rna_tf32(x - hi)).
+__global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, float* __restrict__ img,
+                                   float* __restrict__ WB, int nu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_wb = g.d0p * nu;
+  if (i < n_wb) {
+    const int k = i / nu, n = i % nu;
+    const float x = (k < g.d[0] && n < g.d[1]) ? theta[g.off_flat_W[1] + k * g.d[1] + n] : 0.f;
+    const float h = tf32_rna(x);
+    float* base = WB + (size_t)(k >> 3) * (2 * nu * 8) + ((k & 7) >> 2) * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);
+    base[0] = h;
+    base[nu * 8] = tf32_rna(x - h);
+    return;
+  }
+  const int j = i - n_wb;
+  if (j >= g.img_floats) return;
+  float v = 0.f;
+  if (j < g.bias_floats) {
+    if (j >= g.off_pm_logstd) {
+      const int q = j - g.off_pm_logstd;
+      if (g.off_flat_logstd >= 0 && q < g.d[g.L]) v = theta[g.off_flat_logstd + q];
+    } else {
+      for (int l = g.L; l >= 1; --l)
+        if (j >= g.off_b[l]) {
+          const int q = j - g.off_b[l];
+          if (q < g.d[l]) v = theta[g.off_flat_b[l] + q];
+          break;
+        }
+    }
+  } else if (j < g.bw_floats) {
+    for (int l = g.L; l >= 2; --l)
+      if (j >= g.off_W[l]) {
+        const int q = j - g.off_W[l];
+        const int row = q / g.ldw[l], col = q % g.ldw[l];
+        if (col < g.d[l]) v = theta[g.off_flat_W[l] + row * g.d[l] + col];
+        break;
+      }
+  } else {
+    for (int l = g.L; l >= 2; --l)
+      if (j >= g.off_WT[l]) {
+        const int q = j - g.off_WT[l];
+        const int row = q / g.ldt[l], col = q % g.ldt[l];  // row = output unit, col = input unit
+        if (col < g.d[l - 1]) v = theta[g.off_flat_W[l] + col * g.d[l] + row];
+        break;
+      }
+  }
+  img[j] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// flat[i] = scale * sum_slabs(partials) (+ l2c2 * theta[i]); on the logstd block an Fvp is vls * v[i]
+// (fvp[logstd] = 2 v_logstd is data independent)
+// fp64 accumulation in a fixed slab order -> deterministic.
+#define RED_PX 32
+#define RED_SY 8
+__global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
+    NetGeom g, const float* __restrict__ part1, const float* __restrict__ partm, int n_slabs, double scale,
+    const float* __restrict__ theta, double l2c2, const float* __restrict__ vlogstd_src, double vls,
+    float* __restrict__ out32, double* __restrict__ out64) {
+  __shared__ double acc[RED_SY][RED_PX];
+  const int px = threadIdx.x, sy = threadIdx.y;
+  const int i = blockIdx.x * RED_PX + px;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < g.P) {
+    const float* src = nullptr;
+    size_t stride = 0;
+    if (i < g.off_flat_b[1]) {
+      const int k = i / g.d[1], n = i % g.d[1];
+      src = part1 + (size_t)k * g.n1p + n;
+      stride = (size_t)g.d[0] * g.n1p;
+    } else if (g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) {
+      src = partm + g.off_pm_logstd + (i - g.off_flat_logstd);
+      stride = g.pmid;
+    } else {
+      for (int l = g.L; l >= 1; --l) {
+        if (i >= g.off_flat_b[l]) {
+          src = partm + g.off_b[l] + (i - g.off_flat_b[l]);
+          break;
+        }
+        if (i >= g.off_flat_W[l]) {
+          const int q = i - g.off_flat_W[l];
+          src = partm + g.off_W[l] + (q / g.d[l]) * g.ldw[l] + (q % g.d[l]);
+          break;
+        }
+      }
+      stride = g.pmid;
+    }
+    int sl = sy;   // this thread's slabs: sy, sy+8, ... (two chains for memory-level parallelism)
+    for (; sl + RED_SY < n_slabs; sl += 2 * RED_SY) {
+      s0 += (double)src[(size_t)sl * stride];
+      s1 += (double)src[(size_t)(sl + RED_SY) * stride];
+    }
+    if (sl < n_slabs) s0 += (double)src[(size_t)sl * stride];
+  }
+  acc[sy][px] = s0 + s1;
+  __syncthreads();
+  if (sy == 0 && i < g.P) {
+    double r = 0.0;
+#pragma unroll
+    for (int q = 0; q < RED_SY; ++q) r += acc[q][px];   // fixed order -> deterministic
+    r *= scale;
+    if (vlogstd_src != nullptr && g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) r = vls * (double)vlogstd_src[i];
+    if (theta != nullptr) r += l2c2 * (double)theta[i];
+    if (out32) out32[i] = (float)r;
+    if (out64) out64[i] = r;
+  }
+}
+
+// loss partials [n_slabs][4] doubles -> out[4] = scale * sums (single block)
+__global__ void reduce_losses_kernel(const double* __restrict__ parts, int n_slabs, double scale,
+                                     double* __restrict__ out) {
+  __shared__ double scratch[32];
+  for (int q = 0; q < 4; ++q) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_slabs; i += blockDim.x) s += parts[(size_t)i * 4 + q];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[q] = s * scale;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Batch repacking (once per bind).  src is the caller's row-major array [N x ncols] (float or
+// double, leading dimension ld); dst is tile-major; feature rows [row_off, row_off+ncols_out)
+// of each tile are written, columns >= ncols and timesteps >= N as zeros.
+template <typename T>
+__global__ void pack_tiles_kernel(const T* __restrict__ src, long long ld, int ncols, int ncols_out,
+                                  long long N, float* __restrict__ dst, int rows_per_tile, int row_off) {
+  __shared__ float tr[MRL_TILE][33];
+  const int tile = blockIdx.x;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int r = ty; r < MRL_TILE; r += 8) {
+    const long long n = (long long)tile * MRL_TILE + r;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (n < N && c < ncols) v = (float)src[n * ld + c];
+    tr[r][tx] = v;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc;
+    if (c < ncols_out) {
+      float* d = dst + ((size_t)tile * rows_per_tile + row_off + c) * MRL_LDT;
+      d[tx] = tr[tx][cc];
+      d[tx + 32] = tr[tx + 32][cc];
+    }
+  }
+}
+
+// NnVf.preproc (core.py:659-660): feature `col` = (t - offsets[path(t)]) / timestep_limit, written into
+// both tensor-core operand copies of the observations (mlp_l1_tc.cu layouts).  Also writes the
+// within-path index (int32) for the bit-exact integer contract.
+__global__ void time_feature_kernel(const long long* __restrict__ offsets, int n_paths, long long N,
+                                    double timestep_limit, int col, int* __restrict__ tindex,
+                                    float* __restrict__ XA, int xa_kgroups, float* __restrict__ XG,
+                                    int xg_ftiles) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  int lo = 0, hi = n_paths;  // offsets[lo] <= t < offsets[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= t) lo = mid; else hi = mid;
+  }
+  const long long k = t - offsets[lo];
+  const float f = (float)((double)k / timestep_limit);
+  if (tindex) tindex[t] = (int)k;
+  const float h = tf32_rna(f), l = tf32_rna(f - h);
+  {  // forward operand: [mtile][kg][hi|lo][khalf][mgroup][8 timesteps][4 features]
+    const long long mt = t / 128;
+    const int m = (int)(t % 128);
+    float* base = XA + ((size_t)mt * xa_kgroups + (col >> 3)) * 2048 + ((col & 7) >> 2) * 512 + (m >> 3) * 32 + (m & 7) * 4 + (col & 3);
+    base[0] = h;
+    base[1024] = l;
+  }
+  {  // gradient operand: [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps]
+    const int fm = col % 128;
+    float* base = XG + ((size_t)(t >> 3) * xg_ftiles + col / 128) * 2048 + (int)((t & 7) >> 2) * 512 + (fm >> 3) * 32 +
+                  (fm & 7) * 4 + (int)(t & 3);
+    base[0] = h;
+    base[1024] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img, float* WB, cudaStream_t st) {
+  const int nu = l1tc_nu(g);
+  const int n = g.d0p * nu + g.img_floats;
+  pack_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(g, theta, img, WB, nu);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
+                                   double scale, const float* theta, double l2c2, const float* vflat, double vls,
+                                   float* out32, double* out64, cudaStream_t st) {
+  reduce_partials_kernel<<<(g.P + RED_PX - 1) / RED_PX, dim3(RED_PX, RED_SY), 0, st>>>(
+      g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32, out64);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_losses(const double* parts, int n_slabs, double scale, double* out, cudaStream_t st) {
+  reduce_losses_kernel<<<1, 256, 0, st>>>(parts, n_slabs, scale, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncols, int ncols_out, long long N,
+                              float* dst, int rows_per_tile, int row_off, int n_tiles, cudaStream_t st) {
+  dim3 grid(n_tiles, (ncols_out + 31) / 32), block(32, 8);
+#define PT(T) pack_tiles_kernel<T><<<grid, block, 0, st>>>((const T*)src, ld, ncols, ncols_out, N, dst, rows_per_tile, row_off)
+  switch (dtype) {   // MRL_F32, MRL_F64, MRL_I32, MRL_I64
+    case 0: PT(float); break;
+    case 1: PT(double); break;
+    case 2: PT(int); break;
+    default: PT(long long); break;
+  }
+#undef PT
+  return cudaGetLastError();
+}
+
+cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, int col, int* tindex,
+                                float* XA, int xa_kgroups, float* XG, int xg_ftiles, cudaStream_t st) {
+  time_feature_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(offsets, n_paths, N, limit, col, tindex, XA,
+                                                                   xa_kgroups, XG, xg_ftiles);
+  return cudaGetLastError();
+}

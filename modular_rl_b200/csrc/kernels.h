@@ -2,23 +2,16 @@
 #pragma once
 #include "common.cuh"
 
-// ---- mlp_l1.cu
-cudaError_t launch_l1_forward_strided(const NetGeom& g, const float* Xt, int x_rows, const float* Bp, float* Zt,
-                                      int n_tiles, cudaStream_t st);
-cudaError_t launch_l1_grad(const NetGeom& g, const float* Xr, int d0r, const float* D1r, float* part1,
-                           int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st);
-cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* W1p, float* img, cudaStream_t st);
+// ---- batch_params.cu
+cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img, float* WB, cudaStream_t st);
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
                                    float* out32, double* out64, cudaStream_t st);
 cudaError_t launch_reduce_losses(const double* parts, int n_slabs, double scale, double* out, cudaStream_t st);
 cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncols, int ncols_out, long long N,
                               float* dst, int rows_per_tile, int row_off, int n_tiles, cudaStream_t st);
-cudaError_t launch_pack_rows(const void* src, int dtype, long long ld, int ncols, long long N, float* dst,
-                             int ldo, long long rows_out, cudaStream_t st);
-cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, float* Xt,
-                                int d0p, int col, float* Xr, int d0r, int* tindex, float* XA, int xa_kgroups,
-                                float* XG, int xg_ftiles, cudaStream_t st);
+cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, int col, int* tindex,
+                                float* XA, int xa_kgroups, float* XG, int xg_ftiles, cudaStream_t st);
 
 // ---- mlp_l1_tc.cu  (tcgen05 / TMEM layer-1 GEMMs, 3xTF32)
 int l1tc_nu(const NetGeom& g);
@@ -29,7 +22,6 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
                                  int n_tiles, cudaStream_t st);
 cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, long long N, float* XA, int xa_kgroups,
                            long long n_mtiles, cudaStream_t st);
-cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cudaStream_t st);
 size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles);
 size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles);
 cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, long long N, float* XG, int xg_ftiles,
@@ -55,8 +47,7 @@ struct MidBwdArgs {
   const float* aux;
   const float* cache;
   const double* coef;  // device: {c_surr, c_kl} (gradient mode)
-  float* D1r;          // out: delta_1 row-major [n_tiles*64][n1p]   (SIMT layer-1 gradient; may be null)
-  float* DG;           // out: delta_1 as the tcgen05 B operand [tg][hi|lo][khalf][ngroup][8][4] (may be null)
+  float* DG;           // out: delta_1 as the tcgen05 B operand [tg][hi|lo][khalf][ngroup][8][4] 
   int nu;              // padded layer-1 width of DG
   float* partm;        // out: [n_slabs][pmid]
   long long N;

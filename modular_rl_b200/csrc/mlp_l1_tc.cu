@@ -326,20 +326,6 @@ __global__ void pack_xa_kernel(const T* __restrict__ src, long long ld, int ncol
   *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
-// one feature column (e.g. the time feature) rewritten in place from a flat float array
-__global__ void pack_xa_column_kernel(const float* __restrict__ col, long long N, float* __restrict__ XA, int xa_kgroups,
-                                      int c) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N) return;
-  const int kg = c >> 3, khalf = (c & 7) >> 2, kq = c & 3;
-  const long long mt = t / TC_M;
-  const int m = (int)(t % TC_M);
-  const float x = col[t], h = tf32_rna(x);
-  float* base = XA + ((size_t)mt * xa_kgroups + kg) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4 + kq;
-  base[0] = h;
-  base[TC_M * 8] = tf32_rna(x - h);
-}
-
 // src row-major [N x ld] -> XG [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps].
 // One thread per (4 consecutive timesteps, feature).
 template <typename T>
@@ -363,20 +349,6 @@ __global__ void pack_xg_kernel(const T* __restrict__ src, long long ld, int ncol
   float* base = XG + ((size_t)tg * xg_ftiles + ft) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (fm >> 3) * 32 + (fm & 7) * 4;
   *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-// theta (flat) layer-1 kernel [d0 x d1] -> WB [kg][hi|lo][khalf][ngroup][8][4]
-__global__ void pack_wb_kernel(NetGeom g, const float* __restrict__ theta, float* __restrict__ WB, int nu) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = g.d0p * nu;
-  if (i >= total) return;
-  const int k = i / nu, n = i % nu;
-  const float x = (k < g.d[0] && n < g.d[1]) ? theta[g.off_flat_W[1] + k * g.d[1] + n] : 0.f;
-  const float h = tf32_rna(x);
-  const int kg = k >> 3, khalf = (k & 7) >> 2, kq = k & 3;
-  float* base = WB + (size_t)kg * (2 * nu * 8) + khalf * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4 + kq;
-  base[0] = h;
-  base[nu * 8] = tf32_rna(x - h);
 }
 
 // ------------------------------------------------------------------------------------ launchers
@@ -414,17 +386,6 @@ cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, 
   else pack_xa_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, ld, ncols, N, XA, xa_kgroups, rows_out);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_xa_column(const float* col, long long N, float* XA, int xa_kgroups, int c, cudaStream_t st) {
-  pack_xa_column_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(col, N, XA, xa_kgroups, c);
-  return cudaGetLastError();
-}
-cudaError_t launch_pack_wb(const NetGeom& g, const float* theta, float* WB, cudaStream_t st) {
-  const int nu = l1tc_nu(g);
-  const int total = g.d0p * nu;
-  pack_wb_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, theta, WB, nu);
-  return cudaGetLastError();
-}
-
 size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles) { return (size_t)n_tiles * 8 * xg_ftiles * 2 * TC_M * 8; }
 size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles) { return (size_t)n_tiles * 8 * 2 * l1tc_nu(g) * 8; }
 

@@ -578,17 +578,10 @@ __global__ void __launch_bounds__(MRL_BWD_THREADS, 1) mid_backward_kernel(NetGeo
       }
       __syncthreads();
     }
-    {  // layer 1: bias gradient here, weight gradient by l1_grad_kernel from delta_1 (row-major)
+    {  // layer 1: bias gradient here; delta_1 goes out as the tensor-core operand of l1_grad_tc_kernel
       const float* D1 = E;  // off_act[1] == 0
       const int n1 = g.d[1];
       for (int job = ln.warp; job < ((n1 + 7) >> 3); job += NW) bias_job(job, ln, D1, n1, G + g.off_b[1]);
-      if (a.D1r) {
-        float* out = a.D1r + (size_t)tile * MRL_TILE * g.n1p;
-        for (int i = tid; i < MRL_TILE * g.n1p; i += MRL_BWD_THREADS) {
-          const int r = i / g.n1p, c = i % g.n1p;
-          out[i] = (c < n1) ? D1[c * MRL_LDT + r] : 0.f;
-        }
-      }
       if (a.DG) {   // split-precision tensor-core operand: 4 consecutive timesteps of one column per thread
         const int nu = a.nu;
         for (int i = tid; i < 16 * nu; i += MRL_BWD_THREADS) {
