@@ -543,7 +543,7 @@ struct mrl_net {
   int device = 0;
   NetGeom g;
   DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, img, imgv, vflat, Z1, cache, part1, partm, loss_part, out32,
-      out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, scal, headout, stage;
+      out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, cgscratch, scal, headout, stage;
   unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
   const mrl_batch* cache_batch = nullptr;
   mrl_comm* comm = nullptr;
@@ -589,10 +589,11 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   R(n->out32, P * 4); R(n->out64, P * 8); R(n->g32, P * 4);
   R(n->cg_b, P * 8); R(n->cg_x, P * 8); R(n->cg_r, P * 8); R(n->cg_p, P * 8);
   R(n->p32, P * 4); R(n->x32, P * 4); R(n->fullstep, P * 8);
-  R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8);
+  R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8); R(n->cgscratch, 80 * 8);
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_scal, 32 * 8);
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_cg, sizeof(CgState));
   if (e == cudaSuccess) e = cudaMemset(n->theta.p, 0, P * 4);
+  if (e == cudaSuccess) e = cudaMemset(n->cgscratch.p, 0, 80 * 8);
   if (e != cudaSuccess) {
     mrl_net_destroy(n);
     return fail("mrl_net_create: %s", cudaGetErrorString(e));
@@ -606,7 +607,7 @@ extern "C" int mrl_net_destroy(mrl_net* n) {
   cudaSetDevice(n->device);
   DevBuf* bufs[] = {&n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
-                    &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->scal,
+                    &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->cgscratch, &n->scal,
                     &n->headout, &n->stage};
   for (DevBuf* d : bufs) d->release();
   if (n->h_scal) cudaFreeHost(n->h_scal);
@@ -958,7 +959,8 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
     RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
                       n->out64.as<double>(), st));
     CKP(PK_CG, launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
-                       n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(), st), 1);
+                       n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(),
+                       n->cgscratch.as<double>(), st), 3);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
   RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),

@@ -4,7 +4,7 @@
 // trpo.py:150 with every scalar kept on the device, so the ten CG iterations enqueue without a
 // host round trip.  The reference's early `break` (trpo.py:192-193) becomes a sticky `done`
 // flag: once set, later cg_step launches return without touching x, which leaves the solution
-// bit-identical to a loop that stopped.  One CTA; dot products by warp shuffles, fp64.
+// bit-identical to a loop that stopped.  dot products by warp shuffles, fp64.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,26 +36,53 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_init_kernel(int P, const float
   }
 }
 
-// z32 = Fvp(p32) without damping (already all-reduced); A p = z + damping * p  (trpo.py:86-92)
-__global__ void __launch_bounds__(VEC_THREADS) cg_step_kernel(int P, const float* __restrict__ z32,
-                                                              double damping, double tol, double* x, double* r,
-                                                              double* p, float* p32, CgState* s) {
+// One CG iteration (trpo.py:179-193) as three small multi-CTA kernels.  A single CTA is bound by one
+// SM's L2 bandwidth (~30 us for the 44 484-parameter Humanoid vectors); CG_CTAS CTAs cut that to a few
+// microseconds each.  Dot products: per-CTA partials, then EVERY CTA sums the partials in the same fixed
+// order, so all CTAs (and all ranks) derive bit-identical alpha / beta without atomics.
+//   z32 = Fvp(p32) without damping (already all-reduced); A p = z + damping * p  (trpo.py:86-92)
+#define CG_CTAS 32
+#define CG_THREADS 256
+
+__device__ __forceinline__ void cg_span(int P, int& lo, int& hi) {
+  const int per = (P + CG_CTAS - 1) / CG_CTAS;
+  lo = blockIdx.x * per;
+  hi = min(P, lo + per);
+}
+__device__ __forceinline__ double cg_sum_parts(const double* __restrict__ parts) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < CG_CTAS; ++i) s += parts[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) cg_dot_pz_kernel(int P, const float* __restrict__ z32, double damping,
+                                                               const double* __restrict__ p, const CgState* s,
+                                                               double* __restrict__ parts) {
   __shared__ double scratch[32];
-  __shared__ double sh[2];
   if (s->done) return;
-  const double rdotr = s->rdotr;
+  int lo, hi;
+  cg_span(P, lo, hi);
   double pz = 0.0;
-  for (int i = threadIdx.x; i < P; i += VEC_THREADS) {
+  for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pi = p[i];
     pz += pi * ((double)z32[i] + damping * pi);
   }
   pz = block_sum(pz, scratch);
-  if (threadIdx.x == 0) sh[0] = pz;
-  __syncthreads();
-  pz = sh[0];
-  const double alpha = rdotr / pz;
+  if (threadIdx.x == 0) parts[blockIdx.x] = pz;
+}
+__global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int P, const float* __restrict__ z32, double damping,
+                                                                  double* __restrict__ x, double* __restrict__ r,
+                                                                  const double* __restrict__ p, const CgState* s,
+                                                                  const double* __restrict__ parts_pz,
+                                                                  double* __restrict__ parts_rr) {
+  __shared__ double scratch[32];
+  if (s->done) return;
+  const double alpha = s->rdotr / cg_sum_parts(parts_pz);
+  int lo, hi;
+  cg_span(P, lo, hi);
   double nr = 0.0;
-  for (int i = threadIdx.x; i < P; i += VEC_THREADS) {
+  for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pi = p[i];
     const double zi = (double)z32[i] + damping * pi;
     x[i] += alpha * pi;
@@ -64,19 +91,34 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_step_kernel(int P, const float
     nr += ri * ri;
   }
   nr = block_sum(nr, scratch);
-  if (threadIdx.x == 0) sh[1] = nr;
-  __syncthreads();
-  nr = sh[1];
+  if (threadIdx.x == 0) parts_rr[blockIdx.x] = nr;
+}
+// p = r + (newrdotr/rdotr) p ; the scalar state is advanced by the LAST CTA to finish reading it
+__global__ void __launch_bounds__(CG_THREADS) cg_update_p_kernel(int P, double tol, const double* __restrict__ r,
+                                                                 double* __restrict__ p, float* __restrict__ p32,
+                                                                 CgState* s, const double* __restrict__ parts_pz,
+                                                                 const double* __restrict__ parts_rr,
+                                                                 unsigned int* __restrict__ ticket) {
+  if (s->done) return;
+  const double rdotr = s->rdotr;
+  const double pz = cg_sum_parts(parts_pz), nr = cg_sum_parts(parts_rr);
   const double beta = nr / rdotr;
-  for (int i = threadIdx.x; i < P; i += VEC_THREADS) {
+  int lo, hi;
+  cg_span(P, lo, hi);
+  for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pn = r[i] + beta * p[i];
     p[i] = pn;
     p32[i] = (float)pn;
   }
+  __syncthreads();   // every thread of this CTA has read s->rdotr / s->done
   if (threadIdx.x == 0) {
-    s->pz = pz; s->alpha = alpha; s->beta = beta; s->rdotr = nr;
-    s->iters += 1;
-    if (nr < tol) s->done = 1;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == CG_CTAS - 1) {   // all CTAs are past their reads of the state
+      *ticket = 0;
+      s->pz = pz; s->alpha = rdotr / pz; s->beta = beta; s->rdotr = nr;
+      s->iters += 1;
+      if (nr < tol) s->done = 1;
+    }
   }
 }
 
@@ -137,8 +179,14 @@ cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* 
   return cudaGetLastError();
 }
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
-                           float* p32, CgState* s, cudaStream_t st) {
-  cg_step_kernel<<<1, VEC_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s);
+                           float* p32, CgState* s, double* scratch, cudaStream_t st) {
+  // scratch: [CG_CTAS] pz partials, [CG_CTAS] rr partials, then one uint32 ticket (zero-initialised by the caller)
+  double* parts_pz = scratch;
+  double* parts_rr = scratch + CG_CTAS;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 2 * CG_CTAS);
+  cg_dot_pz_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, p, s, parts_pz);
+  cg_update_xr_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, x, r, p, s, parts_pz, parts_rr);
+  cg_update_p_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, tol, r, p, p32, s, parts_pz, parts_rr, ticket);
   return cudaGetLastError();
 }
 cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st) {
