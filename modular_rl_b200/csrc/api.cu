@@ -674,10 +674,11 @@ static Plan plan_for(const mrl_batch* b) {
   Plan p;
   if (b->n_tiles <= sms * MRL_MAX_SLAB_TILES) {
     p.slab_tiles = (b->n_tiles + sms - 1) / sms;
+    p.slab_tiles += p.slab_tiles & 1;   // even: the chain kernel walks pairs of tiles that must not straddle slabs
   } else {
     long long best = -1;
     p.slab_tiles = MRL_MAX_SLAB_TILES;
-    for (int s = MRL_MAX_SLAB_TILES; s >= 8; --s) {
+    for (int s = MRL_MAX_SLAB_TILES; s >= 8; s -= 2) {
       const long long slabs = (b->n_tiles + s - 1) / s;
       const long long rounds = (slabs + sms - 1) / sms * s;
       if (best < 0 || rounds < best) { best = rounds; p.slab_tiles = s; }
@@ -782,7 +783,8 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.slab_tiles = pl.slab_tiles;
   a.mode = mode;
   a.reverse_kl = reverse_kl;
-  CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
+  if (mode == MRL_MODE_FVP && chain_fvp_shape(g) != 0) CKP(PK_MIDB_FVP, launch_chain_fvp(g, a, pl.n_slabs, st), 1);
+  else CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
                                 pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
   const int world = world_of(n);

@@ -58,6 +58,24 @@ size_t mid_backward_smem(const NetGeom& g, int mode);
 cudaError_t launch_mid_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st);
 cudaError_t launch_mid_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st);
 
+// ---- mlp_chain.cu  (register-resident per-warp chain for the Fisher-vector product)
+#define CH_WARPS 8
+#define CH_NE 3             // weight-gradient entries per warp
+#define CH_NTJ 4            // n-tiles (8 columns each) per entry
+struct ChainEntry {
+  int on;      // 1: active
+  int arow0;   // cache feature row of the m-tile's first input feature (off_act[l-1] + 16 mt)
+  int amax;    // valid input features from there (d[l-1] - 16 mt; may exceed 16)
+  int erow0;   // shared-memory delta row of the first n-tile
+  int cnt;     // n-tiles
+  int poff;    // offset of the block in the slab partial (off_W[l] + 16 mt ldw + 8 nt0)
+  int ldw;
+  int nmax;    // valid output features from the first n-tile (d[l] - 8 nt0)
+};
+struct ChainJobs { ChainEntry e[CH_WARPS][CH_NE]; };
+int chain_fvp_shape(const NetGeom& g);   // 0: not covered by an instantiated chain shape
+cudaError_t launch_chain_fvp(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st);
+
 // ---- vec_kernels.cu  (CG / line-search vector algebra on device-resident fp64 vectors)
 struct CgState {   // device-resident scalars
   double rdotr, pz, alpha, beta, shs, lm, gdots, expected_rate, gmax;

@@ -1,0 +1,628 @@
+// Fisher-vector product through layers >= 2 as a register-resident per-warp chain (trpo.py:45-58).
+//
+// One CTA (8 warps) owns a slab of <= 1024 timesteps and walks it in chain tiles of 128 timesteps.
+//
+//   chain phase  Each warp owns 16 timesteps and carries them through the whole R-forward (Pearlmutter)
+//                and reverse sweep WITHOUT block barriers: the m16n8 accumulator fragment of one layer is
+//                the A fragment of the next (k-slot t <-> feature 2t, slot t+4 <-> feature 2t+1, so no
+//                shuffle is needed), weights are read from shared memory in an 8x8-block layout that is
+//                bank-conflict free for both W (R-forward) and W^T (delta) fragment reads, cached
+//                activations come straight from HBM/L2 in fragment order.  Every product is 3xTF32
+//                (mma_tf32.cuh).  delta_l (l >= 2) is left in shared memory pre-split as (hi, lo) pairs,
+//                delta_1 goes to HBM as the tcgen05 operand of l1_grad_tc_kernel.
+//   grad phase   After ONE barrier the weight gradients G_l = h_{l-1}^T delta_l (K = the 128 timesteps)
+//                are accumulated by a static (layer, m-tile, n-tiles) -> warp assignment, so every
+//                accumulator block lives in registers for the whole slab and is flushed once as the
+//                fp32 slab partial that reduce_partials_kernel sums in fp64.
+//
+// Two barriers per 128 timesteps (the job-list kernel in mlp_mid.cu needs ~10 per 64) and ~3x fewer
+// issued instructions per timestep; see DESIGN.md section 4 for the measured effect.
+#include "common.cuh"
+#include "kernels.h"
+#include "mma_tf32.cuh"
+#include <string.h>
+
+#define CH_THREADS 256
+#define CH_T 128            // timesteps per chain tile (2 cache tiles)
+#define CH_LDE 136          // timesteps between consecutive delta rows in shared memory (x2 floats: hi, lo)
+
+template <int L_, int N1_, int N2_, int N3_, int N4_>
+struct ChainShape {
+  static constexpr int L = L_;
+  __host__ __device__ static constexpr int nt(int l) { return l == 1 ? N1_ : (l == 2 ? N2_ : (l == 3 ? N3_ : N4_)); }
+  // weight blocks of layer l (l >= 2): [in-block][out-block][64]
+  __host__ __device__ static constexpr int woff(int l) {
+    int s = 0;
+    for (int k = 2; k < l; ++k) s += nt(k - 1) * nt(k) * 64;
+    return s;
+  }
+  __host__ __device__ static constexpr int wfloats() { return woff(L_ + 1); }
+  __host__ __device__ static constexpr int eoff(int l) {   // first delta row of layer l (l >= 2)
+    int s = 0;
+    for (int k = 2; k < l; ++k) s += 8 * nt(k);
+    return s;
+  }
+  __host__ __device__ static constexpr int erows() { return eoff(L_ + 1); }
+  __host__ __device__ static constexpr int vboff(int l) {  // tangent bias of layer l (l >= 1)
+    int s = 0;
+    for (int k = 1; k < l; ++k) s += 8 * nt(k);
+    return s;
+  }
+  __host__ __device__ static constexpr int vbfloats() { return vboff(L_ + 1); }
+  __host__ __device__ static constexpr size_t smem_floats() {
+    return (size_t)2 * wfloats() + vbfloats() + 8 * nt(L_) + CH_WARPS * 8 * N1_ + (size_t)erows() * CH_LDE * 2;
+  }
+};
+
+// row of feature j' (0..7) inside an 8x8 weight block: conflict-free for the 64-bit W reads (lanes g = 0..3 /
+// 4..7 of a half-warp hit rows with distinct (row mod 4)) and for the 32-bit W^T reads (rows 2t / 2t+1).
+__device__ __forceinline__ int blk_row(int j) { return j < 4 ? j : (j ^ 1); }
+
+__device__ __forceinline__ void ldfrag(float (&v)[4], const float* __restrict__ p, int f0, int dmax, bool ok) {
+  const bool k0 = ok && f0 < dmax, k1 = ok && f0 + 1 < dmax;
+  v[0] = k0 ? __ldg(p + f0 * MRL_LDT) : 0.f;
+  v[2] = k0 ? __ldg(p + f0 * MRL_LDT + 8) : 0.f;
+  v[1] = k1 ? __ldg(p + (f0 + 1) * MRL_LDT) : 0.f;
+  v[3] = k1 ? __ldg(p + (f0 + 1) * MRL_LDT + 8) : 0.f;
+}
+// accumulator-order values (c0..c3) -> A-fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3), split
+__device__ __forceinline__ void to_frag(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+  split_tf32(v[0], hi[0], lo[0]);
+  split_tf32(v[2], hi[1], lo[1]);
+  split_tf32(v[1], hi[2], lo[2]);
+  split_tf32(v[3], hi[3], lo[3]);
+}
+
+// acc[n] += A(k-step ks) . B(block), n-tiles nb .. nb+NT-1.  TRANS = false: B = W_l (K = in features, N = out),
+// TRANS = true: B = W_l^T (K = out features, N = in).  ntl = out-blocks of layer l.
+template <int NT, bool TRANS>
+__device__ __forceinline__ void kstep(float (&acc)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                      const float* __restrict__ W, int ks, int nb, int ntl, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int n0 = 0; n0 < NT; n0 += 4) {
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n0 + q < NT) {
+        float b0, b1;
+        if (!TRANS) {
+          const float2 b = *reinterpret_cast<const float2*>(W + (ks * ntl + nb + n0 + q) * 64 + blk_row(g) * 8 + 2 * t);
+          b0 = b.x; b1 = b.y;
+        } else {
+          const float* p = W + ((nb + n0 + q) * ntl + ks) * 64 + g;
+          b0 = p[blk_row(2 * t) * 8];
+          b1 = p[blk_row(2 * t + 1) * 8];
+        }
+        split_tf32(b0, bh[q][0], bl[q][0]);
+        split_tf32(b1, bh[q][1], bl[q][1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], al, bh[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bl[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bh[q]);
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+}
+
+// delta rows of one layer -> shared memory, (hi, lo) pairs: E[row = feature][timestep][2]
+template <int NT>
+__device__ __forceinline__ void store_E(float* __restrict__ Erow, const uint32_t (&hi)[NT][4],
+                                        const uint32_t (&lo)[NT][4], int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float2* base = reinterpret_cast<float2*>(Erow) + (2 * t) * CH_LDE + 16 * warp + g;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float2* p = base + n * 8 * CH_LDE;
+    p[0] = make_float2(__uint_as_float(hi[n][0]), __uint_as_float(lo[n][0]));            // (f0, row g)
+    p[8] = make_float2(__uint_as_float(hi[n][1]), __uint_as_float(lo[n][1]));            // (f0, row g+8)
+    p[CH_LDE] = make_float2(__uint_as_float(hi[n][2]), __uint_as_float(lo[n][2]));       // (f0+1, row g)
+    p[CH_LDE + 8] = make_float2(__uint_as_float(hi[n][3]), __uint_as_float(lo[n][3]));   // (f0+1, row g+8)
+  }
+}
+
+// Rh = act'(h) * (acc + vb) for a hidden layer -> fragments of the next GEMM
+template <int ACT, int NT>
+__device__ __forceinline__ void epi_rhidden(const float (&acc)[NT][4], const float (&h)[NT][4],
+                                            const float* __restrict__ vbl, uint32_t (&hi)[NT][4],
+                                            uint32_t (&lo)[NT][4], int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float2 b = *reinterpret_cast<const float2*>(vbl + 8 * n + 2 * t);
+    float v[4];
+    v[0] = dact_from_h<ACT>(h[n][0]) * (acc[n][0] + b.x);
+    v[1] = dact_from_h<ACT>(h[n][1]) * (acc[n][1] + b.y);
+    v[2] = dact_from_h<ACT>(h[n][2]) * (acc[n][2] + b.x);
+    v[3] = dact_from_h<ACT>(h[n][3]) * (acc[n][3] + b.y);
+    to_frag(v, hi[n], lo[n]);
+  }
+}
+// delta_{l-1} = acc * act'(h_{l-1}) -> fragments
+template <int ACT, int NT>
+__device__ __forceinline__ void epi_delta(const float (&acc)[NT][4], const float (&h)[NT][4], uint32_t (&hi)[NT][4],
+                                          uint32_t (&lo)[NT][4]) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = acc[n][i] * dact_from_h<ACT>(h[n][i]);
+    to_frag(v, hi[n], lo[n]);
+  }
+}
+
+// Fisher metric at the head: delta_L from Rz_L = acc + vb_L; rows >= N contribute nothing.
+template <int NT>
+__device__ __forceinline__ void head_metric(const float (&acc)[NT][4], const float* __restrict__ vbl,
+                                            const float* __restrict__ ivar, const float (&p)[NT][4], bool cat,
+                                            bool valid0, bool valid1, uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4],
+                                            int lane) {
+  const int t = lane & 3;
+  float rz[NT][4];
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float2 b = *reinterpret_cast<const float2*>(vbl + 8 * n + 2 * t);
+    rz[n][0] = acc[n][0] + b.x; rz[n][1] = acc[n][1] + b.y;
+    rz[n][2] = acc[n][2] + b.x; rz[n][3] = acc[n][3] + b.y;
+    if (cat) {
+      s0 += p[n][0] * rz[n][0] + p[n][1] * rz[n][1];
+      s1 += p[n][2] * rz[n][2] + p[n][3] * rz[n][3];
+    }
+  }
+  if (cat) {   // the four lanes of a quad hold one row: p . Rz over all columns
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float v[4];
+    if (cat) {                       // M = diag(p) - p p^T
+      v[0] = p[n][0] * (rz[n][0] - s0); v[1] = p[n][1] * (rz[n][1] - s0);
+      v[2] = p[n][2] * (rz[n][2] - s1); v[3] = p[n][3] * (rz[n][3] - s1);
+    } else {                         // M = diag(1/sigma^2) on the mean block
+      const float2 iv = *reinterpret_cast<const float2*>(ivar + 8 * n + 2 * t);
+      v[0] = rz[n][0] * iv.x; v[1] = rz[n][1] * iv.y;
+      v[2] = rz[n][2] * iv.x; v[3] = rz[n][3] * iv.y;
+    }
+    if (!valid0) { v[0] = 0.f; v[1] = 0.f; }
+    if (!valid1) { v[2] = 0.f; v[3] = 0.f; }
+    to_frag(v, hi[n], lo[n]);
+  }
+}
+
+// R-forward of layer 2: A = Rh1 = act'(h1) * (x.V1 + vb1) and A = h1, streamed from HBM per k-step
+template <int ACT, int N1, int N2>
+__device__ __forceinline__ void rfwd_layer2(float (&acc)[N2][4], const float* __restrict__ zp,
+                                            const float* __restrict__ hp, int d1, bool ok,
+                                            const float* __restrict__ vb1, const float* __restrict__ W,
+                                            const float* __restrict__ V, int lane) {
+  const int t = lane & 3;
+  float zc[4], hc[4];
+  ldfrag(zc, zp, 2 * t, d1, ok);
+  ldfrag(hc, hp, 2 * t, d1, ok);
+#pragma unroll 1
+  for (int ks = 0; ks < N1; ++ks) {
+    float zn[4], hn[4];
+    const bool more = ks + 1 < N1;
+    ldfrag(zn, zp, 8 * (ks + 1) + 2 * t, d1, ok && more);
+    ldfrag(hn, hp, 8 * (ks + 1) + 2 * t, d1, ok && more);
+    const float2 b = *reinterpret_cast<const float2*>(vb1 + 8 * ks + 2 * t);
+    float r[4];
+    r[0] = dact_from_h<ACT>(hc[0]) * (zc[0] + b.x);
+    r[1] = dact_from_h<ACT>(hc[1]) * (zc[1] + b.y);
+    r[2] = dact_from_h<ACT>(hc[2]) * (zc[2] + b.x);
+    r[3] = dact_from_h<ACT>(hc[3]) * (zc[3] + b.y);
+    uint32_t ah[4], al[4];
+    to_frag(r, ah, al);
+    kstep<N2, false>(acc, ah, al, W, ks, 0, N2, lane);
+    to_frag(hc, ah, al);
+    kstep<N2, false>(acc, ah, al, V, ks, 0, N2, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { zc[i] = zn[i]; hc[i] = hn[i]; }
+  }
+}
+// R-forward of layer l >= 3: A = Rh_{l-1} (fragments) with W_l, and A = h_{l-1} with V_l
+template <int NI, int NO>
+__device__ __forceinline__ void rfwd_layer(float (&acc)[NO][4], const uint32_t (&rhi)[NI][4],
+                                           const uint32_t (&rlo)[NI][4], const float (&hin)[NI][4],
+                                           const float* __restrict__ W, const float* __restrict__ V, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < NI; ++ks) {
+    kstep<NO, false>(acc, rhi[ks], rlo[ks], W, ks, 0, NO, lane);
+    uint32_t ah[4], al[4];
+    to_frag(hin[ks], ah, al);
+    kstep<NO, false>(acc, ah, al, V, ks, 0, NO, lane);
+  }
+}
+// delta_{l-1} pre-activation = delta_l . W_l^T for in-blocks nb .. nb+NI-1
+template <int NI, int NO>
+__device__ __forceinline__ void delta_layer(float (&acc)[NI][4], const uint32_t (&dhi)[NO][4],
+                                            const uint32_t (&dlo)[NO][4], const float* __restrict__ W, int nb,
+                                            int lane) {
+#pragma unroll
+  for (int ks = 0; ks < NO; ++ks) kstep<NI, true>(acc, dhi[ks], dlo[ks], W, ks, nb, NO, lane);
+}
+
+// delta_1 for in-blocks nb .. nb+NH-1: bias partial sums + the split-precision tcgen05 operand DG
+// [tg = t/8][hi|lo][khalf][ngroup nu/8][8 n][4 timesteps]  (mlp_l1_tc.cu)
+template <int ACT, int NH, int nb, int N1, int NO>
+__device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const uint32_t (&dlo)[NO][4],
+                                             const float* __restrict__ W2, const float* __restrict__ hp,
+                                             int d1, bool ok, float (&gb1)[N1][2], float* __restrict__ dg, int nu,
+                                             int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float h1[NH][4];
+#pragma unroll
+  for (int n = 0; n < NH; ++n) ldfrag(h1[n], hp, 8 * (nb + n) + 2 * t, d1, ok);
+  float acc[NH][4];
+  zero_acc(acc);
+  delta_layer<NH, NO>(acc, dhi, dlo, W2, nb, lane);
+#pragma unroll
+  for (int n = 0; n < NH; ++n) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = acc[n][i] * dact_from_h<ACT>(h1[n][i]);
+    gb1[nb + n][0] += v[0] + v[2];
+    gb1[nb + n][1] += v[1] + v[3];
+    if (ok && 8 * (nb + n) < nu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t hi, lo;
+        split_tf32(v[i], hi, lo);
+        // dg -> this warp's first timestep group; row g + 8 (i >> 1) of the warp's 16 timesteps
+        float* p = dg + (size_t)(i >> 1) * (2 * nu * 8) + (g >> 2) * (nu * 4) + (nb + n) * 32 + (2 * t + (i & 1)) * 4 + (g & 3);
+        p[0] = __uint_as_float(hi);
+        p[nu * 8] = __uint_as_float(lo);
+      }
+    }
+  }
+}
+
+template <class S, int ACT>
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, MidBwdArgs a, ChainJobs jobs) {
+  constexpr int L = S::L;
+  constexpr int N1 = S::nt(1), N2 = S::nt(2), N3 = S::nt(3), N4 = S::nt(4);
+  constexpr int NL = S::nt(L);
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;
+  float* Vs = Ws + S::wfloats();
+  float* vb = Vs + S::wfloats();
+  float* ivar = vb + S::vbfloats();
+  float* gb1s = ivar + 8 * NL;
+  float* E = gb1s + CH_WARPS * 8 * N1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int slab = blockIdx.x;
+  const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
+  const bool cat = g.head == MRL_HEAD_CAT;
+
+  // ---- weights of theta (W) and of the tangent (V) into the 8x8-block layout, tangent biases, 1/sigma^2
+#pragma unroll
+  for (int l = 2; l <= L; ++l) {
+    const int kin = 8 * S::nt(l - 1), nout = 8 * S::nt(l);
+    const float* src = a.img + g.off_W[l];
+    const float* srv = a.imgv + g.off_W[l];
+    float* dw = Ws + S::woff(l);
+    float* dv = Vs + S::woff(l);
+    for (int e = tid; e < kin * nout; e += CH_THREADS) {
+      const int i = e / nout, j = e - i * nout;
+      const bool ok = i < g.d[l - 1] && j < g.d[l];
+      const int dst = ((i >> 3) * S::nt(l) + (j >> 3)) * 64 + blk_row(j & 7) * 8 + (i & 7);
+      dw[dst] = ok ? src[i * g.ldw[l] + j] : 0.f;
+      dv[dst] = ok ? srv[i * g.ldw[l] + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int l = 1; l <= L; ++l)
+    for (int f = tid; f < 8 * S::nt(l); f += CH_THREADS) vb[S::vboff(l) + f] = f < g.d[l] ? a.imgv[g.off_b[l] + f] : 0.f;
+  for (int f = tid; f < 8 * NL; f += CH_THREADS)
+    ivar[f] = (!cat && f < g.d[L]) ? expf(-2.f * a.img[g.off_pm_logstd + f]) : 0.f;
+
+  float G[CH_NE][CH_NTJ][4];
+#pragma unroll
+  for (int e = 0; e < CH_NE; ++e) zero_acc(G[e]);
+  float gb1[N1][2];
+#pragma unroll
+  for (int n = 0; n < N1; ++n) { gb1[n][0] = 0.f; gb1[n][1] = 0.f; }
+  float gbe = 0.f;   // lane j: bias-gradient sum of delta row warp + 8 j
+  __syncthreads();
+
+  for (int ct0 = t0; ct0 < t1; ct0 += 2) {
+    // ================= chain phase: this warp's 16 timesteps
+    {
+      const int ctile = ct0 + (warp >> 2);
+      const bool ok = ctile < t1;
+      const int rr = ((warp & 3) << 4) + gq;
+      const long long ts = (long long)ctile * MRL_TILE + rr;
+      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
+      const float* cb = a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr;
+      const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
+      if (ct0 + 2 < t1) {   // pull the next chain tile into L2 while this one computes
+        const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + 2) * g.act_rows * MRL_LDT);
+        const int nb = min(2, t1 - ct0 - 2) * g.act_rows * MRL_LDT * 4;
+        for (int off = tid * 128; off < nb; off += CH_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + off));
+        const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT);
+        const int nz = min(2, t1 - ct0 - 2) * g.d[1] * MRL_LDT * 4;
+        for (int off = tid * 128; off < nz; off += CH_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + off));
+      }
+      float h2[N2][4];
+#pragma unroll
+      for (int n = 0; n < N2; ++n) ldfrag(h2[n], cb + g.off_act[2] * MRL_LDT, 8 * n + 2 * t, g.d[2], ok);
+      // ---- R-forward
+      float acc2[N2][4];
+      zero_acc(acc2);
+      rfwd_layer2<ACT, N1, N2>(acc2, zb, cb, g.d[1], ok, vb + S::vboff(1), Ws + S::woff(2), Vs + S::woff(2), lane);
+      if constexpr (L == 3) {
+        float ph[N3][4];
+#pragma unroll
+        for (int n = 0; n < N3; ++n) ldfrag(ph[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok && cat);
+        uint32_t r2h[N2][4], r2l[N2][4];
+        epi_rhidden<ACT, N2>(acc2, h2, vb + S::vboff(2), r2h, r2l, lane);
+        float acc3[N3][4];
+        zero_acc(acc3);
+        rfwd_layer<N2, N3>(acc3, r2h, r2l, h2, Ws + S::woff(3), Vs + S::woff(3), lane);
+        uint32_t d3h[N3][4], d3l[N3][4];
+        head_metric<N3>(acc3, vb + S::vboff(3), ivar, ph, cat, valid0, valid1, d3h, d3l, lane);
+        store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, d3h, d3l, warp, lane);
+        // ---- reverse sweep
+        zero_acc(acc2);
+        delta_layer<N2, N3>(acc2, d3h, d3l, Ws + S::woff(3), 0, lane);
+        epi_delta<ACT, N2>(acc2, h2, r2h, r2l);
+        store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
+        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
+        constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
+        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+        if constexpr (NB > 0)
+          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+      } else {
+        float h3[N3][4];
+#pragma unroll
+        for (int n = 0; n < N3; ++n) ldfrag(h3[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok);
+        float ph[N4][4];
+#pragma unroll
+        for (int n = 0; n < N4; ++n) ldfrag(ph[n], cb + g.off_act[4] * MRL_LDT, 8 * n + 2 * t, g.d[4], ok && cat);
+        uint32_t r2h[N2][4], r2l[N2][4];
+        epi_rhidden<ACT, N2>(acc2, h2, vb + S::vboff(2), r2h, r2l, lane);
+        float acc3[N3][4];
+        zero_acc(acc3);
+        rfwd_layer<N2, N3>(acc3, r2h, r2l, h2, Ws + S::woff(3), Vs + S::woff(3), lane);
+        uint32_t r3h[N3][4], r3l[N3][4];
+        epi_rhidden<ACT, N3>(acc3, h3, vb + S::vboff(3), r3h, r3l, lane);
+        float acc4[N4][4];
+        zero_acc(acc4);
+        rfwd_layer<N3, N4>(acc4, r3h, r3l, h3, Ws + S::woff(4), Vs + S::woff(4), lane);
+        uint32_t d4h[N4][4], d4l[N4][4];
+        head_metric<N4>(acc4, vb + S::vboff(4), ivar, ph, cat, valid0, valid1, d4h, d4l, lane);
+        store_E<N4>(E + (size_t)S::eoff(4) * CH_LDE * 2, d4h, d4l, warp, lane);
+        // ---- reverse sweep
+        zero_acc(acc3);
+        delta_layer<N3, N4>(acc3, d4h, d4l, Ws + S::woff(4), 0, lane);
+        epi_delta<ACT, N3>(acc3, h3, r3h, r3l);
+        store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, r3h, r3l, warp, lane);
+        zero_acc(acc2);
+        delta_layer<N2, N3>(acc2, r3h, r3l, Ws + S::woff(3), 0, lane);
+        epi_delta<ACT, N2>(acc2, h2, r2h, r2l);
+        store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
+        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
+        constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
+        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+        if constexpr (NB > 0)
+          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+      }
+      if (ok) {   // operand columns beyond the chain's padded width are zeros
+        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
+        for (int i = lane; i < 2 * 2 * 2 * (a.nu - 8 * N1) * 4; i += 32) {
+          // [tg 2][hi|lo 2][khalf 2][(nu/8 - N1) groups x 32]
+          const int per = (a.nu - 8 * N1) * 4;
+          const int blk = i / per, r = i - blk * per;
+          dg[(size_t)blk * (a.nu * 4) + 8 * N1 * 4 + r] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    // ================= grad phase: G_l += h_{l-1}^T delta_l over the 128 timesteps of this chain tile
+    {
+      const bool t2ok = ct0 + 1 < t1;
+#pragma unroll
+      for (int e = 0; e < CH_NE; ++e) {
+        const ChainEntry en = jobs.e[warp][e];
+        if (!en.on) continue;
+        const bool ok0 = gq < en.amax, ok1 = gq + 8 < en.amax;
+        const float* A0 = a.cache + ((size_t)ct0 * g.act_rows + en.arow0 + gq) * MRL_LDT + 2 * t;
+        const float* Eb = E + ((size_t)(en.erow0 + gq) * CH_LDE + 2 * t) * 2;
+#pragma unroll 2
+        for (int ks = 0; ks < CH_T / 8; ++ks) {
+          const bool hk = ks < 8 || t2ok;
+          const float* Ap = A0 + (size_t)(ks >> 3) * g.act_rows * MRL_LDT + (ks & 7) * 8;
+          float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
+          if (ok0 && hk) x0 = __ldg(reinterpret_cast<const float2*>(Ap));
+          if (ok1 && hk) x1 = __ldg(reinterpret_cast<const float2*>(Ap + 8 * MRL_LDT));
+          uint32_t ah[4], al[4];
+          split_tf32(x0.x, ah[0], al[0]);
+          split_tf32(x1.x, ah[1], al[1]);
+          split_tf32(x0.y, ah[2], al[2]);
+          split_tf32(x1.y, ah[3], al[3]);
+          uint32_t bh[CH_NTJ][2], bl[CH_NTJ][2];
+#pragma unroll
+          for (int q = 0; q < CH_NTJ; ++q)
+            if (q < en.cnt) {
+              const float4 b = *reinterpret_cast<const float4*>(Eb + (size_t)q * 8 * CH_LDE * 2 + ks * 16);
+              bh[q][0] = __float_as_uint(b.x); bl[q][0] = __float_as_uint(b.y);
+              bh[q][1] = __float_as_uint(b.z); bl[q][1] = __float_as_uint(b.w);
+            }
+#pragma unroll
+          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], al, bh[q]);
+#pragma unroll
+          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], ah, bl[q]);
+#pragma unroll
+          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], ah, bh[q]);
+        }
+      }
+      // bias gradients of layers >= 2: row sums of delta (what the tensor cores consumed: hi + truncated lo)
+      for (int j = 0; warp + 8 * j < S::erows(); ++j) {
+        const float4* p = reinterpret_cast<const float4*>(E + (size_t)(warp + 8 * j) * CH_LDE * 2);
+        const float4 u = p[lane], v = p[lane + 32];
+        float s = (u.x + __uint_as_float(__float_as_uint(u.y) & 0xffffe000u)) + (u.z + __uint_as_float(__float_as_uint(u.w) & 0xffffe000u)) +
+                  (v.x + __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + (v.z + __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+        s = warp_sum(s);
+        if (lane == j) gbe += s;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ================= flush the slab partial
+  float* part = a.partm + (size_t)slab * g.pmid;
+#pragma unroll
+  for (int e = 0; e < CH_NE; ++e) {
+    const ChainEntry en = jobs.e[warp][e];
+    if (!en.on) continue;
+#pragma unroll
+    for (int q = 0; q < CH_NTJ; ++q) {
+      if (q >= en.cnt) continue;
+      const int n = 8 * q + 2 * t;
+      float* pr = part + en.poff + n;
+      if (gq < en.amax) {
+        if (n < en.nmax) pr[gq * en.ldw] = G[e][q][0];
+        if (n + 1 < en.nmax) pr[gq * en.ldw + 1] = G[e][q][1];
+      }
+      if (gq + 8 < en.amax) {
+        if (n < en.nmax) pr[(gq + 8) * en.ldw] = G[e][q][2];
+        if (n + 1 < en.nmax) pr[(gq + 8) * en.ldw + 1] = G[e][q][3];
+      }
+    }
+  }
+  {
+    const int r = warp + 8 * lane;
+    if (r < S::erows()) {
+#pragma unroll
+      for (int l = 2; l <= L; ++l)
+        if (r >= S::eoff(l) && r < S::eoff(l + 1)) {
+          const int f = r - S::eoff(l);
+          if (f < g.d[l]) part[g.off_b[l] + f] = gbe;
+        }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N1; ++n)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      float v = gb1[n][b];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (gq == 0) gb1s[warp * 8 * N1 + 8 * n + 2 * t + b] = v;
+    }
+  __syncthreads();
+  for (int f = tid; f < g.d[1]; f += CH_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < CH_WARPS; ++w) s += gb1s[w * 8 * N1 + f];   // fixed order -> deterministic
+    part[g.off_b[1] + f] = s;
+  }
+  for (int j = tid; j < g.d[L]; j += CH_THREADS) part[g.off_pm_logstd + j] = 0.f;   // fvp[logstd] is set by the reduce
+}
+
+// ------------------------------------------------------------------------------------ host side
+// Static (layer, m-tile, n-tiles) -> warp assignment of the weight-gradient blocks: longest job first
+// onto the least loaded warp that still has a free entry.
+template <class S>
+static bool build_jobs(const NetGeom& g, ChainJobs* jobs) {
+  struct Job { int l, mt, nt0, cnt; };
+  Job list[256];
+  int nj = 0;
+  for (int l = 2; l <= S::L; ++l) {
+    const int mts = (g.d[l - 1] + 15) / 16, nts = (g.d[l] + 7) / 8;
+    for (int mt = 0; mt < mts; ++mt) {
+      const int groups = (nts + CH_NTJ - 1) / CH_NTJ;
+      for (int gi = 0; gi < groups; ++gi) {   // spread the n-tiles evenly over the groups
+        const int a0 = nts * gi / groups, a1 = nts * (gi + 1) / groups;
+        if (nj == 256) return false;
+        list[nj++] = {l, mt, a0, a1 - a0};
+      }
+    }
+  }
+  if (nj > CH_WARPS * CH_NE) return false;
+  for (int i = 1; i < nj; ++i)
+    for (int k = i; k > 0 && list[k].cnt > list[k - 1].cnt; --k) { Job tmp = list[k]; list[k] = list[k - 1]; list[k - 1] = tmp; }
+  int load[CH_WARPS] = {0}, used[CH_WARPS] = {0};
+  memset(jobs, 0, sizeof(*jobs));
+  for (int i = 0; i < nj; ++i) {
+    int best = -1;
+    for (int w = 0; w < CH_WARPS; ++w)
+      if (used[w] < CH_NE && (best < 0 || load[w] < load[best])) best = w;
+    if (best < 0) return false;
+    const Job& j = list[i];
+    ChainEntry& en = jobs->e[best][used[best]++];
+    load[best] += j.cnt;
+    en.on = 1;
+    en.arow0 = g.off_act[j.l - 1] + 16 * j.mt;
+    en.amax = g.d[j.l - 1] - 16 * j.mt;
+    en.erow0 = S::eoff(j.l) + 8 * j.nt0;
+    en.cnt = j.cnt;
+    en.poff = g.off_W[j.l] + 16 * j.mt * g.ldw[j.l] + 8 * j.nt0;
+    en.ldw = g.ldw[j.l];
+    en.nmax = g.d[j.l] - 8 * j.nt0;
+  }
+  return true;
+}
+
+template <class S>
+static bool shape_fits(const NetGeom& g) {
+  if (g.L != S::L || g.act != MRL_ACT_TANH) return false;
+  if (g.head != MRL_HEAD_GAUSS && g.head != MRL_HEAD_CAT) return false;
+  for (int l = 1; l <= S::L; ++l)
+    if ((g.d[l] + 7) / 8 > S::nt(l)) return false;
+  // the padded layer-1 width must cover every n-group of the layer-1 gradient operand but one
+  if (l1tc_nu(g) - 8 * S::nt(1) > 8 || l1tc_nu(g) < 8 * S::nt(1)) return false;
+  ChainJobs jobs;
+  return build_jobs<S>(g, &jobs);
+}
+
+template <class S>
+static cudaError_t launch_shape(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  ChainJobs jobs;
+  if (!build_jobs<S>(g, &jobs)) return cudaErrorInvalidConfiguration;
+  const size_t sm = S::smem_floats() * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(chain_fvp_kernel<S, MRL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  chain_fvp_kernel<S, MRL_ACT_TANH><<<n_slabs, CH_THREADS, sm, st>>>(g, a, jobs);
+  return cudaGetLastError();
+}
+
+typedef ChainShape<3, 8, 8, 1, 0> ShapeA;     // 64-64 hidden, <= 8 outputs  (Hopper, Walker2d, CartPole)
+typedef ChainShape<3, 8, 8, 3, 0> ShapeB;     // 64-64 hidden, <= 24 outputs (18-action Categorical)
+typedef ChainShape<4, 13, 7, 4, 3> ShapeC;    // 100-50-25 hidden, <= 24 outputs (Humanoid)
+
+// 0 = not supported (use the job-list kernel of mlp_mid.cu), else the shape id
+int chain_fvp_shape(const NetGeom& g) {
+  if (shape_fits<ShapeA>(g)) return 1;
+  if (shape_fits<ShapeB>(g)) return 2;
+  if (shape_fits<ShapeC>(g)) return 3;
+  return 0;
+}
+
+cudaError_t launch_chain_fvp(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;   // chain tiles must not straddle slabs
+  switch (chain_fvp_shape(g)) {
+    case 1: return launch_shape<ShapeA>(g, a, n_slabs, st);
+    case 2: return launch_shape<ShapeB>(g, a, n_slabs, st);
+    case 3: return launch_shape<ShapeC>(g, a, n_slabs, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
