@@ -54,6 +54,14 @@ struct ChainShape {
   }
 };
 
+// hi = rna_tf32(x) by integer arithmetic, lo = x - hi (exact).  lo is left to the tensor core's own
+// truncation: lo = x - rna(x) has a random sign relative to x, so truncating it toward zero is unbiased
+// (a 2^-22 relative random error per product), unlike a truncated hi (see mma_tf32.cuh).
+__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 // row of feature j' (0..7) inside an 8x8 weight block: conflict-free for the 64-bit W reads (lanes g = 0..3 /
 // 4..7 of a half-warp hit rows with distinct (row mod 4)) and for the 32-bit W^T reads (rows 2t / 2t+1).
 __device__ __forceinline__ int blk_row(int j) { return j < 4 ? j : (j ^ 1); }
@@ -67,10 +75,10 @@ __device__ __forceinline__ void ldfrag(float (&v)[4], const float* __restrict__ 
 }
 // accumulator-order values (c0..c3) -> A-fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3), split
 __device__ __forceinline__ void to_frag(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
-  split_tf32(v[0], hi[0], lo[0]);
-  split_tf32(v[2], hi[1], lo[1]);
-  split_tf32(v[1], hi[2], lo[2]);
-  split_tf32(v[3], hi[3], lo[3]);
+  split3(v[0], hi[0], lo[0]);
+  split3(v[2], hi[1], lo[1]);
+  split3(v[1], hi[2], lo[2]);
+  split3(v[3], hi[3], lo[3]);
 }
 
 // acc[n] += A(k-step ks) . B(block), n-tiles nb .. nb+NT-1.  TRANS = false: B = W_l (K = in features, N = out),
@@ -79,11 +87,13 @@ template <int NT, bool TRANS>
 __device__ __forceinline__ void kstep(float (&acc)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                       const float* __restrict__ W, int ks, int nb, int ntl, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  // RND independent accumulators per pass: consecutive MMAs on one accumulator are RND issues apart
+  constexpr int RND = NT <= 8 ? NT : (NT + 1) / 2;
 #pragma unroll
-  for (int n0 = 0; n0 < NT; n0 += 4) {
-    uint32_t bh[4][2], bl[4][2];
+  for (int n0 = 0; n0 < NT; n0 += RND) {
+    uint32_t bh[RND][2], bl[RND][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < RND; ++q) {
       if (n0 + q < NT) {
         float b0, b1;
         if (!TRANS) {
@@ -94,16 +104,16 @@ __device__ __forceinline__ void kstep(float (&acc)[NT][4], const uint32_t (&ah)[
           b0 = p[blk_row(2 * t) * 8];
           b1 = p[blk_row(2 * t + 1) * 8];
         }
-        split_tf32(b0, bh[q][0], bl[q][0]);
-        split_tf32(b1, bh[q][1], bl[q][1]);
+        split3(b0, bh[q][0], bl[q][0]);
+        split3(b1, bh[q][1], bl[q][1]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], al, bh[q]);
+    for (int q = 0; q < RND; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], al, bh[q]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bl[q]);
+    for (int q = 0; q < RND; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bl[q]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bh[q]);
+    for (int q = 0; q < RND; ++q) if (n0 + q < NT) mma_tf32(acc[n0 + q], ah, bh[q]);
   }
 }
 
@@ -208,15 +218,17 @@ __device__ __forceinline__ void rfwd_layer2(float (&acc)[N2][4], const float* __
                                             const float* __restrict__ vb1, const float* __restrict__ W,
                                             const float* __restrict__ V, int lane) {
   const int t = lane & 3;
-  float zc[4], hc[4];
+  float zc[4], hc[4], z1[4], h1[4];     // k-steps ks and ks+1; ks+2 is requested at the top of the loop
   ldfrag(zc, zp, 2 * t, d1, ok);
   ldfrag(hc, hp, 2 * t, d1, ok);
+  ldfrag(z1, zp, 8 + 2 * t, d1, ok && N1 > 1);
+  ldfrag(h1, hp, 8 + 2 * t, d1, ok && N1 > 1);
 #pragma unroll 1
   for (int ks = 0; ks < N1; ++ks) {
     float zn[4], hn[4];
-    const bool more = ks + 1 < N1;
-    ldfrag(zn, zp, 8 * (ks + 1) + 2 * t, d1, ok && more);
-    ldfrag(hn, hp, 8 * (ks + 1) + 2 * t, d1, ok && more);
+    const bool more = ks + 2 < N1;
+    ldfrag(zn, zp, 8 * (ks + 2) + 2 * t, d1, ok && more);
+    ldfrag(hn, hp, 8 * (ks + 2) + 2 * t, d1, ok && more);
     const float2 b = *reinterpret_cast<const float2*>(vb1 + 8 * ks + 2 * t);
     float r[4];
     r[0] = dact_from_h<ACT>(hc[0]) * (zc[0] + b.x);
@@ -229,7 +241,7 @@ __device__ __forceinline__ void rfwd_layer2(float (&acc)[N2][4], const float* __
     to_frag(hc, ah, al);
     kstep<N2, false>(acc, ah, al, V, ks, 0, N2, lane);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { zc[i] = zn[i]; hc[i] = hn[i]; }
+    for (int i = 0; i < 4; ++i) { zc[i] = z1[i]; hc[i] = h1[i]; z1[i] = zn[i]; h1[i] = hn[i]; }
   }
 }
 // R-forward of layer l >= 3: A = Rh_{l-1} (fragments) with W_l, and A = h_{l-1} with V_l
@@ -237,12 +249,28 @@ template <int NI, int NO>
 __device__ __forceinline__ void rfwd_layer(float (&acc)[NO][4], const uint32_t (&rhi)[NI][4],
                                            const uint32_t (&rlo)[NI][4], const float (&hin)[NI][4],
                                            const float* __restrict__ W, const float* __restrict__ V, int lane) {
+  if constexpr (NO <= 4) {   // narrow layer: the two terms go to separate accumulators (longer dependency distance)
+    float acc2[NO][4];
+    zero_acc(acc2);
 #pragma unroll
-  for (int ks = 0; ks < NI; ++ks) {
-    kstep<NO, false>(acc, rhi[ks], rlo[ks], W, ks, 0, NO, lane);
-    uint32_t ah[4], al[4];
-    to_frag(hin[ks], ah, al);
-    kstep<NO, false>(acc, ah, al, V, ks, 0, NO, lane);
+    for (int ks = 0; ks < NI; ++ks) {
+      kstep<NO, false>(acc, rhi[ks], rlo[ks], W, ks, 0, NO, lane);
+      uint32_t ah[4], al[4];
+      to_frag(hin[ks], ah, al);
+      kstep<NO, false>(acc2, ah, al, V, ks, 0, NO, lane);
+    }
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[n][i] += acc2[n][i];
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < NI; ++ks) {
+      kstep<NO, false>(acc, rhi[ks], rlo[ks], W, ks, 0, NO, lane);
+      uint32_t ah[4], al[4];
+      to_frag(hin[ks], ah, al);
+      kstep<NO, false>(acc, ah, al, V, ks, 0, NO, lane);
+    }
   }
 }
 // delta_{l-1} pre-activation = delta_l . W_l^T for in-blocks nb .. nb+NI-1
@@ -250,8 +278,22 @@ template <int NI, int NO>
 __device__ __forceinline__ void delta_layer(float (&acc)[NI][4], const uint32_t (&dhi)[NO][4],
                                             const uint32_t (&dlo)[NO][4], const float* __restrict__ W, int nb,
                                             int lane) {
+  if constexpr (NI <= 4 && NO >= 2) {   // narrow output: even / odd k-steps on separate accumulators
+    float acc2[NI][4];
+    zero_acc(acc2);
 #pragma unroll
-  for (int ks = 0; ks < NO; ++ks) kstep<NI, true>(acc, dhi[ks], dlo[ks], W, ks, nb, NO, lane);
+    for (int ks = 0; ks < NO; ++ks) {
+      if (ks & 1) kstep<NI, true>(acc2, dhi[ks], dlo[ks], W, ks, nb, NO, lane);
+      else kstep<NI, true>(acc, dhi[ks], dlo[ks], W, ks, nb, NO, lane);
+    }
+#pragma unroll
+    for (int n = 0; n < NI; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[n][i] += acc2[n][i];
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < NO; ++ks) kstep<NI, true>(acc, dhi[ks], dlo[ks], W, ks, nb, NO, lane);
+  }
 }
 
 // delta_1 for in-blocks nb .. nb+NH-1: bias partial sums + the split-precision tcgen05 operand DG
@@ -259,7 +301,7 @@ __device__ __forceinline__ void delta_layer(float (&acc)[NI][4], const uint32_t 
 template <int ACT, int NH, int nb, int N1, int NO>
 __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const uint32_t (&dlo)[NO][4],
                                              const float* __restrict__ W2, const float* __restrict__ hp,
-                                             int d1, bool ok, float (&gb1)[N1][2], float* __restrict__ dg, int nu,
+                                             int d1, bool ok, float* __restrict__ gb1w, float* __restrict__ dg, int nu,
                                              int lane) {
   const int g = lane >> 2, t = lane & 3;
   float h1[NH][4];
@@ -273,13 +315,23 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = acc[n][i] * dact_from_h<ACT>(h1[n][i]);
-    gb1[nb + n][0] += v[0] + v[2];
-    gb1[nb + n][1] += v[1] + v[3];
+    {  // bias gradient of layer 1: column sums over the warp's 16 timesteps into the warp's own slot
+      float s0 = v[0] + v[2], s1 = v[1] + v[3];
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 4); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 8); s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      if (g == 0) {
+        float2* q = reinterpret_cast<float2*>(gb1w + 8 * (nb + n) + 2 * t);
+        float2 c = *q;
+        c.x += s0; c.y += s1;
+        *q = c;
+      }
+    }
     if (ok && 8 * (nb + n) < nu) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t hi, lo;
-        split_tf32(v[i], hi, lo);
+        split3(v[i], hi, lo);
         // dg -> this warp's first timestep group; row g + 8 (i >> 1) of the warp's 16 timesteps
         float* p = dg + (size_t)(i >> 1) * (2 * nu * 8) + (g >> 2) * (nu * 4) + (nb + n) * 32 + (2 * t + (i & 1)) * 4 + (g & 3);
         p[0] = __uint_as_float(hi);
@@ -289,8 +341,56 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
   }
 }
 
+// G[q] += h_{l-1}^T delta_l over the 128 timesteps of the chain tile for one (m-tile, CNT n-tiles) entry.
+// A = cached activations straight from L2 (k-slot t <-> timestep 2t, slot t+4 <-> 2t+1: one 64-bit load per
+// row), B = (hi, lo) pairs of delta from shared memory (one 128-bit load per n-tile and k-step).
+template <int CNT>
+__device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* __restrict__ A0, size_t tile_stride,
+                                           bool ok0, bool ok1, bool t2ok, const float* __restrict__ Eb) {
+  float2 xa[4], xb[4];
+  auto load_group = [&](int kg, float2 (&a)[4], float2 (&b)[4]) {
+    const bool hk = kg < 2 || t2ok;                       // k-steps 8..15 live in the second cache tile
+    const float* Ap = A0 + (size_t)(kg >> 1) * tile_stride + (kg & 1) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j] = (ok0 && hk) ? __ldg(reinterpret_cast<const float2*>(Ap + 8 * j)) : make_float2(0.f, 0.f);
+      b[j] = (ok1 && hk) ? __ldg(reinterpret_cast<const float2*>(Ap + 8 * MRL_LDT + 8 * j)) : make_float2(0.f, 0.f);
+    }
+  };
+  load_group(0, xa, xb);
+#pragma unroll 1
+  for (int kg = 0; kg < 4; ++kg) {
+    float2 ca[4], cb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
+    if (kg < 3) load_group(kg + 1, xa, xb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ks = 4 * kg + j;
+      uint32_t ah[4], al[4];
+      split3(ca[j].x, ah[0], al[0]);
+      split3(cb[j].x, ah[1], al[1]);
+      split3(ca[j].y, ah[2], al[2]);
+      split3(cb[j].y, ah[3], al[3]);
+      uint32_t bh[CNT][2], bl[CNT][2];
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(Eb + (size_t)q * 8 * CH_LDE * 2 + ks * 16);
+        bh[q][0] = __float_as_uint(b.x); bl[q][0] = __float_as_uint(b.y);
+        bh[q][1] = __float_as_uint(b.z); bl[q][1] = __float_as_uint(b.w);
+      }
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) mma_tf32(G[q], al, bh[q]);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) mma_tf32(G[q], ah, bl[q]);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) mma_tf32(G[q], ah, bh[q]);
+    }
+  }
+}
+
 template <class S, int ACT>
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, MidBwdArgs a, ChainJobs jobs) {
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, MidBwdArgs a, ChainJobs jobs, int n_slabs) {
   constexpr int L = S::L;
   constexpr int N1 = S::nt(1), N2 = S::nt(2), N3 = S::nt(3), N4 = S::nt(4);
   constexpr int NL = S::nt(L);
@@ -303,8 +403,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
   float* E = gb1s + CH_WARPS * 8 * N1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const int slab = blockIdx.x;
-  const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
   const bool cat = g.head == MRL_HEAD_CAT;
 
   // ---- weights of theta (W) and of the tangent (V) into the 8x8-block layout, tangent biases, 1/sigma^2
@@ -329,12 +427,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
   for (int f = tid; f < 8 * NL; f += CH_THREADS)
     ivar[f] = (!cat && f < g.d[L]) ? expf(-2.f * a.img[g.off_pm_logstd + f]) : 0.f;
 
+  for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {   // persistent: weights stay in shared memory
+  const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
   float G[CH_NE][CH_NTJ][4];
 #pragma unroll
   for (int e = 0; e < CH_NE; ++e) zero_acc(G[e]);
-  float gb1[N1][2];
-#pragma unroll
-  for (int n = 0; n < N1; ++n) { gb1[n][0] = 0.f; gb1[n][1] = 0.f; }
+  for (int i = tid; i < CH_WARPS * 8 * N1; i += CH_THREADS) gb1s[i] = 0.f;
   float gbe = 0.f;   // lane j: bias-gradient sum of delta row warp + 8 j
   __syncthreads();
 
@@ -382,9 +480,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
         store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
         float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
         constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
-        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
         if constexpr (NB > 0)
-          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
       } else {
         float h3[N3][4];
 #pragma unroll
@@ -416,9 +514,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
         store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
         float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
         constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
-        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
         if constexpr (NB > 0)
-          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1, dg, a.nu, lane);
+          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
       }
       if (ok) {   // operand columns beyond the chain's padded width are zeros
         float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
@@ -441,32 +539,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
         const bool ok0 = gq < en.amax, ok1 = gq + 8 < en.amax;
         const float* A0 = a.cache + ((size_t)ct0 * g.act_rows + en.arow0 + gq) * MRL_LDT + 2 * t;
         const float* Eb = E + ((size_t)(en.erow0 + gq) * CH_LDE + 2 * t) * 2;
-#pragma unroll 2
-        for (int ks = 0; ks < CH_T / 8; ++ks) {
-          const bool hk = ks < 8 || t2ok;
-          const float* Ap = A0 + (size_t)(ks >> 3) * g.act_rows * MRL_LDT + (ks & 7) * 8;
-          float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-          if (ok0 && hk) x0 = __ldg(reinterpret_cast<const float2*>(Ap));
-          if (ok1 && hk) x1 = __ldg(reinterpret_cast<const float2*>(Ap + 8 * MRL_LDT));
-          uint32_t ah[4], al[4];
-          split_tf32(x0.x, ah[0], al[0]);
-          split_tf32(x1.x, ah[1], al[1]);
-          split_tf32(x0.y, ah[2], al[2]);
-          split_tf32(x1.y, ah[3], al[3]);
-          uint32_t bh[CH_NTJ][2], bl[CH_NTJ][2];
-#pragma unroll
-          for (int q = 0; q < CH_NTJ; ++q)
-            if (q < en.cnt) {
-              const float4 b = *reinterpret_cast<const float4*>(Eb + (size_t)q * 8 * CH_LDE * 2 + ks * 16);
-              bh[q][0] = __float_as_uint(b.x); bl[q][0] = __float_as_uint(b.y);
-              bh[q][1] = __float_as_uint(b.z); bl[q][1] = __float_as_uint(b.w);
-            }
-#pragma unroll
-          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], al, bh[q]);
-#pragma unroll
-          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], ah, bl[q]);
-#pragma unroll
-          for (int q = 0; q < CH_NTJ; ++q) if (q < en.cnt) mma_tf32(G[e][q], ah, bh[q]);
+        const size_t tstride = (size_t)g.act_rows * MRL_LDT;
+        switch (en.cnt) {   // warp-uniform
+          case 4: grad_entry<4>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
+          case 3: grad_entry<3>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
+          case 2: grad_entry<2>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
+          default: grad_entry<1>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
         }
       }
       // bias gradients of layers >= 2: row sums of delta (what the tensor cores consumed: hi + truncated lo)
@@ -514,16 +592,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
         }
     }
   }
-#pragma unroll
-  for (int n = 0; n < N1; ++n)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      float v = gb1[n][b];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (gq == 0) gb1s[warp * 8 * N1 + 8 * n + 2 * t + b] = v;
-    }
   __syncthreads();
   for (int f = tid; f < g.d[1]; f += CH_THREADS) {
     float s = 0.f;
@@ -532,6 +600,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
     part[g.off_b[1] + f] = s;
   }
   for (int j = tid; j < g.d[L]; j += CH_THREADS) part[g.off_pm_logstd + j] = 0.f;   // fvp[logstd] is set by the reduce
+  __syncthreads();   // gb1s is re-zeroed by the next slab
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -601,7 +671,13 @@ static cudaError_t launch_shape(const NetGeom& g, const MidBwdArgs& a, int n_sla
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  chain_fvp_kernel<S, MRL_ACT_TANH><<<n_slabs, CH_THREADS, sm, st>>>(g, a, jobs);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  chain_fvp_kernel<S, MRL_ACT_TANH><<<n_slabs < sms ? n_slabs : sms, CH_THREADS, sm, st>>>(g, a, jobs, n_slabs);
   return cudaGetLastError();
 }
 
