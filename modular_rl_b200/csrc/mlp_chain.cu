@@ -446,13 +446,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
       const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
       const float* cb = a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr;
       const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
-      if (ct0 + 2 < t1) {   // pull the next chain tile into L2 while this one computes
-        const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + 2) * g.act_rows * MRL_LDT);
-        const int nb = min(2, t1 - ct0 - 2) * g.act_rows * MRL_LDT * 4;
-        for (int off = tid * 128; off < nb; off += CH_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + off));
-        const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT);
-        const int nz = min(2, t1 - ct0 - 2) * g.d[1] * MRL_LDT * 4;
-        for (int off = tid * 128; off < nz; off += CH_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + off));
+      if (ct0 + 2 < t1 && lane == 0) {   // pull the next chain tile into L2 while this one computes (bulk prefetch, 1/8 per warp)
+        const int nt2 = min(2, t1 - ct0 - 2);
+        const unsigned cbytes = (unsigned)(nt2 * g.act_rows * MRL_LDT * 4), zbytes = (unsigned)(nt2 * g.d[1] * MRL_LDT * 4);
+        const unsigned cchunk = (cbytes / CH_WARPS) & ~15u, zchunk = (zbytes / CH_WARPS) & ~15u;
+        const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + 2) * g.act_rows * MRL_LDT) + (size_t)warp * cchunk;
+        const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT) + (size_t)warp * zchunk;
+        const unsigned cn = warp == CH_WARPS - 1 ? cbytes - (CH_WARPS - 1) * cchunk : cchunk;
+        const unsigned zn = warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(cn) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(zn) : "memory");
       }
       float h2[N2][4];
 #pragma unroll
@@ -518,14 +521,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
         if constexpr (NB > 0)
           delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
       }
-      if (ok) {   // operand columns beyond the chain's padded width are zeros
-        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
-        for (int i = lane; i < 2 * 2 * 2 * (a.nu - 8 * N1) * 4; i += 32) {
-          // [tg 2][hi|lo 2][khalf 2][(nu/8 - N1) groups x 32]
-          const int per = (a.nu - 8 * N1) * 4;
-          const int blk = i / per, r = i - blk * per;
-          dg[(size_t)blk * (a.nu * 4) + 8 * N1 * 4 + r] = 0.f;
-        }
+      if (ok && a.nu > 8 * N1) {   // the one operand n-group beyond the chain's padded width is zeros
+        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8) + 8 * N1 * 4 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dg[(size_t)k * (a.nu * 4)] = 0.f;   // [tg 2][hi|lo 2][khalf 2] x 32 floats
       }
     }
     __syncthreads();
