@@ -176,20 +176,14 @@ __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n
   const long long k = t - offsets[lo];
   const float f = (float)((double)k / timestep_limit);
   if (tindex) tindex[t] = (int)k;
-  const float h = tf32_rna(f), l = tf32_rna(f - h);
-  {  // forward operand: [mtile][kg][hi|lo][khalf][mgroup][8 timesteps][4 features]
+  {  // forward operand: [mtile][kg][khalf][mgroup][8 timesteps][4 features]  (raw fp32, mlp_l1_tc.cu)
     const long long mt = t / 128;
     const int m = (int)(t % 128);
-    float* base = XA + ((size_t)mt * xa_kgroups + (col >> 3)) * 2048 + ((col & 7) >> 2) * 512 + (m >> 3) * 32 + (m & 7) * 4 + (col & 3);
-    base[0] = h;
-    base[1024] = l;
+    XA[((size_t)mt * xa_kgroups + (col >> 3)) * 1024 + ((col & 7) >> 2) * 512 + (m >> 3) * 32 + (m & 7) * 4 + (col & 3)] = f;
   }
-  {  // gradient operand: [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps]
+  {  // gradient operand: [tg][ftile][khalf][fgroup][8 features][4 timesteps]
     const int fm = col % 128;
-    float* base = XG + ((size_t)(t >> 3) * xg_ftiles + col / 128) * 2048 + (int)((t & 7) >> 2) * 512 + (fm >> 3) * 32 +
-                  (fm & 7) * 4 + (int)(t & 3);
-    base[0] = h;
-    base[1024] = l;
+    XG[((size_t)(t >> 3) * xg_ftiles + col / 128) * 1024 + (int)((t & 7) >> 2) * 512 + (fm >> 3) * 32 + (fm & 7) * 4 + (int)(t & 3)] = f;
   }
 }
 

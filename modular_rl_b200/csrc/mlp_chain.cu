@@ -54,14 +54,6 @@ struct ChainShape {
   }
 };
 
-// hi = rna_tf32(x) by integer arithmetic, lo = x - hi (exact).  lo is left to the tensor core's own
-// truncation: lo = x - rna(x) has a random sign relative to x, so truncating it toward zero is unbiased
-// (a 2^-22 relative random error per product), unlike a truncated hi (see mma_tf32.cuh).
-__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
 // row of feature j' (0..7) inside an 8x8 weight block: conflict-free for the 64-bit W reads (lanes g = 0..3 /
 // 4..7 of a half-warp hit rows with distinct (row mod 4)) and for the 32-bit W^T reads (rows 2t / 2t+1).
 __device__ __forceinline__ int blk_row(int j) { return j < 4 ? j : (j ^ 1); }
@@ -75,10 +67,10 @@ __device__ __forceinline__ void ldfrag(float (&v)[4], const float* __restrict__ 
 }
 // accumulator-order values (c0..c3) -> A-fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3), split
 __device__ __forceinline__ void to_frag(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
-  split3(v[0], hi[0], lo[0]);
-  split3(v[2], hi[1], lo[1]);
-  split3(v[1], hi[2], lo[2]);
-  split3(v[3], hi[3], lo[3]);
+  split_tf32(v[0], hi[0], lo[0]);
+  split_tf32(v[2], hi[1], lo[1]);
+  split_tf32(v[1], hi[2], lo[2]);
+  split_tf32(v[3], hi[3], lo[3]);
 }
 
 // acc[n] += A(k-step ks) . B(block), n-tiles nb .. nb+NT-1.  TRANS = false: B = W_l (K = in features, N = out),
@@ -104,8 +96,8 @@ __device__ __forceinline__ void kstep(float (&acc)[NT][4], const uint32_t (&ah)[
           b0 = p[blk_row(2 * t) * 8];
           b1 = p[blk_row(2 * t + 1) * 8];
         }
-        split3(b0, bh[q][0], bl[q][0]);
-        split3(b1, bh[q][1], bl[q][1]);
+        split_tf32(b0, bh[q][0], bl[q][0]);
+        split_tf32(b1, bh[q][1], bl[q][1]);
       }
     }
 #pragma unroll
@@ -331,7 +323,7 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t hi, lo;
-        split3(v[i], hi, lo);
+        split_tf32(v[i], hi, lo);
         // dg -> this warp's first timestep group; row g + 8 (i >> 1) of the warp's 16 timesteps
         float* p = dg + (size_t)(i >> 1) * (2 * nu * 8) + (g >> 2) * (nu * 4) + (nb + n) * 32 + (2 * t + (i & 1)) * 4 + (g & 3);
         p[0] = __uint_as_float(hi);
@@ -368,10 +360,10 @@ __device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* _
     for (int j = 0; j < 4; ++j) {
       const int ks = 4 * kg + j;
       uint32_t ah[4], al[4];
-      split3(ca[j].x, ah[0], al[0]);
-      split3(cb[j].x, ah[1], al[1]);
-      split3(ca[j].y, ah[2], al[2]);
-      split3(cb[j].y, ah[3], al[3]);
+      split_tf32(ca[j].x, ah[0], al[0]);
+      split_tf32(cb[j].x, ah[1], al[1]);
+      split_tf32(ca[j].y, ah[2], al[2]);
+      split_tf32(cb[j].y, ah[3], al[3]);
       uint32_t bh[CNT][2], bl[CNT][2];
 #pragma unroll
       for (int q = 0; q < CNT; ++q) {

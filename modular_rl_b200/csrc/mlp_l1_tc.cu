@@ -3,23 +3,28 @@
 //   l1_forward_tc_kernel : Z1[128 timesteps x NU] = X[128 x d0p] . B[d0p x NU]        (B = W1 or V1)
 //
 // FP32 parity (1e-5 relative, north_star) rules out plain TF32 (10-bit mantissa).  Every operand is
-// stored as hi = rna_tf32(x) and lo = rna_tf32(x - hi) - both exactly representable in TF32 - and
+// used as hi = rna_tf32(x) and lo = x - hi (the tensor core reads the top 19 bits of each) and
 // each K=8 step issues three MMAs  D += A_lo.B_hi ; D += A_hi.B_lo ; D += A_hi.B_hi  with FP32
 // accumulation in TMEM: per-product error ~2^-21, i.e. FP32-class results at 1/3 of the TF32 rate.
 //
 // Operands are pre-arranged in HBM in the UMMA canonical K-major / no-swizzle core-matrix order
 // (8 rows x 16 bytes per core matrix, SBO = 128 B between row groups, LBO between the two K halves),
-// so a pipeline stage is filled by two 1-D bulk async copies (UBLKCP) with no tensor map:
-//   A stage: [hi | lo] x [khalf 2][mgroup 16][8][4] floats (2 x 4 KB)  - one 128-timestep x 8-feature block
-//   B stage: [hi | lo] x [khalf 2][ngroup NU/8][8][4] floats
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter -> Z1 tile-major in HBM).
+// so a pipeline stage is filled by 1-D bulk async copies (UBLKCP) with no tensor map.  The observations
+// - the only operand that does not fit in L2 - are kept in HBM ONCE, as plain fp32 in that order; six
+// converter warps (one per pipeline stage) split each landed block into (hi, lo) in shared memory (hi in place), so the kernels
+// stream 4 bytes per observation element instead of 8: both are HBM-bound, this halves their traffic.
+//   A stage: [khalf 2][mgroup 16][8][4] floats raw (4 KB) -> hi in place, lo in the 4 KB behind it
+//   B stage: [hi | lo] x [khalf 2][ngroup NU/8][8][4] floats (weights / delta_1: small, pre-split)
+// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter -> HBM), warps 6..11 = converters.
 // Two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Persistent grid.
 #include "common.cuh"
 #include "kernels.h"
 
-#define TC_STAGES 6
-#define TC_THREADS 192
+#define TC_STAGES 12         // pipeline depth: ~4 KB of HBM data per stage must cover a ~4000-cycle round trip
+#define TC_CONV 6            // converter warps: warp c owns stages s = c (mod TC_CONV), visited in pipeline order
+                             // (a 1-bit phase parity must never be lapped)
+#define TC_THREADS (192 + 32 * TC_CONV)
 #define TC_M 128
 #define TC_WATCHDOG (1u << 27)
 
@@ -70,26 +75,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Converter: `blocks` raw 4 KB operand blocks, contiguous at st -> hi in place, lo `lo_off` bytes behind.
+// One warp per stage (converter warp c owns the stages s = c mod TC_CONV, so several stages convert
+// concurrently).  The generic-proxy writes are fenced for the async proxy (UMMA).
+__device__ __forceinline__ void convert_stage(unsigned char* st, int blocks, uint32_t lo_off, int lane) {
+  for (int b = 0; b < blocks; ++b) {
+    float4* p = reinterpret_cast<float4*>(st + (size_t)b * 4096) + lane;
+    float4* pl = reinterpret_cast<float4*>(st + (size_t)b * 4096 + lo_off) + lane;
+    float4 x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = p[32 * j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 h, l;
+#define MRL_SPLIT(X, H, L_)                                                   \
+      H = __uint_as_float((__float_as_uint(X) + 0x1000u) & 0xffffe000u);     \
+      L_ = __uint_as_float(__float_as_uint(X - H) + 0x1000u);   /* the tensor core truncates: pre-round */
+      MRL_SPLIT(x[j].x, h.x, l.x) MRL_SPLIT(x[j].y, h.y, l.y) MRL_SPLIT(x[j].z, h.z, l.z) MRL_SPLIT(x[j].w, h.w, l.w)
+#undef MRL_SPLIT
+      p[32 * j] = h;
+      pl[32 * j] = l;
+    }
+  }
+  fence_proxy_async();
+}
+
 // ------------------------------------------------------------------------------------
-// XA: [mtile][kg][hi|lo][khalf][mgroup][8][4]   WB: [kg][hi|lo][khalf][ngroup][8][4]
+// XA: [mtile][kg][khalf][mgroup][8][4] raw fp32   WB: [kg][hi|lo][khalf][ngroup][8][4]
 __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const float* __restrict__ XA,
                                                                       const float* __restrict__ WB,
                                                                       float* __restrict__ Zt, int kgroups,
                                                                       int xa_kgroups, int nu, int d1, int n_mtiles,
-                                                                      int n_tiles, int acc_cols) {
+                                                                      int n_tiles, int acc_cols, int nstages, int kps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [TC_STAGES]
   uint64_t* empty = full + TC_STAGES;                           // [TC_STAGES]
   uint64_t* tfull = empty + TC_STAGES;                          // [2]
   uint64_t* tempty = tfull + 2;                                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  unsigned char* stages = smem_raw + 256;
-  const uint32_t bytesA = 2 * TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
-  const uint32_t stage_bytes = bytesA + bytesB;
+  uint64_t* conv = tempty + 2;                                  // [TC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + TC_STAGES);
+  unsigned char* stages = smem_raw + 512;
+  // a stage holds kps k-groups (8 features each): [A hi: kps x 4 KB][A lo: kps x 4 KB][B: kps x (hi | lo)]
+  const uint32_t blkA = TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
+  const uint32_t offLo = kps * blkA, offB = 2 * kps * blkA;
+  const uint32_t stage_bytes = offB + kps * bytesB;
+  const int spt = (kgroups + kps - 1) / kps;                    // stages per tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -104,17 +138,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {   // ---------------- producer
-      uint32_t it = 0;
+    if (lane == 0) {   // ---------------- producer: one copy of the raw A blocks, one of the B blocks per stage
+      int s = 0, ph = 0;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-        const float* a_src = XA + (size_t)mt * xa_kgroups * (2 * TC_M * 8);
-        for (int kg = 0; kg < kgroups; ++kg, ++it) {
-          const int s = it % TC_STAGES;
-          mbar_wait_guard(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        const float* a_src = XA + (size_t)mt * xa_kgroups * (TC_M * 8);
+        for (int q = 0; q < spt; ++q) {
+          const int kg0 = q * kps, nk = min(kps, kgroups - kg0);
+          mbar_wait_guard(&empty[s], ph ^ 1);
           unsigned char* st = stages + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], stage_bytes);
-          bulk_g2s(st, a_src + (size_t)kg * (2 * TC_M * 8), bytesA, &full[s]);
-          bulk_g2s(st + bytesA, WB + (size_t)kg * (2 * nu * 8), bytesB, &full[s]);
+          mbar_expect_tx(&full[s], nk * (blkA + bytesB));
+          bulk_g2s(st, a_src + (size_t)kg0 * (TC_M * 8), nk * blkA, &full[s]);
+          bulk_g2s(st + offB, WB + (size_t)kg0 * (2 * nu * 8), nk * bytesB, &full[s]);
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -123,28 +158,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=TF32, K-major both
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
       const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;   // bytes between the two K halves
-      uint32_t it = 0, tcount = 0;
+      uint32_t tcount = 0;
+      int s = 0, ph = 0;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
         const int acc = tcount & 1;
         mbar_wait_guard(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        for (int kg = 0; kg < kgroups; ++kg, ++it) {
-          const int s = it % TC_STAGES;
-          mbar_wait_guard(&full[s], (it / TC_STAGES) & 1);
+        for (int q = 0; q < spt; ++q) {
+          const int nk = min(kps, kgroups - q * kps);
+          mbar_wait_guard(&full[s], ph);    // B landed
+          mbar_wait_guard(&conv[s], ph);    // A split into (hi, lo)
           tc_fence_after();
           const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
-          const uint64_t a_hi = umma_desc(sa, lboA, 128), a_lo = umma_desc(sa + bytesA / 2, lboA, 128);
-          const uint64_t b_hi = umma_desc(sa + bytesA, lboB, 128), b_lo = umma_desc(sa + bytesA + bytesB / 2, lboB, 128);
-          umma_tf32(d_tmem, a_lo, b_hi, idesc, kg > 0 ? 1u : 0u);   // small terms first
-          umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-          umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-          tc_commit(&empty[s]);          // frees the stage when the three MMAs have read it
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t a_hi = umma_desc(sa + j * blkA, lboA, 128), a_lo = umma_desc(sa + offLo + j * blkA, lboA, 128);
+            const uint64_t b_hi = umma_desc(sa + offB + j * bytesB, lboB, 128);
+            const uint64_t b_lo = umma_desc(sa + offB + j * bytesB + bytesB / 2, lboB, 128);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, (q | j) ? 1u : 0u);   // small terms first
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          tc_commit(&empty[s]);          // frees the stage when its MMAs have read it
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
         tc_commit(&tfull[acc]);          // accumulator complete
       }
     }
-  } else {             // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+  } else if (warp >= 6) {   // ---------------- converters: raw observations -> (hi, lo)
+    int s = 0, ph = 0;
+    for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+      for (int q = 0; q < spt; ++q) {
+        if (s % TC_CONV == warp - 6) {
+          if (lane == 0) mbar_wait_guard(&full[s], ph);
+          __syncwarp();
+          convert_stage(stages + (size_t)s * stage_bytes, min(kps, kgroups - q * kps), offLo, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv[s]);
+        }
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {   // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
     const int q = warp & 3;
     uint32_t tcount = 0;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
@@ -181,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
 // ------------------------------------------------------------------------------------
 // part1[slab][f][n] = sum_{t in slab} X[t][f] * delta1[t][n]  on the tensor cores:
 // D[128 features x NU] += A[128 x 8 timesteps] . B[NU x 8 timesteps]^T, K = timesteps.
-//   XG: [tg = t/8][ftile][hi|lo][khalf][fgroup 16][8 features][4 timesteps]
+//   XG: [tg = t/8][ftile][khalf][fgroup 16][8 features][4 timesteps]  raw fp32 (split by the converter warps)
 //   DG: [tg][hi|lo][khalf][ngroup NU/8][8][4 timesteps]       (written by mid_backward_kernel)
 // One CTA accumulates a whole slab (<= 1024 timesteps) for all feature tiles in TMEM (ftiles x
 // acc_cols columns), then the epilogue warps store the fp32 partial that reduce_partials_kernel sums
@@ -191,21 +246,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
                                                                    float* __restrict__ part1, int ftiles,
                                                                    int xg_ftiles, int nu, int d0, int n1p,
                                                                    int slab_tiles, int n_tiles, int n_slabs,
-                                                                   int acc_cols, int tmem_cols, int nstages) {
+                                                                   int acc_cols, int tmem_cols, int nstages, int kps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tfull = empty + TC_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  unsigned char* stages = smem_raw + 256;
-  const uint32_t bytesA1 = 2 * TC_M * 8 * 4;                 // one feature tile, hi + lo
-  const uint32_t bytesA = ftiles * bytesA1, bytesB = 2 * nu * 8 * 4;
-  const uint32_t stage_bytes = bytesA + bytesB;
+  uint64_t* conv = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + TC_STAGES);
+  unsigned char* stages = smem_raw + 512;
+  // a stage holds kps timestep groups (8 timesteps each):
+  // [A hi: kps x ftiles x 4 KB][A lo: same][B: kps x (hi | lo)]; HBM order of XG / DG = stage order
+  const uint32_t blkA = TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
+  const uint32_t offLo = kps * ftiles * blkA, offB = 2 * offLo;
+  const uint32_t stage_bytes = offB + kps * bytesB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 1); }
     mbar_init(&tfull[0], 1);
     mbar_init(&tempty[0], 4);
     fence_barrier_init();
@@ -221,50 +279,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
+    if (lane == 0) {   // producer: the raw feature-tile blocks of the stage's timestep groups (contiguous), then DG
+      int s = 0, ph = 0;
       for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
         const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
-        for (int tg = t0 * 8; tg < t1 * 8; ++tg, ++it) {
-          const int s = it % nstages;
-          mbar_wait_guard(&empty[s], ((it / nstages) & 1) ^ 1);
+        for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {   // t1 * 8 - t0 * 8 is a multiple of 8 >= kps
+          mbar_wait_guard(&empty[s], ph ^ 1);
           unsigned char* st = stages + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], stage_bytes);
-          bulk_g2s(st, XG + (size_t)tg * xg_ftiles * (2 * TC_M * 8), bytesA, &full[s]);
-          bulk_g2s(st + bytesA, DG + (size_t)tg * (2 * nu * 8), bytesB, &full[s]);
+          mbar_expect_tx(&full[s], offLo + kps * bytesB);
+          bulk_g2s(st, XG + (size_t)tg * xg_ftiles * (TC_M * 8), offLo, &full[s]);
+          bulk_g2s(st + offB, DG + (size_t)tg * (2 * nu * 8), kps * bytesB, &full[s]);
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0) {   // MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
       const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;
-      uint32_t it = 0, scount = 0;
+      int s = 0, ph = 0;
+      uint32_t scount = 0;
       for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
         const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
         mbar_wait_guard(&tempty[0], (scount & 1) ^ 1);
         tc_fence_after();
-        for (int tg = t0 * 8; tg < t1 * 8; ++tg, ++it) {
-          const int s = it % nstages;
-          mbar_wait_guard(&full[s], (it / nstages) & 1);
+        for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {
+          mbar_wait_guard(&full[s], ph);
+          mbar_wait_guard(&conv[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
-          const uint64_t b_hi = umma_desc(sa + bytesA, lboB, 128), b_lo = umma_desc(sa + bytesA + bytesB / 2, lboB, 128);
-          const uint32_t accf = tg > t0 * 8 ? 1u : 0u;
-          for (int ft = 0; ft < ftiles; ++ft) {
-            const uint32_t ab = sa + ft * bytesA1;
-            const uint64_t a_hi = umma_desc(ab, lboA, 128), a_lo = umma_desc(ab + bytesA1 / 2, lboA, 128);
-            const uint32_t d_tmem = tmem_base + ft * acc_cols;
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, accf);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          for (int j = 0; j < kps; ++j) {
+            const uint64_t b_hi = umma_desc(sa + offB + j * bytesB, lboB, 128);
+            const uint64_t b_lo = umma_desc(sa + offB + j * bytesB + bytesB / 2, lboB, 128);
+            const uint32_t accf = (tg + j) > t0 * 8 ? 1u : 0u;
+            for (int ft = 0; ft < ftiles; ++ft) {
+              const uint32_t ab = sa + (j * ftiles + ft) * blkA;
+              const uint64_t a_hi = umma_desc(ab, lboA, 128), a_lo = umma_desc(ab + offLo, lboA, 128);
+              const uint32_t d_tmem = tmem_base + ft * acc_cols;
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, accf);
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
           }
           tc_commit(&empty[s]);
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
         tc_commit(&tfull[0]);
       }
     }
-  } else {
+  } else if (warp >= 6) {   // converters
+    int s = 0, ph = 0;
+    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+      const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
+      for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {
+        if (s % TC_CONV == warp - 6) {
+          if (lane == 0) mbar_wait_guard(&full[s], ph);
+          __syncwarp();
+          convert_stage(stages + (size_t)s * stage_bytes, kps * ftiles, offLo, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv[s]);
+        }
+        if (++s == nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {   // epilogue warps 2..5
     const int q = warp & 3;
     uint32_t scount = 0;
     for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
@@ -314,19 +392,16 @@ __global__ void pack_xa_kernel(const T* __restrict__ src, long long ld, int ncol
   const int kg = kq4 >> 1, khalf = kq4 & 1;
   const long long mt = t / TC_M;
   const int m = (int)(t % TC_M);
-  float hi[4], lo[4];
+  float x[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = 4 * kq4 + j;
-    const float x = (t < N && c < ncols) ? (float)src[t * ld + c] : 0.f;
-    hi[j] = tf32_rna(x);
-    lo[j] = tf32_rna(x - hi[j]);
+    x[j] = (t < N && c < ncols) ? (float)src[t * ld + c] : 0.f;
   }
-  float* base = XA + ((size_t)mt * xa_kgroups + kg) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4;
-  *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  float* base = XA + ((size_t)mt * xa_kgroups + kg) * (TC_M * 8) + khalf * (TC_M * 4) + (m >> 3) * 32 + (m & 7) * 4;
+  *reinterpret_cast<float4*>(base) = make_float4(x[0], x[1], x[2], x[3]);
 }
-// src row-major [N x ld] -> XG [tg][ftile][hi|lo][khalf][fgroup][8 features][4 timesteps].
+// src row-major [N x ld] -> XG [tg][ftile][khalf][fgroup][8 features][4 timesteps] (raw fp32).
 // One thread per (4 consecutive timesteps, feature).
 template <typename T>
 __global__ void pack_xg_kernel(const T* __restrict__ src, long long ld, int ncols, long long N, float* __restrict__ XG,
@@ -336,31 +411,41 @@ __global__ void pack_xg_kernel(const T* __restrict__ src, long long ld, int ncol
   if (i >= n_tquads * fpad) return;
   const long long tq = i / fpad;
   const int f = (int)(i % fpad);
-  float hi[4], lo[4];
+  float x[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long t = tq * 4 + j;
-    const float x = (t < N && f < ncols) ? (float)src[t * ld + f] : 0.f;
-    hi[j] = tf32_rna(x);
-    lo[j] = tf32_rna(x - hi[j]);
+    x[j] = (t < N && f < ncols) ? (float)src[t * ld + f] : 0.f;
   }
   const long long tg = tq >> 1;
   const int khalf = (int)(tq & 1), ft = f / TC_M, fm = f % TC_M;
-  float* base = XG + ((size_t)tg * xg_ftiles + ft) * (2 * TC_M * 8) + khalf * (TC_M * 4) + (fm >> 3) * 32 + (fm & 7) * 4;
-  *reinterpret_cast<float4*>(base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<float4*>(base + TC_M * 8) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  float* base = XG + ((size_t)tg * xg_ftiles + ft) * (TC_M * 8) + khalf * (TC_M * 4) + (fm >> 3) * 32 + (fm & 7) * 4;
+  *reinterpret_cast<float4*>(base) = make_float4(x[0], x[1], x[2], x[3]);
 }
 
 // ------------------------------------------------------------------------------------ launchers
 int l1tc_nu(const NetGeom& g) { return round_up(g.d[1], 16); }
 size_t l1tc_wb_floats(const NetGeom& g) { return (size_t)g.d0p * l1tc_nu(g) * 2; }
-size_t l1tc_xa_floats(int xa_kgroups, long long n_mtiles) { return (size_t)n_mtiles * xa_kgroups * 2 * TC_M * 8; }
+size_t l1tc_xa_floats(int xa_kgroups, long long n_mtiles) { return (size_t)n_mtiles * xa_kgroups * TC_M * 8; }
 
 cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgroups, const float* WB, float* Zt,
                                  int n_tiles, cudaStream_t st) {
   const int nu = l1tc_nu(g);
   const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
-  const size_t smem = 256 + (size_t)TC_STAGES * (2 * TC_M * 8 * 4 + 2 * nu * 8 * 4);
+  // k-groups per stage: one stage hand-over (bulk copies, mbarrier round trips between the producer, converter
+  // and MMA threads) costs 500-1000 cycles whatever the copy size (tools/micro/bulk_rate*.cu), so a stage
+  // carries several k-groups.  Measured at 1M x 376 -> 100: 1 -> 0.90 ms, 2 -> 0.72, 3 -> 0.62, 4 (3 stages) -> 0.78.
+  int kps = 3;
+  size_t stage_bytes = 0;
+  int nstages = 0;
+  for (; kps >= 1; --kps) {
+    stage_bytes = (size_t)kps * (2 * TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
+    nstages = (int)((227 * 1024 - 512) / stage_bytes);
+    if (nstages >= 3 || kps == 1) break;
+  }
+  if (nstages > TC_STAGES) nstages = TC_STAGES;
+  if (nstages < 2) return cudaErrorInvalidConfiguration;
+  const size_t smem = 512 + (size_t)nstages * stage_bytes;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(l1_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -373,7 +458,7 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   const int n_mtiles = (n_tiles + 1) / 2;
   const int grid = n_mtiles < sms ? n_mtiles : sms;
   l1_forward_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XA, WB, Zt, g.d0p / 8, xa_kgroups, nu, g.d[1], n_mtiles, n_tiles,
-                                                       acc_cols);
+                                                       acc_cols, nstages, kps);
   return cudaGetLastError();
 }
 
@@ -386,7 +471,7 @@ cudaError_t launch_pack_xa(const void* src, int dtype, long long ld, int ncols, 
   else pack_xa_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, ld, ncols, N, XA, xa_kgroups, rows_out);
   return cudaGetLastError();
 }
-size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles) { return (size_t)n_tiles * 8 * xg_ftiles * 2 * TC_M * 8; }
+size_t l1tc_xg_floats(int xg_ftiles, long long n_tiles) { return (size_t)n_tiles * 8 * xg_ftiles * TC_M * 8; }
 size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles) { return (size_t)n_tiles * 8 * 2 * l1tc_nu(g) * 8; }
 
 cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, long long N, float* XG, int xg_ftiles,
@@ -407,11 +492,19 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
   int tmem_cols = 32;
   while (tmem_cols < ftiles * acc_cols) tmem_cols *= 2;
   if (tmem_cols > 512) return cudaErrorInvalidConfiguration;
-  const size_t stage_bytes = (size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4;
-  int nstages = (int)((227 * 1024 - 256) / stage_bytes);
+  // timestep groups per stage: 1 (a stage already carries ftiles x 3 MMAs; 2 measured no faster).  More than one
+  // would need the batch's XG feature tiles to be exactly the net's (contiguous copy) and divide 8.
+  int kps = 1;
+  size_t stage_bytes = 0;
+  int nstages = 0;
+  for (; kps >= 1; kps >>= 1) {
+    stage_bytes = (size_t)kps * ((size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4);
+    nstages = (int)((227 * 1024 - 512) / stage_bytes);
+    if (nstages >= 3 || kps == 1) break;
+  }
   if (nstages > TC_STAGES) nstages = TC_STAGES;
   if (nstages < 2) return cudaErrorInvalidConfiguration;
-  const size_t smem = 256 + (size_t)nstages * stage_bytes;
+  const size_t smem = 512 + (size_t)nstages * stage_bytes;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(l1_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -423,7 +516,7 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_slabs < sms ? n_slabs : sms;
   l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
-                                                    n_tiles, n_slabs, acc_cols, tmem_cols, nstages);
+                                                    n_tiles, n_slabs, acc_cols, tmem_cols, nstages, kps);
   return cudaGetLastError();
 }
 
@@ -434,5 +527,5 @@ bool l1tc_supported(const NetGeom& g) {
   const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
   if (nu > 256 || ftiles * acc_cols > 512) return false;
   const size_t stage_bytes = (size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4;
-  return 2 * stage_bytes + 256 <= 227 * 1024;
+  return 2 * stage_bytes + 512 <= 227 * 1024;
 }
