@@ -783,7 +783,7 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.slab_tiles = pl.slab_tiles;
   a.mode = mode;
   a.reverse_kl = reverse_kl;
-  if (mode == MRL_MODE_FVP && chain_fvp_shape(g) != 0) CKP(PK_MIDB_FVP, launch_chain_fvp(g, a, pl.n_slabs, st), 1);
+  if (chain_bwd_shape(g, mode) != 0) CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_chain_backward(g, a, pl.n_slabs, st), 1);
   else CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
                                 pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);

@@ -49,8 +49,9 @@ struct ChainShape {
     return s;
   }
   __host__ __device__ static constexpr int vbfloats() { return vboff(L_ + 1); }
-  __host__ __device__ static constexpr size_t smem_floats() {
-    return (size_t)2 * wfloats() + vbfloats() + 8 * nt(L_) + CH_WARPS * 8 * N1_ + (size_t)erows() * CH_LDE * 2;
+  __host__ __device__ static constexpr size_t smem_floats(bool fvp) {
+    return (size_t)(fvp ? 2 : 1) * wfloats() + (fvp ? vbfloats() : 0) + 16 * nt(L_) + CH_WARPS * 8 * (N1_ + nt(L_)) +
+           (size_t)erows() * CH_LDE * 2;
   }
 };
 
@@ -201,6 +202,119 @@ __device__ __forceinline__ void head_metric(const float (&acc)[NT][4], const flo
     if (!valid1) { v[2] = 0.f; v[3] = 0.f; }
     to_frag(v, hi[n], lo[n]);
   }
+}
+
+// dL/dz_L of the surrogate / penalised surrogate / squared error at the head (trpo.py:43, ppo.py:47-49,
+// core.py:613-617), un-normalised (1/N is applied by the slab reduce).  ho = cached head output (mean | probs |
+// value) in accumulator order; auxb = this warp's rows of the side inputs.  Also the logstd gradient partials.
+#define CH_LOG1P(x) log1pf(x)
+template <int NT>
+__device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], const float* __restrict__ auxb, int dL,
+                                          const float* __restrict__ sig, const float* __restrict__ ivar, float cs,
+                                          float ck, int reverse_kl, bool valid0, bool valid1, bool ok,
+                                          float (&gls)[NT][2], uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4],
+                                          int lane) {
+  const int t = lane & 3;
+  float d[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[n][i] = 0.f;
+  if (head == MRL_HEAD_GAUSS) {
+    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 8) : 0.f;
+    float ac[NT][4], m0[NT][4], s0[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      ldfrag(ac[n], auxb + MRL_LDT, 8 * n + 2 * t, dL, ok);
+      ldfrag(m0[n], auxb + (1 + dL) * MRL_LDT, 8 * n + 2 * t, dL, ok);
+      ldfrag(s0[n], auxb + (1 + 2 * dL) * MRL_LDT, 8 * n + 2 * t, dL, ok);
+    }
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        if (j < dL && ok) {
+          const float sg = sig[j];
+          const float tt = (ac[n][i] - ho[n][i]) / sg, t0 = (ac[n][i] - m0[n][i]) / s0[n][i];
+          const float v = -0.5f * (tt - t0) * (tt + t0) - CH_LOG1P((sg - s0[n][i]) / s0[n][i]);   // logp - oldlogp, term by term
+          if (i < 2) dl0 += v; else dl1 += v;
+        }
+      }
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1); dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1); dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+    const float w0 = -expf(dl0) * adv0 * cs, w1 = -expf(dl1) * adv1 * cs;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        const bool valid = i < 2 ? valid0 : valid1;
+        if (j < dL && valid) {
+          const float w = i < 2 ? w0 : w1;
+          const float sg = sig[j], iv = ivar[j], mu = ho[n][i], a_ = ac[n][i], m_ = m0[n][i], s_ = s0[n][i];
+          const float t2 = (a_ - mu) * (a_ - mu) * iv;
+          float dkl_dmu, dkl_dls;
+          if (!reverse_kl) {
+            dkl_dmu = (mu - m_) * iv;
+            dkl_dls = ((sg - s_) * (sg + s_) - (m_ - mu) * (m_ - mu)) * iv;   // 1 - (s0^2 + dm^2) / s1^2
+          } else {
+            const float i0 = 1.f / (s_ * s_);
+            dkl_dmu = (mu - m_) * i0;
+            dkl_dls = (sg - s_) * (sg + s_) * i0;                             // -1 + s1^2 / s0^2
+          }
+          d[n][i] = w * (a_ - mu) * iv + ck * dkl_dmu;
+          gls[n][i & 1] += w * (t2 - 1.f) + ck * dkl_dls;
+        }
+      }
+  } else if (head == MRL_HEAD_CAT) {
+    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 8) : 0.f;
+    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 8) : -1;
+    float p0[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) ldfrag(p0[n], auxb + 2 * MRL_LDT, 8 * n + 2 * t, dL, ok);
+    float pa0 = 0.f, pa1 = 0.f, qa0 = 0.f, qa1 = 0.f, kl0 = 0.f, kl1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        if (j < dL && ok) {
+          const float p = ho[n][i], q = p0[n][i];
+          if (i < 2) { if (j == ai0) { pa0 = p; qa0 = q; } } else { if (j == ai1) { pa1 = p; qa1 = q; } }
+          if (reverse_kl) { const float v = p * logf(p / q); if (i < 2) kl0 += v; else kl1 += v; }
+        }
+      }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      pa0 += __shfl_xor_sync(0xffffffffu, pa0, o); pa1 += __shfl_xor_sync(0xffffffffu, pa1, o);
+      qa0 += __shfl_xor_sync(0xffffffffu, qa0, o); qa1 += __shfl_xor_sync(0xffffffffu, qa1, o);
+      kl0 += __shfl_xor_sync(0xffffffffu, kl0, o); kl1 += __shfl_xor_sync(0xffffffffu, kl1, o);
+    }
+    const float w0 = valid0 ? -(pa0 / qa0) * adv0 * cs : 0.f, w1 = valid1 ? -(pa1 / qa1) * adv1 * cs : 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        const bool valid = i < 2 ? valid0 : valid1;
+        if (j < dL && valid) {
+          const float p = ho[n][i], q = p0[n][i];
+          const float w = i < 2 ? w0 : w1;
+          const int ai = i < 2 ? ai0 : ai1;
+          const float dk = reverse_kl ? p * (logf(p / q) - (i < 2 ? kl0 : kl1)) : (p - q);
+          d[n][i] = w * ((j == ai ? 1.f : 0.f) - p) + ck * dk;
+        }
+      }
+  } else {   // value head: d/dpred of (y - pred)^2
+    if (t == 0) {
+      if (valid0) d[0][0] = 2.f * (ho[0][0] - __ldg(auxb));
+      if (valid1) d[0][2] = 2.f * (ho[0][2] - __ldg(auxb + 8));
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) to_frag(d[n], hi[n], lo[n]);
 }
 
 // R-forward of layer 2: A = Rh1 = act'(h1) * (x.V1 + vb1) and A = h1, streamed from HBM per k-step
@@ -381,49 +495,60 @@ __device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* _
   }
 }
 
-template <class S, int ACT>
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, MidBwdArgs a, ChainJobs jobs, int n_slabs) {
+template <class S, int ACT, int MODE>
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, MidBwdArgs a, ChainJobs jobs, int n_slabs) {
   constexpr int L = S::L;
   constexpr int N1 = S::nt(1), N2 = S::nt(2), N3 = S::nt(3), N4 = S::nt(4);
   constexpr int NL = S::nt(L);
+  constexpr bool FVP = MODE == MRL_MODE_FVP;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
-  float* Vs = Ws + S::wfloats();
-  float* vb = Vs + S::wfloats();
-  float* ivar = vb + S::vbfloats();
-  float* gb1s = ivar + 8 * NL;
-  float* E = gb1s + CH_WARPS * 8 * N1;
+  float* Vs = Ws + S::wfloats();                       // tangent weights (Fvp only)
+  float* vb = Vs + (FVP ? S::wfloats() : 0);           // tangent biases (Fvp only)
+  float* ivar = vb + (FVP ? S::vbfloats() : 0);
+  float* sig = ivar + 8 * NL;
+  float* gb1s = sig + 8 * NL;                          // [warp][8 N1] layer-1 bias partials
+  float* glss = gb1s + CH_WARPS * 8 * N1;              // [warp][8 NL] logstd partials (gradient mode)
+  float* E = glss + CH_WARPS * 8 * NL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const bool cat = g.head == MRL_HEAD_CAT;
+  const bool cat = g.head == MRL_HEAD_CAT, gauss = g.head == MRL_HEAD_GAUSS;
 
-  // ---- weights of theta (W) and of the tangent (V) into the 8x8-block layout, tangent biases, 1/sigma^2
+  // ---- weights of theta (W) and of the tangent (V) into the 8x8-block layout, tangent biases, sigma, 1/sigma^2
 #pragma unroll
   for (int l = 2; l <= L; ++l) {
     const int kin = 8 * S::nt(l - 1), nout = 8 * S::nt(l);
     const float* src = a.img + g.off_W[l];
-    const float* srv = a.imgv + g.off_W[l];
     float* dw = Ws + S::woff(l);
-    float* dv = Vs + S::woff(l);
     for (int e = tid; e < kin * nout; e += CH_THREADS) {
       const int i = e / nout, j = e - i * nout;
       const bool ok = i < g.d[l - 1] && j < g.d[l];
       const int dst = ((i >> 3) * S::nt(l) + (j >> 3)) * 64 + blk_row(j & 7) * 8 + (i & 7);
       dw[dst] = ok ? src[i * g.ldw[l] + j] : 0.f;
-      dv[dst] = ok ? srv[i * g.ldw[l] + j] : 0.f;
+      if (FVP) Vs[S::woff(l) + dst] = ok ? a.imgv[g.off_W[l] + i * g.ldw[l] + j] : 0.f;
     }
   }
+  if (FVP) {
 #pragma unroll
-  for (int l = 1; l <= L; ++l)
-    for (int f = tid; f < 8 * S::nt(l); f += CH_THREADS) vb[S::vboff(l) + f] = f < g.d[l] ? a.imgv[g.off_b[l] + f] : 0.f;
-  for (int f = tid; f < 8 * NL; f += CH_THREADS)
-    ivar[f] = (!cat && f < g.d[L]) ? expf(-2.f * a.img[g.off_pm_logstd + f]) : 0.f;
+    for (int l = 1; l <= L; ++l)
+      for (int f = tid; f < 8 * S::nt(l); f += CH_THREADS) vb[S::vboff(l) + f] = f < g.d[l] ? a.imgv[g.off_b[l] + f] : 0.f;
+  }
+  for (int f = tid; f < 8 * NL; f += CH_THREADS) {
+    const float ls = (gauss && f < g.d[L]) ? a.img[g.off_pm_logstd + f] : 0.f;
+    sig[f] = expf(ls);
+    ivar[f] = (gauss && f < g.d[L]) ? expf(-2.f * ls) : 0.f;
+  }
+  float cs = 1.f, ck = 0.f;
+  if (!FVP && a.coef) { cs = (float)a.coef[0]; ck = (float)a.coef[1]; }
 
   for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {   // persistent: weights stay in shared memory
   const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
   float G[CH_NE][CH_NTJ][4];
 #pragma unroll
   for (int e = 0; e < CH_NE; ++e) zero_acc(G[e]);
+  float gls[NL][2];   // logstd gradient partials of this thread's columns (gradient mode, DiagGauss)
+#pragma unroll
+  for (int n = 0; n < NL; ++n) { gls[n][0] = 0.f; gls[n][1] = 0.f; }
   for (int i = tid; i < CH_WARPS * 8 * N1; i += CH_THREADS) gb1s[i] = 0.f;
   float gbe = 0.f;   // lane j: bias-gradient sum of delta row warp + 8 j
   __syncthreads();
@@ -437,86 +562,87 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
       const long long ts = (long long)ctile * MRL_TILE + rr;
       const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
       const float* cb = a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr;
-      const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
       if (ct0 + 2 < t1 && lane == 0) {   // pull the next chain tile into L2 while this one computes (bulk prefetch, 1/8 per warp)
         const int nt2 = min(2, t1 - ct0 - 2);
-        const unsigned cbytes = (unsigned)(nt2 * g.act_rows * MRL_LDT * 4), zbytes = (unsigned)(nt2 * g.d[1] * MRL_LDT * 4);
-        const unsigned cchunk = (cbytes / CH_WARPS) & ~15u, zchunk = (zbytes / CH_WARPS) & ~15u;
+        const unsigned cbytes = (unsigned)(nt2 * g.act_rows * MRL_LDT * 4);
+        const unsigned cchunk = (cbytes / CH_WARPS) & ~15u;
         const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + 2) * g.act_rows * MRL_LDT) + (size_t)warp * cchunk;
-        const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT) + (size_t)warp * zchunk;
         const unsigned cn = warp == CH_WARPS - 1 ? cbytes - (CH_WARPS - 1) * cchunk : cchunk;
-        const unsigned zn = warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(cn) : "memory");
+        const float* side = FVP ? a.Zt : a.aux;                    // Fvp: x.V1 ; gradient: adv / actions / old probs
+        const int srows = FVP ? g.d[1] : g.naux;
+        const unsigned zbytes = (unsigned)(nt2 * srows * MRL_LDT * 4);
+        const unsigned zchunk = (zbytes / CH_WARPS) & ~15u;
+        const char* pz = reinterpret_cast<const char*>(side + (size_t)(ct0 + 2) * srows * MRL_LDT) + (size_t)warp * zchunk;
+        const unsigned zn = warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(zn) : "memory");
       }
       float h2[N2][4];
 #pragma unroll
       for (int n = 0; n < N2; ++n) ldfrag(h2[n], cb + g.off_act[2] * MRL_LDT, 8 * n + 2 * t, g.d[2], ok);
-      // ---- R-forward
-      float acc2[N2][4];
-      zero_acc(acc2);
-      rfwd_layer2<ACT, N1, N2>(acc2, zb, cb, g.d[1], ok, vb + S::vboff(1), Ws + S::woff(2), Vs + S::woff(2), lane);
-      if constexpr (L == 3) {
-        float ph[N3][4];
-#pragma unroll
-        for (int n = 0; n < N3; ++n) ldfrag(ph[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok && cat);
-        uint32_t r2h[N2][4], r2l[N2][4];
-        epi_rhidden<ACT, N2>(acc2, h2, vb + S::vboff(2), r2h, r2l, lane);
-        float acc3[N3][4];
-        zero_acc(acc3);
-        rfwd_layer<N2, N3>(acc3, r2h, r2l, h2, Ws + S::woff(3), Vs + S::woff(3), lane);
-        uint32_t d3h[N3][4], d3l[N3][4];
-        head_metric<N3>(acc3, vb + S::vboff(3), ivar, ph, cat, valid0, valid1, d3h, d3l, lane);
-        store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, d3h, d3l, warp, lane);
-        // ---- reverse sweep
-        zero_acc(acc2);
-        delta_layer<N2, N3>(acc2, d3h, d3l, Ws + S::woff(3), 0, lane);
-        epi_delta<ACT, N2>(acc2, h2, r2h, r2l);
-        store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
-        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
-        constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
-        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
-        if constexpr (NB > 0)
-          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
-      } else {
-        float h3[N3][4];
+      float h3[L == 4 ? N3 : 1][4];
+      if constexpr (L == 4) {
 #pragma unroll
         for (int n = 0; n < N3; ++n) ldfrag(h3[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok);
-        float ph[N4][4];
+      }
+      float ph[NL][4];   // cached head output: probabilities (Fvp, Categorical) / mean | probs | value (gradient)
 #pragma unroll
-        for (int n = 0; n < N4; ++n) ldfrag(ph[n], cb + g.off_act[4] * MRL_LDT, 8 * n + 2 * t, g.d[4], ok && cat);
+      for (int n = 0; n < NL; ++n) ldfrag(ph[n], cb + g.off_act[L] * MRL_LDT, 8 * n + 2 * t, g.d[L], ok && (cat || !FVP));
+      uint32_t dLh[NL][4], dLl[NL][4];   // delta_L fragments
+      if constexpr (FVP) {
+        // ---- R-forward (Pearlmutter) and the Fisher metric
+        const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
+        float acc2[N2][4];
+        zero_acc(acc2);
+        rfwd_layer2<ACT, N1, N2>(acc2, zb, cb, g.d[1], ok, vb + S::vboff(1), Ws + S::woff(2), Vs + S::woff(2), lane);
         uint32_t r2h[N2][4], r2l[N2][4];
         epi_rhidden<ACT, N2>(acc2, h2, vb + S::vboff(2), r2h, r2l, lane);
         float acc3[N3][4];
         zero_acc(acc3);
         rfwd_layer<N2, N3>(acc3, r2h, r2l, h2, Ws + S::woff(3), Vs + S::woff(3), lane);
-        uint32_t r3h[N3][4], r3l[N3][4];
-        epi_rhidden<ACT, N3>(acc3, h3, vb + S::vboff(3), r3h, r3l, lane);
-        float acc4[N4][4];
-        zero_acc(acc4);
-        rfwd_layer<N3, N4>(acc4, r3h, r3l, h3, Ws + S::woff(4), Vs + S::woff(4), lane);
-        uint32_t d4h[N4][4], d4l[N4][4];
-        head_metric<N4>(acc4, vb + S::vboff(4), ivar, ph, cat, valid0, valid1, d4h, d4l, lane);
-        store_E<N4>(E + (size_t)S::eoff(4) * CH_LDE * 2, d4h, d4l, warp, lane);
-        // ---- reverse sweep
-        zero_acc(acc3);
-        delta_layer<N3, N4>(acc3, d4h, d4l, Ws + S::woff(4), 0, lane);
-        epi_delta<ACT, N3>(acc3, h3, r3h, r3l);
-        store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, r3h, r3l, warp, lane);
-        zero_acc(acc2);
-        delta_layer<N2, N3>(acc2, r3h, r3l, Ws + S::woff(3), 0, lane);
-        epi_delta<ACT, N2>(acc2, h2, r2h, r2l);
-        store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, r2h, r2l, warp, lane);
-        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
-        constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
-        delta1_block<ACT, NA, 0, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
-        if constexpr (NB > 0)
-          delta1_block<ACT, NB, NA, N1, N2>(r2h, r2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
+        if constexpr (L == 3) {
+          head_metric<N3>(acc3, vb + S::vboff(3), ivar, ph, cat, valid0, valid1, dLh, dLl, lane);
+        } else {
+          uint32_t r3h[N3][4], r3l[N3][4];
+          epi_rhidden<ACT, N3>(acc3, h3, vb + S::vboff(3), r3h, r3l, lane);
+          float acc4[NL][4];
+          zero_acc(acc4);
+          rfwd_layer<N3, NL>(acc4, r3h, r3l, h3, Ws + S::woff(4), Vs + S::woff(4), lane);
+          head_metric<NL>(acc4, vb + S::vboff(4), ivar, ph, cat, valid0, valid1, dLh, dLl, lane);
+        }
+      } else {
+        const float* auxb = a.aux + (size_t)ctile * g.naux * MRL_LDT + rr;
+        head_grad<NL>(g.head, ph, auxb, g.d[L], sig, ivar, cs, ck, a.reverse_kl, valid0, valid1, ok, gls, dLh, dLl, lane);
       }
+      // ---- reverse sweep
+      store_E<NL>(E + (size_t)S::eoff(L) * CH_LDE * 2, dLh, dLl, warp, lane);
+      uint32_t d2h[N2][4], d2l[N2][4];
+      {
+        float acc2[N2][4];
+        zero_acc(acc2);
+        if constexpr (L == 3) {
+          delta_layer<N2, N3>(acc2, dLh, dLl, Ws + S::woff(3), 0, lane);
+        } else {
+          float acc3[N3][4];
+          zero_acc(acc3);
+          delta_layer<N3, NL>(acc3, dLh, dLl, Ws + S::woff(4), 0, lane);
+          uint32_t d3h[N3][4], d3l[N3][4];
+          epi_delta<ACT, N3>(acc3, h3, d3h, d3l);
+          store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, d3h, d3l, warp, lane);
+          delta_layer<N2, N3>(acc2, d3h, d3l, Ws + S::woff(3), 0, lane);
+        }
+        epi_delta<ACT, N2>(acc2, h2, d2h, d2l);
+      }
+      store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, d2h, d2l, warp, lane);
+      float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
+      constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
+      delta1_block<ACT, NA, 0, N1, N2>(d2h, d2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
+      if constexpr (NB > 0)
+        delta1_block<ACT, NB, NA, N1, N2>(d2h, d2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
       if (ok && a.nu > 8 * N1) {   // the one operand n-group beyond the chain's padded width is zeros
-        float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8) + 8 * N1 * 4 + lane;
+        float* dgz = dg + 8 * N1 * 4 + lane;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dg[(size_t)k * (a.nu * 4)] = 0.f;   // [tg 2][hi|lo 2][khalf 2] x 32 floats
+        for (int k = 0; k < 8; ++k) dgz[(size_t)k * (a.nu * 4)] = 0.f;   // [tg 2][hi|lo 2][khalf 2] x 32 floats
       }
     }
     __syncthreads();
@@ -590,8 +716,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fvp_kernel(NetGeom g, Mid
     for (int w = 0; w < CH_WARPS; ++w) s += gb1s[w * 8 * N1 + f];   // fixed order -> deterministic
     part[g.off_b[1] + f] = s;
   }
-  for (int j = tid; j < g.d[L]; j += CH_THREADS) part[g.off_pm_logstd + j] = 0.f;   // fvp[logstd] is set by the reduce
-  __syncthreads();   // gb1s is re-zeroed by the next slab
+  if (!FVP && gauss) {   // logstd gradient: this thread's column sums -> across rows (shuffles) -> across warps (fixed order)
+#pragma unroll
+    for (int n = 0; n < NL; ++n)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float v = gls[n][b];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (gq == 0) glss[warp * 8 * NL + 8 * n + 2 * t + b] = v;
+      }
+    __syncthreads();
+    for (int j = tid; j < g.d[L]; j += CH_THREADS) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < CH_WARPS; ++w) sum += glss[w * 8 * NL + j];
+      part[g.off_pm_logstd + j] = sum;
+    }
+  } else {
+    for (int j = tid; j < g.d[L]; j += CH_THREADS) part[g.off_pm_logstd + j] = 0.f;   // fvp[logstd] is set by the reduce
+  }
+  __syncthreads();   // gb1s / glss are reused by the next slab
   }
 }
 
@@ -640,9 +786,9 @@ static bool build_jobs(const NetGeom& g, ChainJobs* jobs) {
 }
 
 template <class S>
-static bool shape_fits(const NetGeom& g) {
+static bool shape_fits(const NetGeom& g, int mode) {
   if (g.L != S::L || g.act != MRL_ACT_TANH) return false;
-  if (g.head != MRL_HEAD_GAUSS && g.head != MRL_HEAD_CAT) return false;
+  if (mode == MRL_MODE_FVP && g.head != MRL_HEAD_GAUSS && g.head != MRL_HEAD_CAT) return false;
   for (int l = 1; l <= S::L; ++l)
     if ((g.d[l] + 7) / 8 > S::nt(l)) return false;
   // the padded layer-1 width must cover every n-group of the layer-1 gradient operand but one
@@ -651,14 +797,14 @@ static bool shape_fits(const NetGeom& g) {
   return build_jobs<S>(g, &jobs);
 }
 
-template <class S>
+template <class S, int MODE>
 static cudaError_t launch_shape(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
   ChainJobs jobs;
   if (!build_jobs<S>(g, &jobs)) return cudaErrorInvalidConfiguration;
-  const size_t sm = S::smem_floats() * 4;
+  const size_t sm = S::smem_floats(MODE == MRL_MODE_FVP) * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_fvp_kernel<S, MRL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel<S, MRL_ACT_TANH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -668,28 +814,32 @@ static cudaError_t launch_shape(const NetGeom& g, const MidBwdArgs& a, int n_sla
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  chain_fvp_kernel<S, MRL_ACT_TANH><<<n_slabs < sms ? n_slabs : sms, CH_THREADS, sm, st>>>(g, a, jobs, n_slabs);
+  chain_bwd_kernel<S, MRL_ACT_TANH, MODE><<<n_slabs < sms ? n_slabs : sms, CH_THREADS, sm, st>>>(g, a, jobs, n_slabs);
   return cudaGetLastError();
 }
 
-typedef ChainShape<3, 8, 8, 1, 0> ShapeA;     // 64-64 hidden, <= 8 outputs  (Hopper, Walker2d, CartPole)
+typedef ChainShape<3, 8, 8, 1, 0> ShapeA;     // 64-64 hidden, <= 8 outputs  (Hopper, Walker2d, CartPole, value nets)
 typedef ChainShape<3, 8, 8, 3, 0> ShapeB;     // 64-64 hidden, <= 24 outputs (18-action Categorical)
-typedef ChainShape<4, 13, 7, 4, 3> ShapeC;    // 100-50-25 hidden, <= 24 outputs (Humanoid)
+typedef ChainShape<4, 13, 7, 4, 3> ShapeC;    // 100-50-25 hidden, <= 24 outputs (Humanoid policy and value nets)
 
 // 0 = not supported (use the job-list kernel of mlp_mid.cu), else the shape id
-int chain_fvp_shape(const NetGeom& g) {
-  if (shape_fits<ShapeA>(g)) return 1;
-  if (shape_fits<ShapeB>(g)) return 2;
-  if (shape_fits<ShapeC>(g)) return 3;
+int chain_bwd_shape(const NetGeom& g, int mode) {
+  if (shape_fits<ShapeA>(g, mode)) return 1;
+  if (shape_fits<ShapeB>(g, mode)) return 2;
+  if (shape_fits<ShapeC>(g, mode)) return 3;
   return 0;
 }
 
-cudaError_t launch_chain_fvp(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
-  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;   // chain tiles must not straddle slabs
-  switch (chain_fvp_shape(g)) {
-    case 1: return launch_shape<ShapeA>(g, a, n_slabs, st);
-    case 2: return launch_shape<ShapeB>(g, a, n_slabs, st);
-    case 3: return launch_shape<ShapeC>(g, a, n_slabs, st);
+template <int MODE>
+static cudaError_t launch_mode(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  switch (chain_bwd_shape(g, MODE)) {
+    case 1: return launch_shape<ShapeA, MODE>(g, a, n_slabs, st);
+    case 2: return launch_shape<ShapeB, MODE>(g, a, n_slabs, st);
+    case 3: return launch_shape<ShapeC, MODE>(g, a, n_slabs, st);
     default: return cudaErrorInvalidConfiguration;
   }
+}
+cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
+  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;   // chain tiles must not straddle slabs
+  return a.mode == MRL_MODE_FVP ? launch_mode<MRL_MODE_FVP>(g, a, n_slabs, st) : launch_mode<MRL_MODE_GRAD>(g, a, n_slabs, st);
 }
