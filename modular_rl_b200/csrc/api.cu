@@ -739,7 +739,8 @@ static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_ca
   a.n_tiles = b->n_tiles;
   a.slab_tiles = pl.slab_tiles;
   a.reverse_kl = reverse_kl;
-  CKP(PK_MIDF, launch_mid_forward(g, a, pl.n_slabs, st), 1);
+  if (chain_fwd_shape(g) != 0) CKP(PK_MIDF, launch_chain_forward(g, a, pl.n_slabs, st), 1);
+  else CKP(PK_MIDF, launch_mid_forward(g, a, pl.n_slabs, st), 1);
   if (want_losses) {
     CKL(launch_reduce_losses(n->loss_part.as<double>(), pl.n_slabs, 1.0 / (double)b->Nglobal, n->scal.as<double>(), st), 1);
     if (world_of(n) > 1) RET(mrl_comm_allreduce_f64(n->comm, n->scal.as<double>(), 4, st));

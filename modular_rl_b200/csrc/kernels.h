@@ -75,6 +75,8 @@ struct ChainEntry {
 struct ChainJobs { ChainEntry e[CH_WARPS][CH_NE]; };
 int chain_bwd_shape(const NetGeom& g, int mode);   // 0: not covered by an instantiated chain shape
 cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st);
+int chain_fwd_shape(const NetGeom& g);
+cudaError_t launch_chain_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st);
 
 // ---- vec_kernels.cu  (CG / line-search vector algebra on device-resident fp64 vectors)
 struct CgState {   // device-resident scalars

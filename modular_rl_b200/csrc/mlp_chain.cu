@@ -843,3 +843,320 @@ cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_s
   if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;   // chain tiles must not straddle slabs
   return a.mode == MRL_MODE_FVP ? launch_mode<MRL_MODE_FVP>(g, a, n_slabs, st) : launch_mode<MRL_MODE_GRAD>(g, a, n_slabs, st);
 }
+
+// ====================================================================================================
+// Forward chain: h1 = act(Z1 + b1), ..., head -> surr / kl / ent (or squared error) sums, activation cache,
+// row-major head output (trpo.py:37-42,60-63; core.py:339-365,402-438,613-617).  Same per-warp register
+// chain as above (16 timesteps per warp, no block barriers inside a slab), 8 warps = 128 timesteps per pass.
+#define CH_LOG_2PIE 2.8378770664093453f
+
+__device__ __forceinline__ void st_cfrag(float* __restrict__ p, const float (&v)[4], int f0, int dmax, bool ok) {
+  if (ok && f0 < dmax) { p[f0 * MRL_LDT] = v[0]; p[f0 * MRL_LDT + 8] = v[2]; }
+  if (ok && f0 + 1 < dmax) { p[(f0 + 1) * MRL_LDT] = v[1]; p[(f0 + 1) * MRL_LDT + 8] = v[3]; }
+}
+// hidden-layer epilogue: h = act(acc + b) -> cache, fragments of the next GEMM
+template <int ACT, int NT>
+__device__ __forceinline__ void epi_hidden(const float (&acc)[NT][4], const float* __restrict__ bl, float* __restrict__ cp,
+                                           int dmax, bool ok, uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4], int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float2 b = *reinterpret_cast<const float2*>(bl + 8 * n + 2 * t);
+    float v[4];
+    v[0] = act_fn<ACT>(acc[n][0] + b.x); v[1] = act_fn<ACT>(acc[n][1] + b.y);
+    v[2] = act_fn<ACT>(acc[n][2] + b.x); v[3] = act_fn<ACT>(acc[n][3] + b.y);
+    if (cp) st_cfrag(cp, v, 8 * n + 2 * t, dmax, ok);
+    to_frag(v, hi[n], lo[n]);
+  }
+}
+template <int NI, int NO>
+__device__ __forceinline__ void fwd_layer(float (&acc)[NO][4], const uint32_t (&ahi)[NI][4], const uint32_t (&alo)[NI][4],
+                                          const float* __restrict__ W, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < NI; ++ks) kstep<NO, false>(acc, ahi[ks], alo[ks], W, ks, 0, NO, lane);
+}
+
+// head of one warp's 16 timesteps: out = acc + b_L -> mean | softmax | value; losses; cache; row-major output
+template <int NT>
+__device__ __forceinline__ void head_forward(int head, float (&o)[NT][4], const float* __restrict__ bl,
+                                             const float* __restrict__ auxb, int dL, const float* __restrict__ sig,
+                                             float ent_row, int reverse_kl, bool valid0, bool valid1, bool ok,
+                                             double& s_surr, double& s_kl, double& s_ent, int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float2 b = *reinterpret_cast<const float2*>(bl + 8 * n + 2 * t);
+    o[n][0] += b.x; o[n][1] += b.y; o[n][2] += b.x; o[n][3] += b.y;
+  }
+  if (head == MRL_HEAD_GAUSS) {
+    if (auxb == nullptr) return;
+    float dl0 = 0.f, dl1 = 0.f, kl0 = 0.f, kl1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      float ac[4], m0[4], s0[4];
+      ldfrag(ac, auxb + MRL_LDT, 8 * n + 2 * t, dL, ok);
+      ldfrag(m0, auxb + (1 + dL) * MRL_LDT, 8 * n + 2 * t, dL, ok);
+      ldfrag(s0, auxb + (1 + 2 * dL) * MRL_LDT, 8 * n + 2 * t, dL, ok);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        if (j < dL && ok) {
+          const float sg = sig[j], mu = o[n][i];
+          const float tt = (ac[i] - mu) / sg, t0 = (ac[i] - m0[i]) / s0[i];
+          const float lr = log1pf((sg - s0[i]) / s0[i]);            // log(sigma / sigma0)
+          const float dlv = -0.5f * (tt - t0) * (tt + t0) - lr;     // logp - oldlogp, term by term
+          const float dm = m0[i] - mu;
+          // log(s1/s0) + (s0^2 + dm^2) / (2 s1^2) - 1/2 with the s0 ~ s1 cancellation taken analytically
+          const float den = reverse_kl ? s0[i] : sg;
+          const float u = (reverse_kl ? (sg - s0[i]) : (s0[i] - sg)) / den;
+          const float klv = u_minus_log1p(u) + 0.5f * (u * u + (dm / den) * (dm / den));
+          if (i < 2) { dl0 += dlv; kl0 += klv; } else { dl1 += dlv; kl1 += klv; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 1; q <= 2; q <<= 1) {
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, q); dl1 += __shfl_xor_sync(0xffffffffu, dl1, q);
+      kl0 += __shfl_xor_sync(0xffffffffu, kl0, q); kl1 += __shfl_xor_sync(0xffffffffu, kl1, q);
+    }
+    if (t == 0) {
+      if (valid0) { s_surr += (double)(expf(dl0) * __ldg(auxb)); s_kl += (double)kl0; s_ent += (double)ent_row; }
+      if (valid1) { s_surr += (double)(expf(dl1) * __ldg(auxb + 8)); s_kl += (double)kl1; s_ent += (double)ent_row; }
+    }
+  } else if (head == MRL_HEAD_CAT) {
+    float m0_ = -INFINITY, m1_ = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (8 * n + 2 * t + (i & 1) < dL) { if (i < 2) m0_ = fmaxf(m0_, o[n][i]); else m1_ = fmaxf(m1_, o[n][i]); }
+#pragma unroll
+    for (int q = 1; q <= 2; q <<= 1) {
+      m0_ = fmaxf(m0_, __shfl_xor_sync(0xffffffffu, m0_, q)); m1_ = fmaxf(m1_, __shfl_xor_sync(0xffffffffu, m1_, q));
+    }
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool in = 8 * n + 2 * t + (i & 1) < dL;
+        const float e = in ? expf(o[n][i] - (i < 2 ? m0_ : m1_)) : 0.f;
+        o[n][i] = e;
+        if (i < 2) z0 += e; else z1 += e;
+      }
+#pragma unroll
+    for (int q = 1; q <= 2; q <<= 1) { z0 += __shfl_xor_sync(0xffffffffu, z0, q); z1 += __shfl_xor_sync(0xffffffffu, z1, q); }
+    const float i0 = 1.f / z0, i1 = 1.f / z1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { o[n][0] *= i0; o[n][1] *= i0; o[n][2] *= i1; o[n][3] *= i1; }
+    if (auxb == nullptr) return;
+    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 8) : -1;
+    float pa0 = 0.f, pa1 = 0.f, qa0 = 0.f, qa1 = 0.f, kl0 = 0.f, kl1 = 0.f, en0 = 0.f, en1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      float p0[4];
+      ldfrag(p0, auxb + 2 * MRL_LDT, 8 * n + 2 * t, dL, ok);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 8 * n + 2 * t + (i & 1);
+        if (j < dL && ok) {
+          const float p = o[n][i];
+          // q log(q/w) = q g(v) - (w - q), v = (w - q)/q : no cancellation between the terms of the sum
+          const float q = reverse_kl ? p : p0[i], w = reverse_kl ? p0[i] : p;
+          const float klv = q * u_minus_log1p((w - q) / q) - (w - q);
+          const float env = -p * logf(p);
+          if (i < 2) { kl0 += klv; en0 += env; if (j == ai0) { pa0 = p; qa0 = p0[i]; } }
+          else { kl1 += klv; en1 += env; if (j == ai1) { pa1 = p; qa1 = p0[i]; } }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 1; q <= 2; q <<= 1) {
+      pa0 += __shfl_xor_sync(0xffffffffu, pa0, q); pa1 += __shfl_xor_sync(0xffffffffu, pa1, q);
+      qa0 += __shfl_xor_sync(0xffffffffu, qa0, q); qa1 += __shfl_xor_sync(0xffffffffu, qa1, q);
+      kl0 += __shfl_xor_sync(0xffffffffu, kl0, q); kl1 += __shfl_xor_sync(0xffffffffu, kl1, q);
+      en0 += __shfl_xor_sync(0xffffffffu, en0, q); en1 += __shfl_xor_sync(0xffffffffu, en1, q);
+    }
+    if (t == 0) {
+      if (valid0) { s_surr += (double)((pa0 / qa0) * __ldg(auxb)); s_kl += (double)kl0; s_ent += (double)en0; }
+      if (valid1) { s_surr += (double)((pa1 / qa1) * __ldg(auxb + 8)); s_kl += (double)kl1; s_ent += (double)en1; }
+    }
+  } else {   // value head: squared error against the target row
+    if (auxb != nullptr && t == 0) {
+      if (valid0) { const float df = __ldg(auxb) - o[0][0]; s_surr += (double)df * (double)df; }
+      if (valid1) { const float df = __ldg(auxb + 8) - o[0][2]; s_surr += (double)df * (double)df; }
+    }
+  }
+}
+
+template <class S, int ACT>
+__global__ void __launch_bounds__(CH_THREADS, 2) chain_fwd_kernel(NetGeom g, MidFwdArgs a, int n_slabs) {
+  constexpr int L = S::L;
+  constexpr int N1 = S::nt(1), N2 = S::nt(2), N3 = S::nt(3);
+  constexpr int NL = S::nt(L);
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;
+  float* bs = Ws + S::wfloats();      // biases of layers 1..L (vboff layout)
+  float* sig = bs + S::vbfloats();
+  __shared__ double red[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const bool gauss = g.head == MRL_HEAD_GAUSS;
+
+#pragma unroll
+  for (int l = 2; l <= L; ++l) {
+    const int kin = 8 * S::nt(l - 1), nout = 8 * S::nt(l);
+    const float* src = a.img + g.off_W[l];
+    float* dw = Ws + S::woff(l);
+    for (int e = tid; e < kin * nout; e += CH_THREADS) {
+      const int i = e / nout, j = e - i * nout;
+      const bool ok = i < g.d[l - 1] && j < g.d[l];
+      dw[((i >> 3) * S::nt(l) + (j >> 3)) * 64 + blk_row(j & 7) * 8 + (i & 7)] = ok ? src[i * g.ldw[l] + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int l = 1; l <= L; ++l)
+    for (int f = tid; f < 8 * S::nt(l); f += CH_THREADS) bs[S::vboff(l) + f] = f < g.d[l] ? a.img[g.off_b[l] + f] : 0.f;
+  float ent_row = 0.f;     // DiagGauss entropy is the same for every row: sum log sigma + d/2 log(2 pi e)
+  {
+    float sls = 0.f;
+    for (int j = 0; j < g.d[L] && gauss; ++j) sls += a.img[g.off_pm_logstd + j];
+    ent_row = sls + 0.5f * CH_LOG_2PIE * g.d[L];
+  }
+  for (int f = tid; f < 8 * NL; f += CH_THREADS) sig[f] = (gauss && f < g.d[L]) ? expf(a.img[g.off_pm_logstd + f]) : 1.f;
+  __syncthreads();
+
+  for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+    const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
+    double s_surr = 0.0, s_kl = 0.0, s_ent = 0.0;
+    for (int ct0 = t0; ct0 < t1; ct0 += 2) {
+      const int ctile = ct0 + (warp >> 2);
+      const bool ok = ctile < t1;
+      const int rr = ((warp & 3) << 4) + gq;
+      const long long ts = (long long)ctile * MRL_TILE + rr;
+      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
+      const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
+      float* cb = a.cache ? a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr : nullptr;
+      const float* auxb = a.aux ? a.aux + (size_t)ctile * g.naux * MRL_LDT + rr : nullptr;
+      if (ct0 + 2 < t1 && lane == 0) {   // next chain tile's layer-1 pre-activations (and side inputs) into L2
+        const int nt2 = min(2, t1 - ct0 - 2);
+        const unsigned zbytes = (unsigned)(nt2 * g.d[1] * MRL_LDT * 4), zchunk = (zbytes / CH_WARPS) & ~15u;
+        const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT) + (size_t)warp * zchunk;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk) : "memory");
+        if (a.aux) {
+          const unsigned xbytes = (unsigned)(nt2 * g.naux * MRL_LDT * 4), xchunk = (xbytes / CH_WARPS) & ~15u;
+          const char* px = reinterpret_cast<const char*>(a.aux + (size_t)(ct0 + 2) * g.naux * MRL_LDT) + (size_t)warp * xchunk;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(px), "r"(warp == CH_WARPS - 1 ? xbytes - (CH_WARPS - 1) * xchunk : xchunk) : "memory");
+        }
+      }
+      // ---- layer 1 activation streamed per k-step into the layer-2 GEMM
+      float acc2[N2][4];
+      zero_acc(acc2);
+      {
+        float zc[4], z1[4];
+        ldfrag(zc, zb, 2 * t, g.d[1], ok);
+        ldfrag(z1, zb, 8 + 2 * t, g.d[1], ok && N1 > 1);
+#pragma unroll 1
+        for (int ks = 0; ks < N1; ++ks) {
+          float zn[4];
+          ldfrag(zn, zb, 8 * (ks + 2) + 2 * t, g.d[1], ok && ks + 2 < N1);
+          const float2 b = *reinterpret_cast<const float2*>(bs + S::vboff(1) + 8 * ks + 2 * t);
+          float h[4];
+          if (L > 1) {
+            h[0] = act_fn<ACT>(zc[0] + b.x); h[1] = act_fn<ACT>(zc[1] + b.y);
+            h[2] = act_fn<ACT>(zc[2] + b.x); h[3] = act_fn<ACT>(zc[3] + b.y);
+          }
+          if (cb) st_cfrag(cb, h, 8 * ks + 2 * t, g.d[1], ok);
+          uint32_t ah[4], al[4];
+          to_frag(h, ah, al);
+          kstep<N2, false>(acc2, ah, al, Ws + S::woff(2), ks, 0, N2, lane);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { zc[i] = z1[i]; z1[i] = zn[i]; }
+        }
+      }
+      float o[NL][4];
+      if constexpr (L == 3) {
+        uint32_t h2h[N2][4], h2l[N2][4];
+        epi_hidden<ACT, N2>(acc2, bs + S::vboff(2), cb ? cb + g.off_act[2] * MRL_LDT : nullptr, g.d[2], ok, h2h, h2l, lane);
+        zero_acc(o);
+        fwd_layer<N2, NL>(o, h2h, h2l, Ws + S::woff(3), lane);
+      } else {
+        uint32_t h2h[N2][4], h2l[N2][4];
+        epi_hidden<ACT, N2>(acc2, bs + S::vboff(2), cb ? cb + g.off_act[2] * MRL_LDT : nullptr, g.d[2], ok, h2h, h2l, lane);
+        float acc3[N3][4];
+        zero_acc(acc3);
+        fwd_layer<N2, N3>(acc3, h2h, h2l, Ws + S::woff(3), lane);
+        uint32_t h3h[N3][4], h3l[N3][4];
+        epi_hidden<ACT, N3>(acc3, bs + S::vboff(3), cb ? cb + g.off_act[3] * MRL_LDT : nullptr, g.d[3], ok, h3h, h3l, lane);
+        zero_acc(o);
+        fwd_layer<N3, NL>(o, h3h, h3l, Ws + S::woff(4), lane);
+      }
+      head_forward<NL>(g.head, o, bs + S::vboff(L), auxb, g.d[L], sig, ent_row, a.reverse_kl, valid0, valid1, ok,
+                       s_surr, s_kl, s_ent, lane);
+      if (cb) {
+#pragma unroll
+        for (int n = 0; n < NL; ++n) st_cfrag(cb + g.off_act[L] * MRL_LDT, o[n], 8 * n + 2 * t, g.d[L], ok);
+      }
+      if (a.head_out) {
+        const int dL = g.d[L];
+#pragma unroll
+        for (int n = 0; n < NL; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 8 * n + 2 * t + (i & 1);
+            if (j < dL && (i < 2 ? valid0 : valid1)) a.head_out[(size_t)(ts + (i < 2 ? 0 : 8)) * dL + j] = o[n][i];
+          }
+      }
+    }
+    if (a.loss_part) {
+      double v0 = block_sum(s_surr, red);
+      double v1 = block_sum(s_kl, red);
+      double v2 = block_sum(s_ent, red);
+      if (tid == 0) {
+        double* op = a.loss_part + (size_t)slab * 4;
+        op[0] = v0; op[1] = v1; op[2] = v2; op[3] = 0.0;
+      }
+    }
+  }
+}
+
+template <class S>
+static bool fwd_shape_fits(const NetGeom& g) {
+  if (g.L != S::L || g.act != MRL_ACT_TANH) return false;
+  for (int l = 1; l <= S::L; ++l)
+    if ((g.d[l] + 7) / 8 > S::nt(l)) return false;
+  return true;
+}
+template <class S>
+static cudaError_t launch_fwd_shape(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
+  const size_t sm = ((size_t)S::wfloats() + S::vbfloats() + 8 * S::nt(S::L)) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel<S, MRL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  chain_fwd_kernel<S, MRL_ACT_TANH><<<n_slabs < 2 * sms ? n_slabs : 2 * sms, CH_THREADS, sm, st>>>(g, a, n_slabs);   // 2 CTAs per SM
+  return cudaGetLastError();
+}
+int chain_fwd_shape(const NetGeom& g) {
+  if (fwd_shape_fits<ShapeA>(g)) return 1;
+  if (fwd_shape_fits<ShapeB>(g)) return 2;
+  if (fwd_shape_fits<ShapeC>(g)) return 3;
+  return 0;
+}
+cudaError_t launch_chain_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
+  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;
+  switch (chain_fwd_shape(g)) {
+    case 1: return launch_fwd_shape<ShapeA>(g, a, n_slabs, st);
+    case 2: return launch_fwd_shape<ShapeB>(g, a, n_slabs, st);
+    case 3: return launch_fwd_shape<ShapeC>(g, a, n_slabs, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
