@@ -306,11 +306,11 @@ def main():
                 traffic = tr["kernels"][top]["read"] + tr["kernels"][top]["write"]
         except Exception:
             pass
-        pipes = {"mid_backward_fvp": "mma.sync TF32 x3 split precision (FP32-class accuracy) + FP32 epilogues",
-                 "mid_backward_grad": "mma.sync TF32 x3 split precision + FP32 heads",
-                 "mid_forward": "mma.sync TF32 x3 split precision + FP32 heads",
-                 "l1_forward": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, HBM-bound",
-                 "l1_grad": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, HBM-bound"}
+        pipes = {"mid_backward_fvp": "per-warp register chain, mma.sync TF32 x3 split precision (FP32-class accuracy) + FP32 epilogues",
+                 "mid_backward_grad": "per-warp register chain, mma.sync TF32 x3 split precision + FP32 heads",
+                 "mid_forward": "per-warp register chain, mma.sync TF32 x3 split precision + FP32 heads",
+                 "l1_forward": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, raw-fp32 operand split in shared memory",
+                 "l1_grad": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, raw-fp32 operand split in shared memory"}
         roof = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["algo_tflops"], "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": kernels[top]["algo_tflops"] / peak_tf, "traffic": traffic,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
