@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="timesteps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="sum over ranks with NCCL instead of the NVLink peer-memory push")
     return ap.parse_args()
 
 
@@ -188,9 +189,8 @@ def main():
     batch = DeviceBatch(wl.dims[0], True, device=local_rank)
     comm = None
     if world > 1:
-        uid = [Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        comm = Comm(uid[0], rank, world, local_rank)
+        from modular_rl_b200.parallel import comm_from_torch_distributed
+        comm = comm_from_torch_distributed(local_rank, p2p=not args.nccl_only)
         net.set_comm(comm)
     batch.set_obs(ob_h.numpy()).set_paths(offsets, terminated, float(wl.t_max))
     batch.set_global_n(n_total)
@@ -332,6 +332,8 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_desc(wl, n_total), "timesteps": n_total,
                            "timesteps_per_gpu": n_local, "parallelism": f"dp{world}",
+                           "allreduce": ("none" if world == 1 else ("nvlink peer-memory push (fused into the slab reduce)"
+                                                                    if comm.p2p else "nccl")),
                            "l2": "inputs larger than L2 (observations %.2f GB per GPU)" % (n_local * wl.dims[0] * 4 / 1e9),
                            **CFG},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

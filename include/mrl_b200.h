@@ -155,6 +155,14 @@ int mrl_comm_unique_id(char id_out[128]);
 int mrl_comm_create(mrl_comm** out, const char id[128], int rank, int world, int device);
 int mrl_comm_destroy(mrl_comm* c);
 int mrl_comm_allreduce_f64(mrl_comm* c, double* buf, long long n, void* stream); /* in place, device memory */
+/* Peer-memory transport over NVLink / NVSwitch (CUDA IPC) for vectors of <= max_doubles: every rank exports its
+ * receive buffer, the caller all-gathers the 64-byte handles (any side channel; torch.distributed in this repo)
+ * and every rank connects.  Afterwards the slab reduce PUSHES each rank's gradient / Fvp partial straight into
+ * its peers' buffers and a second kernel sums the slots in rank order (bit-identical on all ranks); NCCL stays
+ * the fallback for longer vectors.  All operations on one communicator must be enqueued on one stream. */
+int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char handle_out[64]);
+int mrl_comm_p2p_connect(mrl_comm* c, const char* handles /* [world][64] */);
+int mrl_comm_p2p_enable(mrl_comm* c, int on);   /* after every rank connected successfully */
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,9 @@ _SIGS = {
     "mrl_comm_create": (_I, [C.POINTER(_P), _P, _I, _I, _I]),
     "mrl_comm_destroy": (_I, [_P]),
     "mrl_comm_allreduce_f64": (_I, [_P, _P, _LL, _P]),
+    "mrl_comm_p2p_export": (_I, [_P, _LL, _P]),
+    "mrl_comm_p2p_connect": (_I, [_P, _P]),
+    "mrl_comm_p2p_enable": (_I, [_P, _I]),
 }
 
 

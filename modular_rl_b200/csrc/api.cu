@@ -789,12 +789,19 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
                                 pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
   const int world = world_of(n);
-  // terms that are not sums over timesteps are divided by `world` so that the all-reduce restores them
+  // terms that are not sums over timesteps are divided by `world` so that the sum over ranks restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;
+  const bool p2p = world > 1 && mrl_comm_p2p_ready(n->comm, g.P);
+  P2pPush push;
+  if (p2p) RET(mrl_comm_p2p_begin(n->comm, g.P, &push));
   CKP(PK_REDUCE, launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
-                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32, out64, st), 1);
-  if (world > 1) {
+                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32,
+                             p2p ? nullptr : out64, p2p ? &push : nullptr, st), 1);
+  if (p2p) {          // fused: the reduce kernel pushed this rank's vector to every peer; wait + sum in rank order
+    RET(mrl_comm_p2p_finish(n->comm, g.P, out64, out32, st));
+    g_launches += 1;
+  } else if (world > 1) {
     RET(mrl_comm_allreduce_f64(n->comm, out64, g.P, st));
     if (out32) {
       cast_f64_f32(out64, out32, g.P, st);

@@ -6,6 +6,7 @@
 // (advantages, actions, old probabilities, value targets) are repacked into the tile-major layout.
 #include "common.cuh"
 #include "kernels.h"
+#include "comm.h"
 
 // ------------------------------------------------------------------------------------
 // theta (flat, reference order) -> the shared-memory image and the layer-1 tensor-core operand
@@ -67,7 +68,7 @@ __global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, f
 __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     NetGeom g, const float* __restrict__ part1, const float* __restrict__ partm, int n_slabs, double scale,
     const float* __restrict__ theta, double l2c2, const float* __restrict__ vlogstd_src, double vls,
-    float* __restrict__ out32, double* __restrict__ out64) {
+    float* __restrict__ out32, double* __restrict__ out64, P2pPush push) {
   __shared__ double acc[RED_SY][RED_PX];
   const int px = threadIdx.x, sy = threadIdx.y;
   const int i = blockIdx.x * RED_PX + px;
@@ -114,7 +115,10 @@ __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     if (theta != nullptr) r += l2c2 * (double)theta[i];
     if (out32) out32[i] = (float)r;
     if (out64) out64[i] = r;
+    // data-parallel: this rank's partial goes straight into every peer's receive buffer over NVLink
+    if (push.world) p2p_push_value(push, i, r);
   }
+  if (push.world) p2p_push_done(push);
 }
 
 // loss partials [n_slabs][4] doubles -> out[4] = scale * sums (single block)
@@ -197,9 +201,11 @@ cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img,
 
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
-                                   float* out32, double* out64, cudaStream_t st) {
+                                   float* out32, double* out64, const P2pPush* push, cudaStream_t st) {
+  P2pPush none;
+  none.world = 0;
   reduce_partials_kernel<<<(g.P + RED_PX - 1) / RED_PX, dim3(RED_PX, RED_SY), 0, st>>>(
-      g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32, out64);
+      g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32, out64, push ? *push : none);
   return cudaGetLastError();
 }
 

@@ -56,9 +56,27 @@ static int nccl_fail(const char* what, int rc) {
   return mrl_set_error(buf);
 }
 
+// receive buffer of one rank: [flags 2 x 8][data 2 (parity) x world x cap]
+struct P2pState {
+  bool on = false;
+  long long cap = 0;                                  // doubles per slot
+  unsigned char* local = nullptr;                     // this rank's buffer (cudaMalloc)
+  unsigned char* peer[MRL_P2P_MAX_WORLD] = {nullptr}; // every rank's buffer as mapped here (peer[rank] == local)
+  unsigned int* counter = nullptr;
+  unsigned long long seq = 0;
+};
+#define P2P_HEADER 256
+static inline unsigned long long* p2p_flags(unsigned char* base, int parity) {
+  return reinterpret_cast<unsigned long long*>(base) + parity * MRL_P2P_MAX_WORLD;
+}
+static inline double* p2p_slot(unsigned char* base, long long cap, int world, int parity, int r) {
+  return reinterpret_cast<double*>(base + P2P_HEADER) + ((size_t)parity * world + r) * cap;
+}
+
 struct mrl_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  P2pState p2p;
 };
 int mrl_comm_world(const mrl_comm* c) { return c ? c->world : 1; }
 int mrl_comm_rank(const mrl_comm* c) { return c ? c->rank : 0; }
@@ -91,12 +109,138 @@ extern "C" int mrl_comm_create(mrl_comm** out, const char id[128], int rank, int
 }
 extern "C" int mrl_comm_destroy(mrl_comm* c) {
   if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->p2p.local) {
+    cudaDeviceSynchronize();
+    for (int q = 0; q < c->world; ++q)
+      if (q != c->rank && c->p2p.peer[q]) cudaIpcCloseMemHandle(c->p2p.peer[q]);
+    cudaFree(c->p2p.local);
+    cudaFree(c->p2p.counter);
+  }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------- peer-memory transport
+// Step 1 (every rank): allocate the receive buffer, return its CUDA IPC handle (64 bytes).
+extern "C" int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char handle_out[64]) {
+  if (!c || !handle_out || max_doubles <= 0) return mrl_set_error("mrl_comm_p2p_export: bad arguments");
+  if (c->world > MRL_P2P_MAX_WORLD) return mrl_set_error("mrl_comm_p2p_export: world > 8");
+  if (cudaSetDevice(c->device) != cudaSuccess) return mrl_set_error("mrl_comm_p2p_export: cudaSetDevice failed");
+  P2pState& p = c->p2p;
+  if (p.local) return mrl_set_error("mrl_comm_p2p_export: already exported");
+  p.cap = (max_doubles + 31) / 32 * 32;
+  const size_t bytes = P2P_HEADER + (size_t)2 * c->world * p.cap * 8;
+  if (cudaMalloc(&p.local, bytes) != cudaSuccess || cudaMalloc(&p.counter, 4) != cudaSuccess)
+    return mrl_set_error("mrl_comm_p2p_export: out of device memory");
+  cudaMemset(p.local, 0, bytes);
+  cudaMemset(p.counter, 0, 4);
+  cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p.local);
+  if (e != cudaSuccess) return mrl_set_error(cudaGetErrorString(e));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+// Step 2 (every rank, after an all-gather of the handles by the caller): map the peers' buffers.
+extern "C" int mrl_comm_p2p_connect(mrl_comm* c, const char* handles /* [world][64] */) {
+  if (!c || !handles || !c->p2p.local) return mrl_set_error("mrl_comm_p2p_connect: export first");
+  if (cudaSetDevice(c->device) != cudaSuccess) return mrl_set_error("mrl_comm_p2p_connect: cudaSetDevice failed");
+  P2pState& p = c->p2p;
+  for (int q = 0; q < c->world; ++q) {
+    if (q == c->rank) { p.peer[q] = p.local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)q * 64, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      char buf[200];
+      snprintf(buf, sizeof(buf), "mrl_comm_p2p_connect: cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+      return mrl_set_error(buf);
+    }
+    p.peer[q] = (unsigned char*)ptr;
+  }
+  return 0;
+}
+// Step 3 (every rank, once all ranks have connected): switch the transport on (or back off).
+extern "C" int mrl_comm_p2p_enable(mrl_comm* c, int on) {
+  if (!c) return mrl_set_error("mrl_comm_p2p_enable: null communicator");
+  if (on) {
+    for (int q = 0; q < c->world; ++q)
+      if (!c->p2p.peer[q]) return mrl_set_error("mrl_comm_p2p_enable: connect first");
+  }
+  c->p2p.on = on != 0;
+  return 0;
+}
+bool mrl_comm_p2p_ready(const mrl_comm* c, long long n) { return c && c->world > 1 && c->p2p.on && n <= c->p2p.cap; }
+
+int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push) {
+  if (!mrl_comm_p2p_ready(c, n)) return mrl_set_error("mrl_comm_p2p_begin: transport not ready");
+  P2pState& p = c->p2p;
+  p.seq += 1;
+  const int parity = (int)(p.seq & 1);
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) { push->slot[q] = nullptr; push->flag[q] = nullptr; }
+  for (int q = 0; q < c->world; ++q) {
+    push->slot[q] = p2p_slot(p.peer[q], p.cap, c->world, parity, c->rank);
+    push->flag[q] = p2p_flags(p.peer[q], parity) + c->rank;
+  }
+  push->counter = p.counter;
+  push->seq = p.seq;
+  push->world = c->world;
+  return 0;
+}
+
+// Wait until every rank's flag of this parity shows `seq`, then out[i] = sum_r slot[r][i] in rank order.
+// Double buffering by parity is enough: rank r can only start operation seq+2 after it has seen every
+// rank's flag for seq+1, which a rank raises after it finished reading the slots of seq.
+__global__ void p2p_gather_kernel(const unsigned long long* __restrict__ flags, const double* __restrict__ slots,
+                                  long long cap, int world, unsigned long long seq, long long n,
+                                  double* __restrict__ out64, float* __restrict__ out32) {
+  if (threadIdx.x < world) {
+    const volatile unsigned long long* f = flags + threadIdx.x;
+    unsigned int spins = 0;
+    while (*f < seq) {
+      if (++spins > (1u << 28)) __trap();   // a lost peer becomes an error, never a hung GPU
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += __ldcg(slots + (size_t)r * cap + i);
+    if (out64) out64[i] = s;
+    if (out32) out32[i] = (float)s;
+  }
+}
+int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st) {
+  P2pState& p = c->p2p;
+  const int parity = (int)(p.seq & 1);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 64) blocks = 64;     // all CTAs are resident: they spin on the flags
+  p2p_gather_kernel<<<blocks, 256, 0, st>>>(p2p_flags(p.local, parity), p2p_slot(p.local, p.cap, c->world, parity, 0), p.cap,
+                                            c->world, p.seq, n, out64, out32);
+  if (cudaGetLastError() != cudaSuccess) return mrl_set_error("p2p_gather_kernel launch failed");
+  return 0;
+}
+__global__ void p2p_push_kernel(const double* __restrict__ in, long long n, P2pPush push) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p2p_push_value(push, i, in[i]);
+  p2p_push_done(push);
+}
+
 extern "C" int mrl_comm_allreduce_f64(mrl_comm* c, double* buf, long long n, void* stream) {
   if (!c || c->world == 1) return 0;
+  if (mrl_comm_p2p_ready(c, n)) {
+    P2pPush push;
+    if (mrl_comm_p2p_begin(c, n, &push)) return 1;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 64) blocks = 64;
+    p2p_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(buf, n, push);
+    if (cudaGetLastError() != cudaSuccess) return mrl_set_error("p2p_push_kernel launch failed");
+    return mrl_comm_p2p_finish(c, n, buf, nullptr, (cudaStream_t)stream);
+  }
   int rc = g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, c->comm, (cudaStream_t)stream);
   if (rc != NCCL_SUCCESS) return nccl_fail("ncclAllReduce", rc);
   return 0;

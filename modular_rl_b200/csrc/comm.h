@@ -1,7 +1,48 @@
-// Data-parallel communicator: NCCL (the copy torch already loaded, found with dlopen) over NVLink.
+// Data-parallel communicator.  Two transports for the sum over ranks of small fp64 vectors:
+//   * peer memory over NVLink / NVSwitch (CUDA IPC): every rank PUSHES its vector into slot [rank] of every
+//     peer's receive buffer straight from the kernel that produced it, then each rank sums the slots in rank
+//     order - one NVLink hop, no collective launch, and bit-identical sums on all ranks;
+//   * NCCL (the copy torch already loaded, found with dlopen) as the fallback for vectors that do not fit the
+//     receive buffer or when peer access is unavailable.
 #pragma once
 #include <cuda_runtime.h>
+#define MRL_P2P_MAX_WORLD 8
 struct mrl_comm;
 int mrl_comm_world(const mrl_comm* c);
 int mrl_comm_rank(const mrl_comm* c);
 extern "C" int mrl_comm_allreduce_f64(mrl_comm* c, double* buf, long long n, void* stream);
+
+// One push target per rank: where this rank's values go in peer q's receive buffer, and the flag that tells q
+// they have landed.  Passed by value to the producing kernel (see reduce_partials_kernel).
+struct P2pPush {
+  double* slot[MRL_P2P_MAX_WORLD];
+  unsigned long long* flag[MRL_P2P_MAX_WORLD];
+  unsigned int* counter;        // device counter: the last CTA of the producing kernel raises the flags
+  unsigned long long seq;
+  int world;                    // 0: no push
+};
+bool mrl_comm_p2p_ready(const mrl_comm* c, long long n);
+// Begin one all-reduce of n doubles: fills `push` for the producing kernel.  Every begin must be followed by
+// mrl_comm_p2p_finish on the same stream.
+int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push);
+// Wait for all ranks' slots, sum them in rank order -> out64 (and out32 if not null)
+int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st);
+__device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) {
+#pragma unroll
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q)
+    if (q < p.world) p.slot[q][i] = v;
+}
+// Call once per CTA after its last p2p_push_value (all threads).  The last CTA to arrive raises the flags.
+__device__ __forceinline__ void p2p_push_done(const P2pPush& p) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    if (atomicAdd(p.counter, 1u) == total - 1) {
+      *p.counter = 0;
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) *reinterpret_cast<volatile unsigned long long*>(p.flag[q]) = p.seq;
+      __threadfence_system();
+    }
+  }
+}

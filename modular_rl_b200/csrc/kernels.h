@@ -6,7 +6,7 @@
 cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img, float* WB, cudaStream_t st);
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
-                                   float* out32, double* out64, cudaStream_t st);
+                                   float* out32, double* out64, const struct P2pPush* push, cudaStream_t st);
 cudaError_t launch_reduce_losses(const double* parts, int n_slabs, double scale, double* out, cudaStream_t st);
 cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncols, int ncols_out, long long N,
                               float* dst, int rows_per_tile, int row_off, int n_tiles, cudaStream_t st);

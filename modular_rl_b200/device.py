@@ -49,12 +49,29 @@ class Comm:
         buf = C.create_string_buffer(unique_id, 128)
         L.check(L.lib().mrl_comm_create(C.byref(self._h), buf, rank, world, device))
         self.rank, self.world = rank, world
+        self.p2p = False
 
     @staticmethod
     def unique_id() -> bytes:
         buf = C.create_string_buffer(128)
         L.check(L.lib().mrl_comm_unique_id(buf))
         return buf.raw
+
+    def p2p_export(self, max_doubles: int) -> bytes:
+        """Allocate this rank's NVLink receive buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        L.check(L.lib().mrl_comm_p2p_export(self._h, int(max_doubles), buf))
+        return buf.raw
+
+    def p2p_connect(self, handles) -> None:
+        """handles: the 64-byte handles of all ranks, in rank order (this rank's own included)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        L.check(L.lib().mrl_comm_p2p_connect(self._h, C.create_string_buffer(blob, len(blob))))
+
+    def p2p_enable(self, on: bool = True) -> None:
+        L.check(L.lib().mrl_comm_p2p_enable(self._h, int(on)))
+        self.p2p = bool(on)
 
     def close(self):
         if self._h:

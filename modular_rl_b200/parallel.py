@@ -75,12 +75,44 @@ def zfilter_prefix(states: Sequence[Tuple[float, np.ndarray, np.ndarray]], rank:
     return n, M, S
 
 
-def comm_from_torch_distributed(device: int):
-    """Build the library's NCCL communicator inside an initialised torch.distributed job: rank 0
-    creates the NCCL unique id, torch broadcasts it (plumbing only)."""
+P2P_MAX_DOUBLES = 1 << 17     # receive-slot size: covers parameter vectors up to 131 072 entries
+
+
+def comm_from_torch_distributed(device: int, p2p: bool = True):
+    """Build the library's communicator inside an initialised torch.distributed job: rank 0 creates the
+    NCCL unique id, torch broadcasts it (plumbing only).  With p2p (default) the ranks then exchange the
+    CUDA IPC handles of their NVLink receive buffers, so that parameter-sized sums bypass NCCL; if any rank
+    cannot map a peer (no peer access between the GPUs) every rank stays on NCCL."""
     import torch.distributed as dist
     from .device import Comm
     rank, world = dist.get_rank(), dist.get_world_size()
     box = [Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    return Comm(box[0], rank, world, device)
+    comm = Comm(box[0], rank, world, device)
+    if p2p and 1 < world <= 8:
+        enable_p2p(comm)
+    return comm
+
+
+def enable_p2p(comm, max_doubles: int = P2P_MAX_DOUBLES) -> bool:
+    """All ranks must call this together.  Returns True when the peer-memory transport is active."""
+    import torch.distributed as dist
+    try:
+        handle, err = comm.p2p_export(max_doubles), None
+    except RuntimeError as e:                       # every rank must still take part in the all-gather
+        handle, err = b"", str(e)
+    handles = [None] * comm.world
+    dist.all_gather_object(handles, (handle, err))
+    if any(e is not None for _, e in handles):
+        return False
+    ok = True
+    try:
+        comm.p2p_connect([h for h, _ in handles])
+    except RuntimeError:
+        ok = False
+    flags = [None] * comm.world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        return False
+    comm.p2p_enable(True)
+    return True

@@ -29,7 +29,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    comm = comm_from_torch_distributed(local)
+    comm = comm_from_torch_distributed(local, p2p=os.environ.get("MRL_NCCL_ONLY") != "1")
+    if rank == 0:
+        print("transport:", "nvlink peer-memory push" if comm.p2p else "nccl", flush=True)
 
     failures = []
     for name, dims, head in (("gauss", (23, 32, 16, 4), synth.GAUSS), ("cat", (10, 24, 24, 5), synth.CAT)):
