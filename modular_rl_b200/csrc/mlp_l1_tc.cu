@@ -57,6 +57,25 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// Descriptors of one kernel differ only in the start address (low 14 bits of the low word, units of 16 bytes;
+// shared memory is < 256 KB so adding an offset never carries out of the field): the MMA thread keeps the
+// low words as plain integers and adds offsets instead of rebuilding 64-bit descriptors - it is the ONE thread
+// that feeds the tensor core, and ~10 dependent integer instructions per descriptor x 4 per k-group cost more
+// cycles than the MMAs they describe.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_d),
+      "r"(da_lo), "r"(db_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\n"
@@ -158,6 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=TF32, K-major both
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
       const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;   // bytes between the two K halves
+      const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+      const uint32_t dA0 = umma_desc_lo(smem_u32(stages), lboA), dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
       uint32_t tcount = 0;
       int s = 0, ph = 0;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
@@ -170,14 +191,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
           mbar_wait_guard(&full[s], ph);    // B landed
           mbar_wait_guard(&conv[s], ph);    // A split into (hi, lo)
           tc_fence_after();
-          const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
+          uint32_t da = dA0 + s * (stage_bytes >> 4), db = dB0 + s * (stage_bytes >> 4);
           for (int j = 0; j < nk; ++j) {
-            const uint64_t a_hi = umma_desc(sa + j * blkA, lboA, 128), a_lo = umma_desc(sa + offLo + j * blkA, lboA, 128);
-            const uint64_t b_hi = umma_desc(sa + offB + j * bytesB, lboB, 128);
-            const uint64_t b_lo = umma_desc(sa + offB + j * bytesB + bytesB / 2, lboB, 128);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, (q | j) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            umma_tf32_lo(d_tmem, da + (offLo >> 4), db, desc_hi, idesc, (q | j) ? 1u : 0u);   // lo.hi: small terms first
+            umma_tf32_lo(d_tmem, da, db + (bytesB >> 5), desc_hi, idesc, 1u);                  // hi.lo
+            umma_tf32_lo(d_tmem, da, db, desc_hi, idesc, 1u);                                  // hi.hi
+            da += blkA >> 4;
+            db += bytesB >> 4;
           }
           tc_commit(&empty[s]);          // frees the stage when its MMAs have read it
           if (++s == nstages) { s = 0; ph ^= 1; }
@@ -297,6 +317,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
     if (lane == 0) {   // MMA issuer
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
       const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;
+      const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+      const uint32_t dA0 = umma_desc_lo(smem_u32(stages), lboA), dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
       int s = 0, ph = 0;
       uint32_t scount = 0;
       for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
@@ -307,19 +329,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
           mbar_wait_guard(&full[s], ph);
           mbar_wait_guard(&conv[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stages + (size_t)s * stage_bytes);
+          uint32_t da = dA0 + s * (stage_bytes >> 4), db = dB0 + s * (stage_bytes >> 4);
           for (int j = 0; j < kps; ++j) {
-            const uint64_t b_hi = umma_desc(sa + offB + j * bytesB, lboB, 128);
-            const uint64_t b_lo = umma_desc(sa + offB + j * bytesB + bytesB / 2, lboB, 128);
             const uint32_t accf = (tg + j) > t0 * 8 ? 1u : 0u;
+            uint32_t d_tmem = tmem_base;
             for (int ft = 0; ft < ftiles; ++ft) {
-              const uint32_t ab = sa + (j * ftiles + ft) * blkA;
-              const uint64_t a_hi = umma_desc(ab, lboA, 128), a_lo = umma_desc(ab + offLo, lboA, 128);
-              const uint32_t d_tmem = tmem_base + ft * acc_cols;
-              umma_tf32(d_tmem, a_lo, b_hi, idesc, accf);
-              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              umma_tf32_lo(d_tmem, da + (offLo >> 4), db, desc_hi, idesc, accf);
+              umma_tf32_lo(d_tmem, da, db + (bytesB >> 5), desc_hi, idesc, 1u);
+              umma_tf32_lo(d_tmem, da, db, desc_hi, idesc, 1u);
+              da += blkA >> 4;
+              d_tmem += acc_cols;
             }
+            db += bytesB >> 4;
           }
           tc_commit(&empty[s]);
           if (++s == nstages) { s = 0; ph ^= 1; }
