@@ -295,3 +295,71 @@ def test_ppo_lossgrad_golden(dev, golden, tag, ptag):
     assert relerr(g, og) < 2 * TOL
     assert relerr(g, golden[f"{tag}_{ptag}_grad"]) < 1e-4
     assert np.allclose(ls, golden[f"{tag}_{ptag}_losses"], rtol=1e-4, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- register-chain kernels at scale
+@pytest.mark.parametrize("name,N", [("hopper", 160_001), ("humanoid", 20_000), ("cat128", 9_999)])
+def test_chain_kernels_many_slabs(dev, name, N):
+    """The chain kernels (mlp_chain.cu) on batches that need several slabs per CTA (persistent loop, last slab and
+    last chain tile partial, N not a multiple of 64): losses, gradient and Fvp against the oracle."""
+    from modular_rl_b200 import synth
+    _, _, pm, *_ = _oracle()
+    dims, head, _ = SHAPES[name]
+    wl = synth.Workload(name, dims, head, N, 500, 17)
+    spec = pm.NetSpec(dims, pm.GAUSS if head == 0 else pm.CAT)
+
+    def fwd(th, ob):
+        _, z = pm.forward(th, spec, ob)
+        return z if head == 0 else pm.softmax(z)
+    d = synth.policy_batch(wl, fwd)
+    theta = synth.perturb(d["theta"], 0.02, 9)
+    net, batch = _bind(dev, spec.dims, head, d["ob"], d["act"], d["adv"], d["oldprob"], theta)
+    args = (d["ob"], d["act"], d["adv"], d["oldprob"])
+    assert np.allclose(net.losses(batch), pm.losses(theta, spec, *args), rtol=TOL, atol=2e-7)
+    g, _ = net.policy_gradient(batch)
+    assert relerr(g, pm.policy_gradient(theta, spec, *args)) < TOL
+    v = np.random.default_rng(5).standard_normal(net.P).astype(np.float32)
+    assert relerr(net.fvp(batch, v), pm.fisher_vector_product(theta, spec, d["ob"], v)) < TOL
+
+
+@pytest.mark.parametrize("vdims,N", [((12, 64, 64, 1), 7001), ((30, 100, 50, 25, 1), 5000)])
+def test_vf_lossgrad_chain_shapes(dev, vdims, N):
+    """NnVf loss / gradient (core.py:613-617) on value nets that take the chain kernels (value head)."""
+    from modular_rl_b200 import synth
+    *_, pm, _, vf, _ = _oracle()
+    rng = np.random.default_rng(3)
+    off = np.asarray(synth.make_paths(N, 300, rng)[0], np.int64)
+    ob = synth.make_obs(N, vdims[0] - 1, rng)
+    y = rng.standard_normal(N)
+    theta = synth.init_params(vdims, synth.VALUE, rng, last_scale=1.0)
+    net = dev.DeviceNet(vdims, 2)
+    b = dev.DeviceBatch(vdims[0] - 1, with_time_feature=True)
+    b.set_obs(ob).set_paths(off, np.ones(len(off) - 1, np.uint8), 300.0)
+    b.set_vf_target(y)
+    net.set_params(theta)
+    spec = pm.NetSpec(vdims, pm.VALUE)
+    tidx = np.concatenate([np.arange(off[i + 1] - off[i]) for i in range(len(off) - 1)])
+    x = np.concatenate([ob.astype(np.float64), (tidx / 300.0)[:, None]], axis=1)
+    pred = net.forward(b)
+    assert relerr(pred, vf.vf_forward(theta, spec, x)) < TOL
+    ls, g = net.vf_lossgrad(b, 1e-3)
+    _, og = vf.vf_lossgrad(theta, spec, x, y.reshape(-1, 1), l2coeff=1e-3)
+    assert np.allclose(ls, vf.vf_losses(theta, spec, x, y.reshape(-1, 1), l2coeff=1e-3), rtol=TOL)
+    assert relerr(g, og) < TOL
+
+
+@pytest.mark.parametrize("name", ["walker", "cat128"])
+@pytest.mark.parametrize("rev", [False, True])
+def test_ppo_lossgrad_chain_shapes(dev, name, rev):
+    """PpoLbfgsUpdater's penalised surrogate and gradient (ppo.py:35-49) on chain shapes, both KL directions."""
+    spec, head, theta, d = _synth_case(name)
+    _, _, pm, *_ = _oracle()
+    net, batch = _bind(dev, spec.dims, head, d["ob"], d["act"], d["adv"], d["oldprob"], theta)
+    args = (d["ob"], d["act"], d["adv"], d["oldprob"])
+    klc, cutoff = 0.7, 1e-4
+    pen, g, ls = net.ppo_lossgrad(batch, klc, cutoff, rev)
+    open_, og = pm.ppo_lossgrad(theta, spec, *args, klc, cutoff, reverse_kl=rev)
+    ols, _, _ = pm.surr_kl_grads(theta, spec, *args, ratio="lik", reverse_kl=rev)
+    dpen_dkl = klc + 2000.0 * (ols[1] > cutoff) * (ols[1] - cutoff)
+    assert abs(pen - open_) < TOL * (abs(ols[0]) + abs(dpen_dkl) * ols[1]) + 1e-7
+    assert relerr(g, og) < 2 * TOL
