@@ -12,7 +12,9 @@
 #include "kernels.h"
 
 #define GAE_THREADS 256
+#ifndef GAE_PER_THREAD
 #define GAE_PER_THREAD 4
+#endif
 #define GAE_CHUNK (GAE_THREADS * GAE_PER_THREAD)
 
 struct Aff { double a, b; };   // y_first = b + a * y_after
