@@ -379,6 +379,15 @@ class StochPolicy(object):
             return self.probtype.sample(prob)[0], {"prob": prob[0]}
         return self.probtype.maxprob(prob)[0], {"prob": prob[0]}
 
+    def act_batch(self, ob_no, stochastic=True):
+        """`act` for a block of observations (vectorised environments): ONE device
+        forward for all rows instead of one batch-1 call per environment step (core.py:193).  Returns
+        (actions [N, ...], {"prob": rows [N, K | 2d]}); row i is exactly what act(ob_no[i]) computes, the
+        sampling draws come from the same numpy generator (core.py:432-435, distributions.py:3-13)."""
+        prob = self._act_prob(np.asarray(ob_no))
+        act = self.probtype.sample(prob) if stochastic else self.probtype.maxprob(prob)
+        return act, {"prob": prob}
+
 
 class StochPolicyMLP(StochPolicy, EzFlat):
     """The reference's StochPolicyKeras (core.py:296-336) with the Keras Sequential replaced by a

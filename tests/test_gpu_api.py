@@ -173,3 +173,29 @@ def test_multi_gpu_parity_two_ranks():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, (out.stdout[-3000:], out.stderr[-3000:])
+
+
+@pytest.mark.parametrize("kind", ["box", "discrete"])
+def test_act_batch_matches_act(kind):
+    """Batched rollout-side inference: act_batch(obs) rows == act(ob) row by row (same probabilities, and the
+    same actions when the numpy generator is reseeded), and the ZFilter block scan == per-sample calls."""
+    from modular_rl_b200 import agentzoo, filters, spaces
+    rng = np.random.default_rng(1)
+    ob_space = spaces.Box(-np.ones(7), np.ones(7))
+    ac_space = spaces.Box(-np.ones(3), np.ones(3)) if kind == "box" else spaces.Discrete(4)
+    agent = agentzoo.TrpoAgent(ob_space, ac_space, dict(hid_sizes=[16, 8], timestep_limit=50))
+    obs = rng.standard_normal((37, 7))
+    z1, z2 = filters.ZFilter((7,), clip=5), filters.ZFilter((7,), clip=5)
+    fobs = z1.filter_batch(obs)
+    assert np.allclose(fobs, np.stack([z2(o) for o in obs]), rtol=1e-10, atol=1e-12)
+    pol = agent.policy
+    _, info = pol.act_batch(fobs, stochastic=False)
+    rows = np.stack([pol.act(o, stochastic=False)[1]["prob"] for o in fobs])
+    assert np.allclose(info["prob"], rows, rtol=1e-6, atol=1e-7)
+    np.random.seed(5)
+    a_batch, _ = pol.act_batch(fobs[:1], stochastic=True)
+    np.random.seed(5)
+    a_one, _ = pol.act(fobs[0], stochastic=True)
+    assert np.allclose(a_batch[0], a_one)
+    det, _ = pol.act_batch(fobs, stochastic=False)
+    assert len(det) == 37
