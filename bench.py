@@ -316,6 +316,7 @@ def main():
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
                                 "fallback 1.4 PFLOP/s sustained (of fallback)"),
                 "pipe": pipes.get(top, ""), "flops_counted": "algorithmic FP32 flops; each costs 3 TF32 MMAs",
+                "tf32_mma_tflops_issued": 3.0 * kernels[top]["algo_tflops"],
                 "fp32_fma_peak_tflops": fp32.value,
                 "frac_of_fp32_fma_peak": kernels[top]["algo_tflops"] / fp32.value,
                 "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
