@@ -76,6 +76,22 @@ __device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t da_lo, ui
       "r"(da_lo), "r"(db_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from tensor memory ([128 lanes = rows] x [8 columns = k]), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t db_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(db_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\n"
@@ -125,7 +141,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
                                                                       const float* __restrict__ WB,
                                                                       float* __restrict__ Zt, int kgroups,
                                                                       int xa_kgroups, int nu, int d1, int n_mtiles,
-                                                                      int n_tiles, int acc_cols, int nstages, int kps) {
+                                                                      int n_tiles, int acc_cols, int n_acc, int tmem_cols,
+                                                                      int nstages, int kps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [TC_STAGES]
   uint64_t* empty = full + TC_STAGES;                           // [TC_STAGES]
@@ -134,21 +151,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
   uint64_t* conv = tempty + 2;                                  // [TC_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + TC_STAGES);
   unsigned char* stages = smem_raw + 512;
-  // a stage holds kps k-groups (8 features each): [A hi: kps x 4 KB][A lo: kps x 4 KB][B: kps x (hi | lo)]
+  // a stage holds kps k-groups (8 features each): [A raw fp32: kps x 4 KB][B: kps x (hi | lo)].  The converter
+  // warps move A into tensor memory as (hi, lo): the MMAs then read only B from shared memory - with both
+  // operands in shared memory the three MMAs of a k-group read 22.5 KB of it, the converter and the bulk copies
+  // another 23 KB, and shared-memory bandwidth (128 B/cycle), not the tensor pipe, set the pace.
   const uint32_t blkA = TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
-  const uint32_t offLo = kps * blkA, offB = 2 * kps * blkA;
+  const uint32_t offB = kps * blkA;
   const uint32_t stage_bytes = offB + kps * bytesB;
   const int spt = (kgroups + kps - 1) / kps;                    // stages per tile
+  const uint32_t a_col0 = n_acc * acc_cols;                     // TMEM: accumulators, then the A ring [stage][kg][hi 8 | lo 8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 4); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) {   // TMEM: 2 accumulators of acc_cols columns each
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(2 * acc_cols)));
+                 "r"((uint32_t)tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -176,55 +197,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
     if (lane == 0) {   // ---------------- MMA issuer
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=TF32, K-major both
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
-      const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;   // bytes between the two K halves
+      const uint32_t lboB = nu * 4 * 4;   // bytes between the two K halves
       const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
-      const uint32_t dA0 = umma_desc_lo(smem_u32(stages), lboA), dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
+      const uint32_t dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
       uint32_t tcount = 0;
       int s = 0, ph = 0;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
-        const int acc = tcount & 1;
-        mbar_wait_guard(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        const int acc = n_acc == 2 ? (tcount & 1) : 0;
+        mbar_wait_guard(&tempty[acc], (n_acc == 2 ? ((tcount >> 1) & 1) : (tcount & 1)) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int q = 0; q < spt; ++q) {
           const int nk = min(kps, kgroups - q * kps);
           mbar_wait_guard(&full[s], ph);    // B landed
-          mbar_wait_guard(&conv[s], ph);    // A split into (hi, lo)
+          mbar_wait_guard(&conv[s], ph);    // A is in tensor memory as (hi, lo)
           tc_fence_after();
-          uint32_t da = dA0 + s * (stage_bytes >> 4), db = dB0 + s * (stage_bytes >> 4);
+          uint32_t db = dB0 + s * (stage_bytes >> 4);
+          uint32_t ta = tmem_base + a_col0 + (uint32_t)(s * kps) * 16;
           for (int j = 0; j < nk; ++j) {
-            umma_tf32_lo(d_tmem, da + (offLo >> 4), db, desc_hi, idesc, (q | j) ? 1u : 0u);   // lo.hi: small terms first
-            umma_tf32_lo(d_tmem, da, db + (bytesB >> 5), desc_hi, idesc, 1u);                  // hi.lo
-            umma_tf32_lo(d_tmem, da, db, desc_hi, idesc, 1u);                                  // hi.hi
-            da += blkA >> 4;
+            umma_tf32_ts(d_tmem, ta + 8, db, desc_hi, idesc, (q | j) ? 1u : 0u);   // lo.hi: small terms first
+            umma_tf32_ts(d_tmem, ta, db + (bytesB >> 5), desc_hi, idesc, 1u);      // hi.lo
+            umma_tf32_ts(d_tmem, ta, db, desc_hi, idesc, 1u);                      // hi.hi
+            ta += 16;
             db += bytesB >> 4;
           }
-          tc_commit(&empty[s]);          // frees the stage when its MMAs have read it
+          tc_commit(&empty[s]);          // frees the stage (B in shared memory, A in tensor memory)
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
         tc_commit(&tfull[acc]);          // accumulator complete
       }
     }
-  } else if (warp >= 6) {   // ---------------- converters: raw observations -> (hi, lo)
+  } else if (warp >= 6 && warp < 10) {   // ---------------- converters: raw A rows -> tensor memory (hi, lo)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;     // row of the 128-timestep tile
     int s = 0, ph = 0;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
       for (int q = 0; q < spt; ++q) {
-        if (s % TC_CONV == warp - 6) {
-          if (lane == 0) mbar_wait_guard(&full[s], ph);
-          __syncwarp();
-          convert_stage(stages + (size_t)s * stage_bytes, min(kps, kgroups - q * kps), offLo, lane);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&conv[s]);
+        const int nk = min(kps, kgroups - q * kps);
+        mbar_wait_guard(&full[s], ph);
+        const unsigned char* st = stages + (size_t)s * stage_bytes;
+        uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0 + (uint32_t)(s * kps) * 16;
+        for (int j = 0; j < nk; ++j) {
+          const float4 x0 = *reinterpret_cast<const float4*>(st + (size_t)j * blkA + (size_t)m * 16);          // k 0..3
+          const float4 x1 = *reinterpret_cast<const float4*>(st + (size_t)j * blkA + 2048 + (size_t)m * 16);   // k 4..7
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            hi[k] = (__float_as_uint(x[k]) + 0x1000u) & 0xffffe000u;
+            lo[k] = __float_as_uint(x[k] - __uint_as_float(hi[k])) + 0x1000u;   // the tensor core truncates: pre-round
+          }
+          tmem_st8(ta, hi);
+          tmem_st8(ta + 8, lo);
+          ta += 16;
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 2) {   // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+  } else if (warp >= 2 && warp < 6) {   // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
     const int q = warp & 3;
     uint32_t tcount = 0;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
-      const int acc = tcount & 1;
-      mbar_wait_guard(&tfull[acc], (tcount >> 1) & 1);
+      const int acc = n_acc == 2 ? (tcount & 1) : 0;
+      mbar_wait_guard(&tfull[acc], n_acc == 2 ? ((tcount >> 1) & 1) : (tcount & 1));
       tc_fence_after();
       const int r = q * 32 + lane;                 // timestep row inside the 128-row tile
       const int tile = 2 * mt + (r >> 6);
@@ -249,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * acc_cols)));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
   }
 }
 
@@ -453,19 +492,20 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
                                  int n_tiles, cudaStream_t st) {
   const int nu = l1tc_nu(g);
   const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
+  const int n_acc = acc_cols <= 128 ? 2 : 1;     // double-buffered accumulator when tensor memory has room
   // k-groups per stage: one stage hand-over (bulk copies, mbarrier round trips between the producer, converter
   // and MMA threads) costs 500-1000 cycles whatever the copy size (tools/micro/bulk_rate*.cu), so a stage
-  // carries several k-groups.  Measured at 1M x 376 -> 100: 1 -> 0.90 ms, 2 -> 0.72, 3 -> 0.62, 4 (3 stages) -> 0.78.
-  int kps = 3;
-  size_t stage_bytes = 0;
-  int nstages = 0;
-  for (; kps >= 1; --kps) {
-    stage_bytes = (size_t)kps * (2 * TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
-    nstages = (int)((227 * 1024 - 512) / stage_bytes);
-    if (nstages >= 3 || kps == 1) break;
-  }
+  // carries 3 k-groups.  Stage count: shared memory (227 KB) and the tensor-memory A ring (48 columns per stage
+  // behind the accumulators, 512 columns in all).
+  const int kps = 3;
+  const size_t stage_bytes = (size_t)kps * (TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
+  int nstages = (int)((227 * 1024 - 512) / stage_bytes);
+  const int tmem_room = (512 - n_acc * acc_cols) / (kps * 16);
+  if (nstages > tmem_room) nstages = tmem_room;
   if (nstages > TC_STAGES) nstages = TC_STAGES;
   if (nstages < 2) return cudaErrorInvalidConfiguration;
+  int tmem_cols = 32;
+  while (tmem_cols < n_acc * acc_cols + nstages * kps * 16) tmem_cols *= 2;
   const size_t smem = 512 + (size_t)nstages * stage_bytes;
   static size_t attr = 0;
   if (smem > attr) {
@@ -479,7 +519,7 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   const int n_mtiles = (n_tiles + 1) / 2;
   const int grid = n_mtiles < sms ? n_mtiles : sms;
   l1_forward_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XA, WB, Zt, g.d0p / 8, xa_kgroups, nu, g.d[1], n_mtiles, n_tiles,
-                                                       acc_cols, nstages, kps);
+                                                       acc_cols, n_acc, tmem_cols, nstages, kps);
   return cudaGetLastError();
 }
 
