@@ -28,6 +28,15 @@
 #define TC_M 128
 #define TC_WATCHDOG (1u << 27)
 
+#ifdef MRL_TRACE
+// Pipeline trace of CTA 0 of l1_forward_tc_kernel (experiments only: build.sh -DMRL_TRACE, tools/micro/l1_trace.py):
+// clock64 of event e for stage use u
+__device__ long long g_trace[8][512];
+#define TRACE(e, u) do { if (blockIdx.x == 0 && (u) < 512) g_trace[e][u] = clock64(); } while (0)
+extern "C" int mrl_debug_l1_trace(long long* out) { return cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)) != cudaSuccess; }
+#else
+#define TRACE(e, u) do { } while (0)
+#endif
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
@@ -41,6 +50,25 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) 
     if (done) return;
     if (++spins > TC_WATCHDOG) __trap();   // a protocol bug becomes an error, never a hung GPU
   }
+}
+// warp-converged election of one lane (the pattern the tcgen05 issue path is compiled best for: inside an
+// `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// one non-blocking probe: true if the phase with this parity has completed
+__device__ __forceinline__ bool mbar_probe(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -179,62 +207,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
 
   if (warp == 0) {
     if (lane == 0) {   // ---------------- producer: one copy of the raw A blocks, one of the B blocks per stage
-      int s = 0, ph = 0;
+      int s = 0, ph = 0, u = 0;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const float* a_src = XA + (size_t)mt * xa_kgroups * (TC_M * 8);
-        for (int q = 0; q < spt; ++q) {
+        for (int q = 0; q < spt; ++q, ++u) {
           const int kg0 = q * kps, nk = min(kps, kgroups - kg0);
           mbar_wait_guard(&empty[s], ph ^ 1);
+          TRACE(0, u);
           unsigned char* st = stages + (size_t)s * stage_bytes;
           mbar_expect_tx(&full[s], nk * (blkA + bytesB));
           bulk_g2s(st, a_src + (size_t)kg0 * (TC_M * 8), nk * blkA, &full[s]);
           bulk_g2s(st + offB, WB + (size_t)kg0 * (2 * nu * 8), nk * bytesB, &full[s]);
+          TRACE(1, u);
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---------------- MMA issuer
+    {                  // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=TF32, K-major both
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
       const uint32_t lboB = nu * 4 * 4;   // bytes between the two K halves
       const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
       const uint32_t dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
       uint32_t tcount = 0;
-      int s = 0, ph = 0;
+      int s = 0, ph = 0, u = 0;
+      bool next_ready = false;
       for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x, ++tcount) {
         const int acc = n_acc == 2 ? (tcount & 1) : 0;
         mbar_wait_guard(&tempty[acc], (n_acc == 2 ? ((tcount >> 1) & 1) : (tcount & 1)) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        for (int q = 0; q < spt; ++q) {
+        for (int q = 0; q < spt; ++q, ++u) {
           const int nk = min(kps, kgroups - q * kps);
-          mbar_wait_guard(&full[s], ph);    // B landed
-          mbar_wait_guard(&conv[s], ph);    // A is in tensor memory as (hi, lo)
+          TRACE(4, u);
+          // conv[s] is raised by the converter warps after THEY saw full[s] (A and B land in one transaction), so
+          // this one wait covers both operands; every mbarrier wait costs this thread ~170 cycles during which
+          // the tensor core idles (its instruction queue holds only ~2 MMAs)
+          if (!next_ready) mbar_wait_guard(&conv[s], ph);    // A is in tensor memory as (hi, lo), B in shared memory
+          TRACE(6, u);
           tc_fence_after();
           uint32_t db = dB0 + s * (stage_bytes >> 4);
           uint32_t ta = tmem_base + a_col0 + (uint32_t)(s * kps) * 16;
-          for (int j = 0; j < nk; ++j) {
-            umma_tf32_ts(d_tmem, ta + 8, db, desc_hi, idesc, (q | j) ? 1u : 0u);   // lo.hi: small terms first
-            umma_tf32_ts(d_tmem, ta, db + (bytesB >> 5), desc_hi, idesc, 1u);      // hi.lo
-            umma_tf32_ts(d_tmem, ta, db, desc_hi, idesc, 1u);                      // hi.hi
-            ta += 16;
-            db += bytesB >> 4;
+          if (elect_one()) {
+            for (int j = 0; j < nk; ++j) {
+              umma_tf32_ts(d_tmem, ta + 8, db, desc_hi, idesc, (q | j) ? 1u : 0u);   // lo.hi: small terms first
+              umma_tf32_ts(d_tmem, ta, db + (bytesB >> 5), desc_hi, idesc, 1u);      // hi.lo
+              umma_tf32_ts(d_tmem, ta, db, desc_hi, idesc, 1u);                      // hi.hi
+              ta += 16;
+              db += bytesB >> 4;
+            }
+            tc_commit(&empty[s]);          // frees the stage (B in shared memory, A in tensor memory)
+            if (q == spt - 1) tc_commit(&tfull[acc]);          // accumulator complete
           }
-          tc_commit(&empty[s]);          // frees the stage (B in shared memory, A in tensor memory)
+          __syncwarp();
+          {   // with MMAs queued, look whether the next stage is converted already (usually it is)
+            const int sn = s + 1 == nstages ? 0 : s + 1;
+            next_ready = mbar_probe(&conv[sn], s + 1 == nstages ? ph ^ 1 : ph);
+          }
+          TRACE(7, u);
           if (++s == nstages) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tfull[acc]);          // accumulator complete
       }
     }
   } else if (warp >= 6 && warp < 10) {   // ---------------- converters: raw A rows -> tensor memory (hi, lo)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;     // row of the 128-timestep tile
-    int s = 0, ph = 0;
+    int s = 0, ph = 0, u = 0;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-      for (int q = 0; q < spt; ++q) {
+      for (int q = 0; q < spt; ++q, ++u) {
         const int nk = min(kps, kgroups - q * kps);
         mbar_wait_guard(&full[s], ph);
+        if (warp == 6 && lane == 0) TRACE(2, u);
         const unsigned char* st = stages + (size_t)s * stage_bytes;
         uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0 + (uint32_t)(s * kps) * 16;
         for (int j = 0; j < nk; ++j) {
@@ -255,6 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
+        if (warp == 6 && lane == 0) TRACE(3, u);
         if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
