@@ -350,24 +350,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
                                                                    float* __restrict__ part1, int ftiles,
                                                                    int xg_ftiles, int nu, int d0, int n1p,
                                                                    int slab_tiles, int n_tiles, int n_slabs,
-                                                                   int acc_cols, int tmem_cols, int nstages, int kps) {
+                                                                   int acc_stride, int tmem_cols, int nss, int nts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tfull = empty + TC_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* conv = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv + TC_STAGES);
+  // two rings: nss shared-memory stages (raw A blocks + B) cover the HBM latency; nts tensor-memory slots hold
+  // the converted A operand (hi, lo) of the stages the MMA thread is working on - tensor memory is mostly taken
+  // by the ftiles accumulators, and a slot only has to live from conversion to the end of its MMAs
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);   // [TC_STAGES] stage landed
+  uint64_t* sempty = full + TC_STAGES;                      // [TC_STAGES] stage consumed by its MMAs
+  uint64_t* conv = sempty + TC_STAGES;                      // [TC_STAGES] A slot converted
+  uint64_t* aempty = conv + TC_STAGES;                      // [TC_STAGES] A slot consumed by its MMAs
+  uint64_t* tfull = aempty + TC_STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
   unsigned char* stages = smem_raw + 512;
-  // a stage holds kps timestep groups (8 timesteps each):
-  // [A hi: kps x ftiles x 4 KB][A lo: same][B: kps x (hi | lo)]; HBM order of XG / DG = stage order
+  // a stage = one group of 8 timesteps: [A raw fp32: ftiles x 4 KB][B = delta_1 (hi | lo)]; HBM order = stage order
   const uint32_t blkA = TC_M * 8 * 4, bytesB = 2 * nu * 8 * 4;
-  const uint32_t offLo = kps * ftiles * blkA, offB = 2 * offLo;
-  const uint32_t stage_bytes = offB + kps * bytesB;
+  const uint32_t offB = ftiles * blkA;
+  const uint32_t stage_bytes = offB + bytesB;
+  const uint32_t a_col0 = ftiles * acc_stride;              // TMEM: accumulators, then the A ring [slot][ftile][hi 8 | lo 8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 1); }
+    for (int s = 0; s < nss; ++s) { mbar_init(&full[s], 1); mbar_init(&sempty[s], 1); }
+    for (int s = 0; s < nts; ++s) { mbar_init(&conv[s], 4); mbar_init(&aempty[s], 1); }
     mbar_init(&tfull[0], 1);
     mbar_init(&tempty[0], 4);
     fence_barrier_init();
@@ -383,71 +388,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {   // producer: the raw feature-tile blocks of the stage's timestep groups (contiguous), then DG
+    if (lane == 0) {   // producer: the raw feature-tile blocks of the timestep group (contiguous), then DG
       int s = 0, ph = 0;
       for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
         const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
-        for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {   // t1 * 8 - t0 * 8 is a multiple of 8 >= kps
-          mbar_wait_guard(&empty[s], ph ^ 1);
+        for (int tg = t0 * 8; tg < t1 * 8; ++tg) {
+          mbar_wait_guard(&sempty[s], ph ^ 1);
           unsigned char* st = stages + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], offLo + kps * bytesB);
-          bulk_g2s(st, XG + (size_t)tg * xg_ftiles * (TC_M * 8), offLo, &full[s]);
-          bulk_g2s(st + offB, DG + (size_t)tg * (2 * nu * 8), kps * bytesB, &full[s]);
-          if (++s == nstages) { s = 0; ph ^= 1; }
+          mbar_expect_tx(&full[s], offB + bytesB);
+          bulk_g2s(st, XG + (size_t)tg * xg_ftiles * (TC_M * 8), offB, &full[s]);
+          bulk_g2s(st + offB, DG + (size_t)tg * (2 * nu * 8), bytesB, &full[s]);
+          if (++s == nss) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {   // MMA issuer
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
-      const uint32_t lboA = TC_M * 4 * 4, lboB = nu * 4 * 4;
-      const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
-      const uint32_t dA0 = umma_desc_lo(smem_u32(stages), lboA), dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
-      int s = 0, ph = 0;
-      uint32_t scount = 0;
-      for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
-        const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
-        mbar_wait_guard(&tempty[0], (scount & 1) ^ 1);
+  } else if (warp == 1) {   // MMA issuer: the whole warp walks the loop, one elected lane issues
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
+    const uint32_t lboB = nu * 4 * 4;
+    const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+    const uint32_t dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
+    int s = 0, a = 0, aph = 0;
+    uint32_t scount = 0;
+    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
+      const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
+      mbar_wait_guard(&tempty[0], (scount & 1) ^ 1);
+      tc_fence_after();
+      for (int tg = t0 * 8; tg < t1 * 8; ++tg) {
+        mbar_wait_guard(&conv[a], aph);   // raised after the converters saw full[s]: covers A (tensor memory) and B
         tc_fence_after();
-        for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {
-          mbar_wait_guard(&full[s], ph);
-          mbar_wait_guard(&conv[s], ph);
-          tc_fence_after();
-          uint32_t da = dA0 + s * (stage_bytes >> 4), db = dB0 + s * (stage_bytes >> 4);
-          for (int j = 0; j < kps; ++j) {
-            const uint32_t accf = (tg + j) > t0 * 8 ? 1u : 0u;
-            uint32_t d_tmem = tmem_base;
-            for (int ft = 0; ft < ftiles; ++ft) {
-              umma_tf32_lo(d_tmem, da + (offLo >> 4), db, desc_hi, idesc, accf);
-              umma_tf32_lo(d_tmem, da, db + (bytesB >> 5), desc_hi, idesc, 1u);
-              umma_tf32_lo(d_tmem, da, db, desc_hi, idesc, 1u);
-              da += blkA >> 4;
-              d_tmem += acc_cols;
-            }
-            db += bytesB >> 4;
+        if (elect_one()) {
+          const uint32_t db = dB0 + s * (stage_bytes >> 4);
+          uint32_t ta = tmem_base + a_col0 + (uint32_t)(a * ftiles) * 16;
+          uint32_t d_tmem = tmem_base;
+          const uint32_t accf = tg > t0 * 8 ? 1u : 0u;
+          for (int ft = 0; ft < ftiles; ++ft) {
+            umma_tf32_ts(d_tmem, ta + 8, db, desc_hi, idesc, accf);             // lo.hi
+            umma_tf32_ts(d_tmem, ta, db + (bytesB >> 5), desc_hi, idesc, 1u);  // hi.lo
+            umma_tf32_ts(d_tmem, ta, db, desc_hi, idesc, 1u);                  // hi.hi
+            ta += 16;
+            d_tmem += acc_stride;
           }
-          tc_commit(&empty[s]);
-          if (++s == nstages) { s = 0; ph ^= 1; }
+          tc_commit(&sempty[s]);
+          tc_commit(&aempty[a]);
+          if (tg + 1 == t1 * 8) tc_commit(&tfull[0]);
         }
-        tc_commit(&tfull[0]);
+        __syncwarp();
+        if (++s == nss) s = 0;
+        if (++a == nts) { a = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 6) {   // converters
-    int s = 0, ph = 0;
+  } else if (warp >= 6 && warp < 10) {   // converters: raw A rows -> tensor memory (hi, lo)
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    int s = 0, ph = 0, a = 0, aph = 0;
     for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
       const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
-      for (int tg = t0 * 8; tg < t1 * 8; tg += kps) {
-        if (s % TC_CONV == warp - 6) {
-          if (lane == 0) mbar_wait_guard(&full[s], ph);
-          __syncwarp();
-          convert_stage(stages + (size_t)s * stage_bytes, kps * ftiles, offLo, lane);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&conv[s]);
+      for (int tg = t0 * 8; tg < t1 * 8; ++tg) {
+        mbar_wait_guard(&full[s], ph);
+        mbar_wait_guard(&aempty[a], aph ^ 1);
+        tc_fence_after();
+        const unsigned char* st = stages + (size_t)s * stage_bytes;
+        uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_col0 + (uint32_t)(a * ftiles) * 16;
+        for (int ft = 0; ft < ftiles; ++ft) {
+          const float4 x0 = *reinterpret_cast<const float4*>(st + (size_t)ft * blkA + (size_t)m * 16);          // timesteps 0..3
+          const float4 x1 = *reinterpret_cast<const float4*>(st + (size_t)ft * blkA + 2048 + (size_t)m * 16);   // timesteps 4..7
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            hi[k] = (__float_as_uint(x[k]) + 0x1000u) & 0xffffe000u;
+            lo[k] = __float_as_uint(x[k] - __uint_as_float(hi[k])) + 0x1000u;   // the tensor core truncates: pre-round
+          }
+          tmem_st8(ta, hi);
+          tmem_st8(ta + 8, lo);
+          ta += 16;
         }
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[a]);
+        if (++s == nss) { s = 0; ph ^= 1; }
+        if (++a == nts) { a = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 2) {   // epilogue warps 2..5
+  } else if (warp >= 2 && warp < 6) {   // epilogue warps 2..5
     const int q = warp & 3;
     uint32_t scount = 0;
     for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++scount) {
@@ -456,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
       for (int ft = 0; ft < ftiles; ++ft) {
         const int f = ft * TC_M + q * 32 + lane;
         float* dst = part1 + ((size_t)slab * d0 + f) * n1p;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ft * acc_cols;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ft * acc_stride;
         for (int c0 = 0; c0 < nu; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -590,27 +614,29 @@ cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, 
   return cudaGetLastError();
 }
 
+// tensor-memory plan of the gradient kernel: ftiles accumulators of nu columns, then the A ring
+static bool l1g_plan(const NetGeom& g, int* acc_stride, int* nts, int* nss, int* tmem_cols, size_t* smem) {
+  const int nu = l1tc_nu(g);
+  const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
+  *acc_stride = nu;                                   // nu is a multiple of 16
+  *nts = (512 - ftiles * nu) / (ftiles * 16);
+  if (*nts > TC_STAGES) *nts = TC_STAGES;
+  const size_t stage_bytes = (size_t)ftiles * TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4;
+  *nss = (int)((227 * 1024 - 512) / stage_bytes);
+  if (*nss > TC_STAGES) *nss = TC_STAGES;
+  *tmem_cols = 32;
+  while (*tmem_cols < ftiles * nu + *nts * ftiles * 16) *tmem_cols *= 2;
+  *smem = 512 + (size_t)*nss * stage_bytes;
+  return nu <= 256 && *nts >= 2 && *nss >= 2 && *tmem_cols <= 512;
+}
+
 cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,
                               int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st) {
   const int nu = l1tc_nu(g);
   const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
-  const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
-  int tmem_cols = 32;
-  while (tmem_cols < ftiles * acc_cols) tmem_cols *= 2;
-  if (tmem_cols > 512) return cudaErrorInvalidConfiguration;
-  // timestep groups per stage: 1 (a stage already carries ftiles x 3 MMAs; 2 measured no faster).  More than one
-  // would need the batch's XG feature tiles to be exactly the net's (contiguous copy) and divide 8.
-  int kps = 1;
-  size_t stage_bytes = 0;
-  int nstages = 0;
-  for (; kps >= 1; kps >>= 1) {
-    stage_bytes = (size_t)kps * ((size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4);
-    nstages = (int)((227 * 1024 - 512) / stage_bytes);
-    if (nstages >= 3 || kps == 1) break;
-  }
-  if (nstages > TC_STAGES) nstages = TC_STAGES;
-  if (nstages < 2) return cudaErrorInvalidConfiguration;
-  const size_t smem = 512 + (size_t)nstages * stage_bytes;
+  int acc_stride, nts, nss, tmem_cols;
+  size_t smem;
+  if (!l1g_plan(g, &acc_stride, &nts, &nss, &tmem_cols, &smem)) return cudaErrorInvalidConfiguration;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(l1_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -622,16 +648,13 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_slabs < sms ? n_slabs : sms;
   l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
-                                                    n_tiles, n_slabs, acc_cols, tmem_cols, nstages, kps);
+                                                    n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts);
   return cudaGetLastError();
 }
 
 // nets the tensor-core layer-1 path can hold: TMEM (512 columns) and shared memory (>= 2 stages)
 bool l1tc_supported(const NetGeom& g) {
-  const int nu = l1tc_nu(g);
-  const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
-  const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
-  if (nu > 256 || ftiles * acc_cols > 512) return false;
-  const size_t stage_bytes = (size_t)ftiles * 2 * TC_M * 8 * 4 + 2 * nu * 8 * 4;
-  return 2 * stage_bytes + 512 <= 227 * 1024;
+  int acc_stride, nts, nss, tmem_cols;
+  size_t smem;
+  return l1g_plan(g, &acc_stride, &nts, &nss, &tmem_cols, &smem);
 }
