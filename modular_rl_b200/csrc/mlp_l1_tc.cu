@@ -10,14 +10,21 @@
 // Operands are pre-arranged in HBM in the UMMA canonical K-major / no-swizzle core-matrix order
 // (8 rows x 16 bytes per core matrix, SBO = 128 B between row groups, LBO between the two K halves),
 // so a pipeline stage is filled by 1-D bulk async copies (UBLKCP) with no tensor map.  The observations
-// - the only operand that does not fit in L2 - are kept in HBM ONCE, as plain fp32 in that order; six
-// converter warps (one per pipeline stage) split each landed block into (hi, lo) in shared memory (hi in place), so the kernels
-// stream 4 bytes per observation element instead of 8: both are HBM-bound, this halves their traffic.
-//   A stage: [khalf 2][mgroup 16][8][4] floats raw (4 KB) -> hi in place, lo in the 4 KB behind it
-//   B stage: [hi | lo] x [khalf 2][ngroup NU/8][8][4] floats (weights / delta_1: small, pre-split)
-// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter -> HBM), warps 6..11 = converters.
-// Two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Persistent grid.
+// - the only operand that does not fit in L2 - are kept in HBM ONCE, as plain fp32 in that order.
+//
+// A (the observations) is fed to the tensor core from TENSOR MEMORY (TS-mode tcgen05.mma): four converter
+// warps read each landed raw block from shared memory, split it into (hi, lo) in registers and write both with
+// tcgen05.st into a ring of TMEM slots; B (weights / delta_1: small, pre-split hi | lo) stays in shared memory.
+// With both operands in shared memory (round 1b/1c-early) the three MMAs of a k-group read 22.5 KB of it and the
+// copies + converter another 23 KB: shared-memory bandwidth (128 B/cycle), not the tensor pipe, set the pace.
+//   stage (forward):  [A raw fp32: 3 k-groups x 4 KB][B: 3 x (hi | lo) x [khalf 2][ngroup NU/8][8][4]]
+//   stage (gradient): [A raw fp32: ftiles x 4 KB][B = delta_1 of 8 timesteps (hi | lo)]
+// Warp roles (384 threads): warp 0 = bulk-copy producer (one thread), warp 1 = TMEM allocator + MMA issuer (the
+// whole warp walks the loop, one elected lane issues: inside an `if (lane == 0)` region ptxas wraps every
+// tcgen05.mma in an ELECT / BRA.U.ANY loop), warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter ->
+// HBM), warps 6..9 = converters (one TMEM lane quarter each), warps 10..11 idle.  The forward kernel double-
+// buffers its accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent grid.
+// The pipeline was tuned with a clock64 trace of every hand-over (-DMRL_TRACE, tools/micro/l1_trace.py).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -418,16 +425,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t db = dB0 + s * (stage_bytes >> 4);
-          uint32_t ta = tmem_base + a_col0 + (uint32_t)(a * ftiles) * 16;
-          uint32_t d_tmem = tmem_base;
+          const uint32_t ta = tmem_base + a_col0 + (uint32_t)(a * ftiles) * 16;
+          const uint32_t d_tmem = tmem_base;
           const uint32_t accf = tg > t0 * 8 ? 1u : 0u;
-          for (int ft = 0; ft < ftiles; ++ft) {
-            umma_tf32_ts(d_tmem, ta + 8, db, desc_hi, idesc, accf);             // lo.hi
-            umma_tf32_ts(d_tmem, ta, db + (bytesB >> 5), desc_hi, idesc, 1u);  // hi.lo
-            umma_tf32_ts(d_tmem, ta, db, desc_hi, idesc, 1u);                  // hi.hi
-            ta += 16;
-            d_tmem += acc_stride;
-          }
+          // pass by pass over the feature tiles: consecutive MMAs then accumulate into DIFFERENT accumulators
+          for (int ft = 0; ft < ftiles; ++ft) umma_tf32_ts(d_tmem + ft * acc_stride, ta + ft * 16 + 8, db, desc_hi, idesc, accf);   // lo.hi
+          for (int ft = 0; ft < ftiles; ++ft) umma_tf32_ts(d_tmem + ft * acc_stride, ta + ft * 16, db + (bytesB >> 5), desc_hi, idesc, 1u);   // hi.lo
+          for (int ft = 0; ft < ftiles; ++ft) umma_tf32_ts(d_tmem + ft * acc_stride, ta + ft * 16, db, desc_hi, idesc, 1u);   // hi.hi
           tc_commit(&sempty[s]);
           tc_commit(&aempty[a]);
           if (tg + 1 == t1 * 8) tc_commit(&tfull[0]);
@@ -566,7 +570,7 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   // and MMA threads) costs 500-1000 cycles whatever the copy size (tools/micro/bulk_rate*.cu), so a stage
   // carries 3 k-groups.  Stage count: shared memory (227 KB) and the tensor-memory A ring (48 columns per stage
   // behind the accumulators, 512 columns in all).
-  const int kps = 3;
+  const int kps = 3;   // measured at 1M x 376 -> 100: 2 -> 0.47 ms, 3 -> 0.43, 4 -> 0.42, 5 -> 0.44
   const size_t stage_bytes = (size_t)kps * (TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
   int nstages = (int)((227 * 1024 - 512) / stage_bytes);
   const int tmem_room = (512 - n_acc * acc_cols) / (kps * 16);

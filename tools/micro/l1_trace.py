@@ -17,17 +17,17 @@ for _ in range(3):
 lib = C.CDLL(L.LIB_PATH)
 out = np.zeros((8, 512), np.int64)
 assert lib.mrl_debug_l1_trace(out.ctypes.data_as(C.c_void_p)) == 0
-names = ["P:empty ok", "P:issued", "C:full ok", "C:conv done", "M:start", "M:full ok", "M:conv ok", "M:committed"]
+names = ["P:empty ok", "P:issued", "C:full ok", "C:conv done", "M:start", "-", "M:conv ok", "M:committed"]
 t0 = out[1, 0]
-print("use " + " ".join("%12s" % n for n in names))
-for u in range(32, 64):
-    print("%3d " % u + " ".join("%12d" % (out[e, u] - t0) for e in range(8)))
-print("fence.proxy.async cycles (warp 6):", (out[5, 32:96] - out[4, 32:96]).mean(), " convert body:", (out[4, 32:96] - out[2, 32:96]).mean())
-d = np.diff(out[7, 32:96])
-print("mean cycles per stage (MMA commit to commit):", d.mean())
-print("P issued -> C full ok (copy latency):", (out[2, 32:96] - out[1, 32:96]).mean())
-print("C full ok -> conv done (convert):", (out[3, 32:96] - out[2, 32:96]).mean())
-print("C conv done -> M conv ok:", (out[6, 32:96] - out[3, 32:96]).mean())
-print("M conv ok -> committed (issue):", (out[7, 32:96] - out[6, 32:96]).mean())
-print("M committed(u) -> P empty ok(u + nstages=5):", (out[0, 37:101] - out[7, 32:96]).mean())
-print("P empty ok -> issued:", (out[1, 32:96] - out[0, 32:96]).mean())
+print("use " + " ".join("%12s" % n for n in names if n != "-"))
+for u in range(40, 64):
+    print("%3d " % u + " ".join("%12d" % (out[e, u] - t0) for e in range(8) if e != 5))
+R = slice(32, 96)
+print("mean cycles per stage (MMA commit to commit):", np.diff(out[7, R]).mean())
+print("P issued -> C full ok (copy latency):", (out[2, R] - out[1, R]).mean())
+print("C full ok -> conv done (convert into tensor memory):", (out[3, R] - out[2, R]).mean())
+print("C conv done -> M conv ok:", (out[6, R] - out[3, R]).mean())
+print("M start -> conv ok (wait):", (out[6, R] - out[4, R]).mean())
+print("M conv ok -> committed (issue of the stage's MMAs):", (out[7, R] - out[6, R]).mean())
+print("M committed(u) -> P empty ok(u + 5 stages):", (out[0, 37:101] - out[7, R]).mean())
+print("P empty ok -> issued:", (out[1, R] - out[0, R]).mean())
