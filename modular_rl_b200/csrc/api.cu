@@ -672,16 +672,18 @@ static Plan plan_for(const mrl_batch* b) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device) != cudaSuccess || sms <= 0) sms = 148;
   }
   Plan p;
-  if (b->n_tiles <= sms * MRL_MAX_SLAB_TILES) {
-    p.slab_tiles = (b->n_tiles + sms - 1) / sms;
-    p.slab_tiles += p.slab_tiles & 1;   // even: the chain kernel walks pairs of tiles that must not straddle slabs
+  // The backward chain kernel walks 3 tiles per pass (the forward one 2) and clips the last pass of a slab, so
+  // any slab size is legal; the cost of a plan is (waves of slabs) x (passes per slab).
+  if (b->n_tiles <= sms * 3) {
+    p.slab_tiles = 3;
   } else {
     long long best = -1;
-    p.slab_tiles = MRL_MAX_SLAB_TILES;
-    for (int s = MRL_MAX_SLAB_TILES; s >= 8; s -= 2) {
+    p.slab_tiles = 15;
+    const int smin = b->n_tiles <= sms * MRL_MAX_SLAB_TILES ? 3 : 8;
+    for (int s = MRL_MAX_SLAB_TILES; s >= smin; --s) {
       const long long slabs = (b->n_tiles + s - 1) / s;
-      const long long rounds = (slabs + sms - 1) / sms * s;
-      if (best < 0 || rounds < best) { best = rounds; p.slab_tiles = s; }
+      const long long cost = (slabs + sms - 1) / sms * ((s + 2) / 3);
+      if (best < 0 || cost < best) { best = cost; p.slab_tiles = s; }
     }
   }
   if (p.slab_tiles < 1) p.slab_tiles = 1;

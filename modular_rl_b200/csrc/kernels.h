@@ -59,11 +59,12 @@ cudaError_t launch_mid_forward(const NetGeom& g, const MidFwdArgs& a, int n_slab
 cudaError_t launch_mid_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st);
 
 // ---- mlp_chain.cu  (register-resident per-warp chain for the Fisher-vector product)
-#define CH_WARPS 8
+#define CH_WARPS 12          // backward chain: 12 warps x 16 timesteps = 3 cache tiles per pass
 #define CH_NE 3             // weight-gradient entries per warp
 #define CH_NTJ 4            // n-tiles (8 columns each) per entry
 struct ChainEntry {
   int on;      // 1: active
+  int gsoff;   // offset (floats) of the entry's accumulator blocks in shared memory: [n-tile][lane][4]
   int arow0;   // cache feature row of the m-tile's first input feature (off_act[l-1] + 16 mt)
   int amax;    // valid input features from there (d[l-1] - 16 mt; may exceed 16)
   int erow0;   // shared-memory delta row of the first n-tile

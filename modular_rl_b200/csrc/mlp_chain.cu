@@ -22,9 +22,13 @@
 #include "mma_tf32.cuh"
 #include <string.h>
 
-#define CH_THREADS 256
-#define CH_T 128            // timesteps per chain tile (2 cache tiles)
-#define CH_LDE 136          // timesteps between consecutive delta rows in shared memory (x2 floats: hi, lo)
+#define CH_THREADS (32 * CH_WARPS)   // backward chain kernel: 384 threads, <= 168 registers
+#define CH_TILES (CH_WARPS / 4)     // cache tiles (64 timesteps) per chain tile
+#define CH_T (16 * CH_WARPS)        // timesteps per chain tile
+#define CH_LDE (CH_T + 8)           // floats between consecutive delta rows in shared memory (= 8 mod 32: the
+                                    // 64-bit fragment reads of the grad phase are bank-conflict free)
+#define FW_WARPS 8                  // forward chain kernel: 256 threads, 2 CTAs per SM
+#define FW_THREADS (32 * FW_WARPS)
 
 template <int L_, int N1_, int N2_, int N3_, int N4_>
 struct ChainShape {
@@ -49,9 +53,15 @@ struct ChainShape {
     return s;
   }
   __host__ __device__ static constexpr int vbfloats() { return vboff(L_ + 1); }
+  // weight-gradient accumulator blocks (m16 x n8, one float4 per lane) of all layers >= 2, upper bound
+  __host__ __device__ static constexpr int gblocks() {
+    int s = 0;
+    for (int k = 2; k <= L_; ++k) s += ((8 * nt(k - 1) + 15) / 16) * nt(k);
+    return s;
+  }
   __host__ __device__ static constexpr size_t smem_floats(bool fvp) {
     return (size_t)(fvp ? 2 : 1) * wfloats() + (fvp ? vbfloats() : 0) + 16 * nt(L_) + CH_WARPS * 8 * (N1_ + nt(L_)) +
-           (size_t)erows() * CH_LDE * 2;
+           (size_t)gblocks() * 128 + (size_t)erows() * CH_LDE;
   }
 };
 
@@ -118,20 +128,24 @@ __device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
     for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
 }
 
-// delta rows of one layer -> shared memory, (hi, lo) pairs: E[row = feature][timestep][2]
+// delta rows of one layer -> shared memory: E[row = feature][timestep] fp32 (accumulator-order values)
 template <int NT>
-__device__ __forceinline__ void store_E(float* __restrict__ Erow, const uint32_t (&hi)[NT][4],
-                                        const uint32_t (&lo)[NT][4], int warp, int lane) {
+__device__ __forceinline__ void store_E(float* __restrict__ Erow, const float (&d)[NT][4], int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  float2* base = reinterpret_cast<float2*>(Erow) + (2 * t) * CH_LDE + 16 * warp + g;
+  float* base = Erow + (2 * t) * CH_LDE + 16 * warp + g;
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
-    float2* p = base + n * 8 * CH_LDE;
-    p[0] = make_float2(__uint_as_float(hi[n][0]), __uint_as_float(lo[n][0]));            // (f0, row g)
-    p[8] = make_float2(__uint_as_float(hi[n][1]), __uint_as_float(lo[n][1]));            // (f0, row g+8)
-    p[CH_LDE] = make_float2(__uint_as_float(hi[n][2]), __uint_as_float(lo[n][2]));       // (f0+1, row g)
-    p[CH_LDE + 8] = make_float2(__uint_as_float(hi[n][3]), __uint_as_float(lo[n][3]));   // (f0+1, row g+8)
+    float* p = base + n * 8 * CH_LDE;
+    p[0] = d[n][0];              // (f0, row g)
+    p[CH_LDE] = d[n][1];         // (f0+1, row g)
+    p[8] = d[n][2];              // (f0, row g+8)
+    p[CH_LDE + 8] = d[n][3];     // (f0+1, row g+8)
   }
+}
+template <int NT>
+__device__ __forceinline__ void to_frags(const float (&d)[NT][4], uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4]) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) to_frag(d[n], hi[n], lo[n]);
 }
 
 // Rh = act'(h) * (acc + vb) for a hidden layer -> fragments of the next GEMM
@@ -151,25 +165,20 @@ __device__ __forceinline__ void epi_rhidden(const float (&acc)[NT][4], const flo
     to_frag(v, hi[n], lo[n]);
   }
 }
-// delta_{l-1} = acc * act'(h_{l-1}) -> fragments
+// delta_{l-1} = acc * act'(h_{l-1})
 template <int ACT, int NT>
-__device__ __forceinline__ void epi_delta(const float (&acc)[NT][4], const float (&h)[NT][4], uint32_t (&hi)[NT][4],
-                                          uint32_t (&lo)[NT][4]) {
+__device__ __forceinline__ void epi_delta(const float (&acc)[NT][4], const float (&h)[NT][4], float (&d)[NT][4]) {
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    float v[4];
+  for (int n = 0; n < NT; ++n)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = acc[n][i] * dact_from_h<ACT>(h[n][i]);
-    to_frag(v, hi[n], lo[n]);
-  }
+    for (int i = 0; i < 4; ++i) d[n][i] = acc[n][i] * dact_from_h<ACT>(h[n][i]);
 }
 
 // Fisher metric at the head: delta_L from Rz_L = acc + vb_L; rows >= N contribute nothing.
 template <int NT>
 __device__ __forceinline__ void head_metric(const float (&acc)[NT][4], const float* __restrict__ vbl,
                                             const float* __restrict__ ivar, const float (&p)[NT][4], bool cat,
-                                            bool valid0, bool valid1, uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4],
-                                            int lane) {
+                                            bool valid0, bool valid1, float (&d)[NT][4], int lane) {
   const int t = lane & 3;
   float rz[NT][4];
   float s0 = 0.f, s1 = 0.f;
@@ -200,7 +209,8 @@ __device__ __forceinline__ void head_metric(const float (&acc)[NT][4], const flo
     }
     if (!valid0) { v[0] = 0.f; v[1] = 0.f; }
     if (!valid1) { v[2] = 0.f; v[3] = 0.f; }
-    to_frag(v, hi[n], lo[n]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[n][i] = v[i];
   }
 }
 
@@ -212,10 +222,8 @@ template <int NT>
 __device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], const float* __restrict__ auxb, int dL,
                                           const float* __restrict__ sig, const float* __restrict__ ivar, float cs,
                                           float ck, int reverse_kl, bool valid0, bool valid1, bool ok,
-                                          float (&gls)[NT][2], uint32_t (&hi)[NT][4], uint32_t (&lo)[NT][4],
-                                          int lane) {
+                                          float (&gls)[NT][2], float (&d)[NT][4], int lane) {
   const int t = lane & 3;
-  float d[NT][4];
 #pragma unroll
   for (int n = 0; n < NT; ++n)
 #pragma unroll
@@ -313,8 +321,6 @@ __device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], co
       if (valid1) d[0][2] = 2.f * (ho[0][2] - __ldg(auxb + 8));
     }
   }
-#pragma unroll
-  for (int n = 0; n < NT; ++n) to_frag(d[n], hi[n], lo[n]);
 }
 
 // R-forward of layer 2: A = Rh1 = act'(h1) * (x.V1 + vb1) and A = h1, streamed from HBM per k-step
@@ -447,15 +453,22 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
   }
 }
 
-// G[q] += h_{l-1}^T delta_l over the 128 timesteps of the chain tile for one (m-tile, CNT n-tiles) entry.
+// G[q] += h_{l-1}^T delta_l over the CH_T timesteps of the chain tile for one (m-tile, CNT n-tiles) entry.
 // A = cached activations straight from L2 (k-slot t <-> timestep 2t, slot t+4 <-> 2t+1: one 64-bit load per
-// row), B = (hi, lo) pairs of delta from shared memory (one 128-bit load per n-tile and k-step).
+// row), B = delta rows from shared memory (one 64-bit load per n-tile and k-step, split here).  The accumulator
+// blocks live in shared memory between chain tiles ([n-tile][lane] float4): with 12 warps a thread has 168 registers.
 template <int CNT>
-__device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* __restrict__ A0, size_t tile_stride,
-                                           bool ok0, bool ok1, bool t2ok, const float* __restrict__ Eb) {
+__device__ __forceinline__ void grad_entry(float* __restrict__ Gs, const float* __restrict__ A0, size_t tile_stride,
+                                           bool ok0, bool ok1, int tiles_here, const float* __restrict__ Eb, int lane) {
+  float G[CNT][4];
+#pragma unroll
+  for (int q = 0; q < CNT; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(Gs + (q * 32 + lane) * 4);
+    G[q][0] = v.x; G[q][1] = v.y; G[q][2] = v.z; G[q][3] = v.w;
+  }
   float2 xa[4], xb[4];
-  auto load_group = [&](int kg, float2 (&a)[4], float2 (&b)[4]) {
-    const bool hk = kg < 2 || t2ok;                       // k-steps 8..15 live in the second cache tile
+  auto load_group = [&](int kg, float2 (&a)[4], float2 (&b)[4]) {   // 4 k-steps = 32 timesteps = half a cache tile
+    const bool hk = (kg >> 1) < tiles_here;
     const float* Ap = A0 + (size_t)(kg >> 1) * tile_stride + (kg & 1) * 32;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -465,11 +478,11 @@ __device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* _
   };
   load_group(0, xa, xb);
 #pragma unroll 1
-  for (int kg = 0; kg < 4; ++kg) {
+  for (int kg = 0; kg < 2 * CH_TILES; ++kg) {
     float2 ca[4], cb[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
-    if (kg < 3) load_group(kg + 1, xa, xb);
+    if (kg + 1 < 2 * CH_TILES) load_group(kg + 1, xa, xb);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ks = 4 * kg + j;
@@ -481,9 +494,9 @@ __device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* _
       uint32_t bh[CNT][2], bl[CNT][2];
 #pragma unroll
       for (int q = 0; q < CNT; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(Eb + (size_t)q * 8 * CH_LDE * 2 + ks * 16);
-        bh[q][0] = __float_as_uint(b.x); bl[q][0] = __float_as_uint(b.y);
-        bh[q][1] = __float_as_uint(b.z); bl[q][1] = __float_as_uint(b.w);
+        const float2 b = *reinterpret_cast<const float2*>(Eb + (size_t)q * 8 * CH_LDE + ks * 8);
+        split_tf32(b.x, bh[q][0], bl[q][0]);
+        split_tf32(b.y, bh[q][1], bl[q][1]);
       }
 #pragma unroll
       for (int q = 0; q < CNT; ++q) mma_tf32(G[q], al, bh[q]);
@@ -493,6 +506,9 @@ __device__ __forceinline__ void grad_entry(float (&G)[CH_NTJ][4], const float* _
       for (int q = 0; q < CNT; ++q) mma_tf32(G[q], ah, bh[q]);
     }
   }
+#pragma unroll
+  for (int q = 0; q < CNT; ++q)
+    *reinterpret_cast<float4*>(Gs + (q * 32 + lane) * 4) = make_float4(G[q][0], G[q][1], G[q][2], G[q][3]);
 }
 
 template <class S, int ACT, int MODE>
@@ -509,7 +525,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
   float* sig = ivar + 8 * NL;
   float* gb1s = sig + 8 * NL;                          // [warp][8 N1] layer-1 bias partials
   float* glss = gb1s + CH_WARPS * 8 * N1;              // [warp][8 NL] logstd partials (gradient mode)
-  float* E = glss + CH_WARPS * 8 * NL;
+  float* Gs = glss + CH_WARPS * 8 * NL;                // weight-gradient accumulator blocks of all entries
+  float* E = Gs + S::gblocks() * 128;                  // delta rows [row][CH_LDE]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
   const bool cat = g.head == MRL_HEAD_CAT, gauss = g.head == MRL_HEAD_GAUSS;
@@ -543,9 +560,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
 
   for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {   // persistent: weights stay in shared memory
   const int t0 = slab * a.slab_tiles, t1 = min(t0 + a.slab_tiles, a.n_tiles);
-  float G[CH_NE][CH_NTJ][4];
-#pragma unroll
-  for (int e = 0; e < CH_NE; ++e) zero_acc(G[e]);
+  for (int i = tid; i < S::gblocks() * 128; i += CH_THREADS) Gs[i] = 0.f;
   float gls[NL][2];   // logstd gradient partials of this thread's columns (gradient mode, DiagGauss)
 #pragma unroll
   for (int n = 0; n < NL; ++n) { gls[n][0] = 0.f; gls[n][1] = 0.f; }
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
   float gbe = 0.f;   // lane j: bias-gradient sum of delta row warp + 8 j
   __syncthreads();
 
-  for (int ct0 = t0; ct0 < t1; ct0 += 2) {
+  for (int ct0 = t0; ct0 < t1; ct0 += CH_TILES) {
     // ================= chain phase: this warp's 16 timesteps
     {
       const int ctile = ct0 + (warp >> 2);
@@ -562,18 +577,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
       const long long ts = (long long)ctile * MRL_TILE + rr;
       const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
       const float* cb = a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr;
-      if (ct0 + 2 < t1 && lane == 0) {   // pull the next chain tile into L2 while this one computes (bulk prefetch, 1/8 per warp)
-        const int nt2 = min(2, t1 - ct0 - 2);
+      if (ct0 + CH_TILES < t1 && lane == 0) {   // pull the next chain tile into L2 while this one computes (bulk prefetch, one share per warp)
+        const int nt2 = min(CH_TILES, t1 - ct0 - CH_TILES);
         const unsigned cbytes = (unsigned)(nt2 * g.act_rows * MRL_LDT * 4);
         const unsigned cchunk = (cbytes / CH_WARPS) & ~15u;
-        const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + 2) * g.act_rows * MRL_LDT) + (size_t)warp * cchunk;
+        const char* pc = reinterpret_cast<const char*>(a.cache + (size_t)(ct0 + CH_TILES) * g.act_rows * MRL_LDT) + (size_t)warp * cchunk;
         const unsigned cn = warp == CH_WARPS - 1 ? cbytes - (CH_WARPS - 1) * cchunk : cchunk;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(cn) : "memory");
         const float* side = FVP ? a.Zt : a.aux;                    // Fvp: x.V1 ; gradient: adv / actions / old probs
         const int srows = FVP ? g.d[1] : g.naux;
         const unsigned zbytes = (unsigned)(nt2 * srows * MRL_LDT * 4);
         const unsigned zchunk = (zbytes / CH_WARPS) & ~15u;
-        const char* pz = reinterpret_cast<const char*>(side + (size_t)(ct0 + 2) * srows * MRL_LDT) + (size_t)warp * zchunk;
+        const char* pz = reinterpret_cast<const char*>(side + (size_t)(ct0 + CH_TILES) * srows * MRL_LDT) + (size_t)warp * zchunk;
         const unsigned zn = warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(zn) : "memory");
       }
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
       float ph[NL][4];   // cached head output: probabilities (Fvp, Categorical) / mean | probs | value (gradient)
 #pragma unroll
       for (int n = 0; n < NL; ++n) ldfrag(ph[n], cb + g.off_act[L] * MRL_LDT, 8 * n + 2 * t, g.d[L], ok && (cat || !FVP));
-      uint32_t dLh[NL][4], dLl[NL][4];   // delta_L fragments
+      float dL[NL][4];   // delta_L (accumulator order)
       if constexpr (FVP) {
         // ---- R-forward (Pearlmutter) and the Fisher metric
         const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
@@ -601,23 +616,25 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         zero_acc(acc3);
         rfwd_layer<N2, N3>(acc3, r2h, r2l, h2, Ws + S::woff(3), Vs + S::woff(3), lane);
         if constexpr (L == 3) {
-          head_metric<N3>(acc3, vb + S::vboff(3), ivar, ph, cat, valid0, valid1, dLh, dLl, lane);
+          head_metric<N3>(acc3, vb + S::vboff(3), ivar, ph, cat, valid0, valid1, dL, lane);
         } else {
           uint32_t r3h[N3][4], r3l[N3][4];
           epi_rhidden<ACT, N3>(acc3, h3, vb + S::vboff(3), r3h, r3l, lane);
           float acc4[NL][4];
           zero_acc(acc4);
           rfwd_layer<N3, NL>(acc4, r3h, r3l, h3, Ws + S::woff(4), Vs + S::woff(4), lane);
-          head_metric<NL>(acc4, vb + S::vboff(4), ivar, ph, cat, valid0, valid1, dLh, dLl, lane);
+          head_metric<NL>(acc4, vb + S::vboff(4), ivar, ph, cat, valid0, valid1, dL, lane);
         }
       } else {
         const float* auxb = a.aux + (size_t)ctile * g.naux * MRL_LDT + rr;
-        head_grad<NL>(g.head, ph, auxb, g.d[L], sig, ivar, cs, ck, a.reverse_kl, valid0, valid1, ok, gls, dLh, dLl, lane);
+        head_grad<NL>(g.head, ph, auxb, g.d[L], sig, ivar, cs, ck, a.reverse_kl, valid0, valid1, ok, gls, dL, lane);
       }
       // ---- reverse sweep
-      store_E<NL>(E + (size_t)S::eoff(L) * CH_LDE * 2, dLh, dLl, warp, lane);
+      store_E<NL>(E + (size_t)S::eoff(L) * CH_LDE, dL, warp, lane);
       uint32_t d2h[N2][4], d2l[N2][4];
       {
+        uint32_t dLh[NL][4], dLl[NL][4];
+        to_frags<NL>(dL, dLh, dLl);
         float acc2[N2][4];
         zero_acc(acc2);
         if constexpr (L == 3) {
@@ -626,14 +643,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
           float acc3[N3][4];
           zero_acc(acc3);
           delta_layer<N3, NL>(acc3, dLh, dLl, Ws + S::woff(4), 0, lane);
+          float d3[N3][4];
+          epi_delta<ACT, N3>(acc3, h3, d3);
+          store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE, d3, warp, lane);
           uint32_t d3h[N3][4], d3l[N3][4];
-          epi_delta<ACT, N3>(acc3, h3, d3h, d3l);
-          store_E<N3>(E + (size_t)S::eoff(3) * CH_LDE * 2, d3h, d3l, warp, lane);
+          to_frags<N3>(d3, d3h, d3l);
           delta_layer<N2, N3>(acc2, d3h, d3l, Ws + S::woff(3), 0, lane);
         }
-        epi_delta<ACT, N2>(acc2, h2, d2h, d2l);
+        float d2[N2][4];
+        epi_delta<ACT, N2>(acc2, h2, d2);
+        store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE, d2, warp, lane);
+        to_frags<N2>(d2, d2h, d2l);
       }
-      store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE * 2, d2h, d2l, warp, lane);
       float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
       constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
       delta1_block<ACT, NA, 0, N1, N2>(d2h, d2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
@@ -646,30 +667,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
       }
     }
     __syncthreads();
-    // ================= grad phase: G_l += h_{l-1}^T delta_l over the 128 timesteps of this chain tile
+    // ================= grad phase: G_l += h_{l-1}^T delta_l over the CH_T timesteps of this chain tile
     {
-      const bool t2ok = ct0 + 1 < t1;
+      const int tiles_here = min(CH_TILES, t1 - ct0);
 #pragma unroll
       for (int e = 0; e < CH_NE; ++e) {
         const ChainEntry en = jobs.e[warp][e];
         if (!en.on) continue;
         const bool ok0 = gq < en.amax, ok1 = gq + 8 < en.amax;
         const float* A0 = a.cache + ((size_t)ct0 * g.act_rows + en.arow0 + gq) * MRL_LDT + 2 * t;
-        const float* Eb = E + ((size_t)(en.erow0 + gq) * CH_LDE + 2 * t) * 2;
+        const float* Eb = E + (size_t)(en.erow0 + gq) * CH_LDE + 2 * t;
         const size_t tstride = (size_t)g.act_rows * MRL_LDT;
         switch (en.cnt) {   // warp-uniform
-          case 4: grad_entry<4>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
-          case 3: grad_entry<3>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
-          case 2: grad_entry<2>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
-          default: grad_entry<1>(G[e], A0, tstride, ok0, ok1, t2ok, Eb); break;
+          case 4: grad_entry<4>(Gs + en.gsoff, A0, tstride, ok0, ok1, tiles_here, Eb, lane); break;
+          case 3: grad_entry<3>(Gs + en.gsoff, A0, tstride, ok0, ok1, tiles_here, Eb, lane); break;
+          case 2: grad_entry<2>(Gs + en.gsoff, A0, tstride, ok0, ok1, tiles_here, Eb, lane); break;
+          default: grad_entry<1>(Gs + en.gsoff, A0, tstride, ok0, ok1, tiles_here, Eb, lane); break;
         }
       }
-      // bias gradients of layers >= 2: row sums of delta (what the tensor cores consumed: hi + truncated lo)
-      for (int j = 0; warp + 8 * j < S::erows(); ++j) {
-        const float4* p = reinterpret_cast<const float4*>(E + (size_t)(warp + 8 * j) * CH_LDE * 2);
-        const float4 u = p[lane], v = p[lane + 32];
-        float s = (u.x + __uint_as_float(__float_as_uint(u.y) & 0xffffe000u)) + (u.z + __uint_as_float(__float_as_uint(u.w) & 0xffffe000u)) +
-                  (v.x + __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + (v.z + __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+      // bias gradients of layers >= 2: row sums of delta
+      for (int j = 0; warp + CH_WARPS * j < S::erows(); ++j) {
+        const float2* p = reinterpret_cast<const float2*>(E + (size_t)(warp + CH_WARPS * j) * CH_LDE);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH_T / 64; ++i) { const float2 u = p[lane + 32 * i]; s += u.x + u.y; }
         s = warp_sum(s);
         if (lane == j) gbe += s;
       }
@@ -683,23 +704,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
   for (int e = 0; e < CH_NE; ++e) {
     const ChainEntry en = jobs.e[warp][e];
     if (!en.on) continue;
-#pragma unroll
-    for (int q = 0; q < CH_NTJ; ++q) {
-      if (q >= en.cnt) continue;
+    for (int q = 0; q < en.cnt; ++q) {
+      const float4 G = *reinterpret_cast<const float4*>(Gs + en.gsoff + (q * 32 + lane) * 4);
       const int n = 8 * q + 2 * t;
       float* pr = part + en.poff + n;
       if (gq < en.amax) {
-        if (n < en.nmax) pr[gq * en.ldw] = G[e][q][0];
-        if (n + 1 < en.nmax) pr[gq * en.ldw + 1] = G[e][q][1];
+        if (n < en.nmax) pr[gq * en.ldw] = G.x;
+        if (n + 1 < en.nmax) pr[gq * en.ldw + 1] = G.y;
       }
       if (gq + 8 < en.amax) {
-        if (n < en.nmax) pr[(gq + 8) * en.ldw] = G[e][q][2];
-        if (n + 1 < en.nmax) pr[(gq + 8) * en.ldw + 1] = G[e][q][3];
+        if (n < en.nmax) pr[(gq + 8) * en.ldw] = G.z;
+        if (n + 1 < en.nmax) pr[(gq + 8) * en.ldw + 1] = G.w;
       }
     }
   }
   {
-    const int r = warp + 8 * lane;
+    const int r = warp + CH_WARPS * lane;
     if (r < S::erows()) {
 #pragma unroll
       for (int l = 2; l <= L; ++l)
@@ -764,6 +784,7 @@ static bool build_jobs(const NetGeom& g, ChainJobs* jobs) {
   for (int i = 1; i < nj; ++i)
     for (int k = i; k > 0 && list[k].cnt > list[k - 1].cnt; --k) { Job tmp = list[k]; list[k] = list[k - 1]; list[k - 1] = tmp; }
   int load[CH_WARPS] = {0}, used[CH_WARPS] = {0};
+  int gs = 0;
   memset(jobs, 0, sizeof(*jobs));
   for (int i = 0; i < nj; ++i) {
     int best = -1;
@@ -774,6 +795,8 @@ static bool build_jobs(const NetGeom& g, ChainJobs* jobs) {
     ChainEntry& en = jobs->e[best][used[best]++];
     load[best] += j.cnt;
     en.on = 1;
+    en.gsoff = gs;
+    gs += j.cnt * 128;
     en.arow0 = g.off_act[j.l - 1] + 16 * j.mt;
     en.amax = g.d[j.l - 1] - 16 * j.mt;
     en.erow0 = S::eoff(j.l) + 8 * j.nt0;
@@ -840,7 +863,6 @@ static cudaError_t launch_mode(const NetGeom& g, const MidBwdArgs& a, int n_slab
   }
 }
 cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_slabs, cudaStream_t st) {
-  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;   // chain tiles must not straddle slabs
   return a.mode == MRL_MODE_FVP ? launch_mode<MRL_MODE_FVP>(g, a, n_slabs, st) : launch_mode<MRL_MODE_GRAD>(g, a, n_slabs, st);
 }
 
@@ -990,7 +1012,7 @@ __device__ __forceinline__ void head_forward(int head, float (&o)[NT][4], const 
 }
 
 template <class S, int ACT>
-__global__ void __launch_bounds__(CH_THREADS, 2) chain_fwd_kernel(NetGeom g, MidFwdArgs a, int n_slabs) {
+__global__ void __launch_bounds__(FW_THREADS, 2) chain_fwd_kernel(NetGeom g, MidFwdArgs a, int n_slabs) {
   constexpr int L = S::L;
   constexpr int N1 = S::nt(1), N2 = S::nt(2), N3 = S::nt(3);
   constexpr int NL = S::nt(L);
@@ -1008,7 +1030,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chain_fwd_kernel(NetGeom g, Mid
     const int kin = 8 * S::nt(l - 1), nout = 8 * S::nt(l);
     const float* src = a.img + g.off_W[l];
     float* dw = Ws + S::woff(l);
-    for (int e = tid; e < kin * nout; e += CH_THREADS) {
+    for (int e = tid; e < kin * nout; e += FW_THREADS) {
       const int i = e / nout, j = e - i * nout;
       const bool ok = i < g.d[l - 1] && j < g.d[l];
       dw[((i >> 3) * S::nt(l) + (j >> 3)) * 64 + blk_row(j & 7) * 8 + (i & 7)] = ok ? src[i * g.ldw[l] + j] : 0.f;
@@ -1016,14 +1038,14 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chain_fwd_kernel(NetGeom g, Mid
   }
 #pragma unroll
   for (int l = 1; l <= L; ++l)
-    for (int f = tid; f < 8 * S::nt(l); f += CH_THREADS) bs[S::vboff(l) + f] = f < g.d[l] ? a.img[g.off_b[l] + f] : 0.f;
+    for (int f = tid; f < 8 * S::nt(l); f += FW_THREADS) bs[S::vboff(l) + f] = f < g.d[l] ? a.img[g.off_b[l] + f] : 0.f;
   float ent_row = 0.f;     // DiagGauss entropy is the same for every row: sum log sigma + d/2 log(2 pi e)
   {
     float sls = 0.f;
     for (int j = 0; j < g.d[L] && gauss; ++j) sls += a.img[g.off_pm_logstd + j];
     ent_row = sls + 0.5f * CH_LOG_2PIE * g.d[L];
   }
-  for (int f = tid; f < 8 * NL; f += CH_THREADS) sig[f] = (gauss && f < g.d[L]) ? expf(a.img[g.off_pm_logstd + f]) : 1.f;
+  for (int f = tid; f < 8 * NL; f += FW_THREADS) sig[f] = (gauss && f < g.d[L]) ? expf(a.img[g.off_pm_logstd + f]) : 1.f;
   __syncthreads();
 
   for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
@@ -1040,13 +1062,13 @@ __global__ void __launch_bounds__(CH_THREADS, 2) chain_fwd_kernel(NetGeom g, Mid
       const float* auxb = a.aux ? a.aux + (size_t)ctile * g.naux * MRL_LDT + rr : nullptr;
       if (ct0 + 2 < t1 && lane == 0) {   // next chain tile's layer-1 pre-activations (and side inputs) into L2
         const int nt2 = min(2, t1 - ct0 - 2);
-        const unsigned zbytes = (unsigned)(nt2 * g.d[1] * MRL_LDT * 4), zchunk = (zbytes / CH_WARPS) & ~15u;
+        const unsigned zbytes = (unsigned)(nt2 * g.d[1] * MRL_LDT * 4), zchunk = (zbytes / FW_WARPS) & ~15u;
         const char* pz = reinterpret_cast<const char*>(a.Zt + (size_t)(ct0 + 2) * g.d[1] * MRL_LDT) + (size_t)warp * zchunk;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(warp == CH_WARPS - 1 ? zbytes - (CH_WARPS - 1) * zchunk : zchunk) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(warp == FW_WARPS - 1 ? zbytes - (FW_WARPS - 1) * zchunk : zchunk) : "memory");
         if (a.aux) {
-          const unsigned xbytes = (unsigned)(nt2 * g.naux * MRL_LDT * 4), xchunk = (xbytes / CH_WARPS) & ~15u;
+          const unsigned xbytes = (unsigned)(nt2 * g.naux * MRL_LDT * 4), xchunk = (xbytes / FW_WARPS) & ~15u;
           const char* px = reinterpret_cast<const char*>(a.aux + (size_t)(ct0 + 2) * g.naux * MRL_LDT) + (size_t)warp * xchunk;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(px), "r"(warp == CH_WARPS - 1 ? xbytes - (CH_WARPS - 1) * xchunk : xchunk) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(px), "r"(warp == FW_WARPS - 1 ? xbytes - (FW_WARPS - 1) * xchunk : xchunk) : "memory");
         }
       }
       // ---- layer 1 activation streamed per k-step into the layer-2 GEMM
@@ -1142,7 +1164,7 @@ static cudaError_t launch_fwd_shape(const NetGeom& g, const MidFwdArgs& a, int n
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  chain_fwd_kernel<S, MRL_ACT_TANH><<<n_slabs < 2 * sms ? n_slabs : 2 * sms, CH_THREADS, sm, st>>>(g, a, n_slabs);   // 2 CTAs per SM
+  chain_fwd_kernel<S, MRL_ACT_TANH><<<n_slabs < 2 * sms ? n_slabs : 2 * sms, FW_THREADS, sm, st>>>(g, a, n_slabs);   // 2 CTAs per SM
   return cudaGetLastError();
 }
 int chain_fwd_shape(const NetGeom& g) {
@@ -1152,7 +1174,6 @@ int chain_fwd_shape(const NetGeom& g) {
   return 0;
 }
 cudaError_t launch_chain_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
-  if (n_slabs > 1 && (a.slab_tiles & 1)) return cudaErrorInvalidConfiguration;
   switch (chain_fwd_shape(g)) {
     case 1: return launch_fwd_shape<ShapeA>(g, a, n_slabs, st);
     case 2: return launch_fwd_shape<ShapeB>(g, a, n_slabs, st);
