@@ -69,12 +69,14 @@ struct ChainShape {
 // 4..7 of a half-warp hit rows with distinct (row mod 4)) and for the 32-bit W^T reads (rows 2t / 2t+1).
 __device__ __forceinline__ int blk_row(int j) { return j < 4 ? j : (j ^ 1); }
 
+// A thread's two fragment rows (g and g+8 of the m16 tile) are mapped to ADJACENT timesteps 2g and 2g+1 of the
+// warp's 16, so one 64-bit access moves both rows of a feature (p already points at timestep 2g).
 __device__ __forceinline__ void ldfrag(float (&v)[4], const float* __restrict__ p, int f0, int dmax, bool ok) {
   const bool k0 = ok && f0 < dmax, k1 = ok && f0 + 1 < dmax;
-  v[0] = k0 ? __ldg(p + f0 * MRL_LDT) : 0.f;
-  v[2] = k0 ? __ldg(p + f0 * MRL_LDT + 8) : 0.f;
-  v[1] = k1 ? __ldg(p + (f0 + 1) * MRL_LDT) : 0.f;
-  v[3] = k1 ? __ldg(p + (f0 + 1) * MRL_LDT + 8) : 0.f;
+  const float2 a = k0 ? __ldg(reinterpret_cast<const float2*>(p + f0 * MRL_LDT)) : make_float2(0.f, 0.f);
+  const float2 b = k1 ? __ldg(reinterpret_cast<const float2*>(p + (f0 + 1) * MRL_LDT)) : make_float2(0.f, 0.f);
+  v[0] = a.x; v[2] = a.y;
+  v[1] = b.x; v[3] = b.y;
 }
 // accumulator-order values (c0..c3) -> A-fragment order (a0 = c0, a1 = c2, a2 = c1, a3 = c3), split
 __device__ __forceinline__ void to_frag(const float (&v)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
@@ -128,18 +130,17 @@ __device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
     for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
 }
 
-// delta rows of one layer -> shared memory: E[row = feature][timestep] fp32 (accumulator-order values)
+// delta rows of one layer -> shared memory: E[row = feature][timestep] fp32 (accumulator-order values; the
+// thread's two rows are adjacent timesteps: one 64-bit store per feature)
 template <int NT>
 __device__ __forceinline__ void store_E(float* __restrict__ Erow, const float (&d)[NT][4], int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  float* base = Erow + (2 * t) * CH_LDE + 16 * warp + g;
+  float* base = Erow + (2 * t) * CH_LDE + 16 * warp + 2 * g;
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     float* p = base + n * 8 * CH_LDE;
-    p[0] = d[n][0];              // (f0, row g)
-    p[CH_LDE] = d[n][1];         // (f0+1, row g)
-    p[8] = d[n][2];              // (f0, row g+8)
-    p[CH_LDE + 8] = d[n][3];     // (f0+1, row g+8)
+    *reinterpret_cast<float2*>(p) = make_float2(d[n][0], d[n][2]);            // feature f0
+    *reinterpret_cast<float2*>(p + CH_LDE) = make_float2(d[n][1], d[n][3]);   // feature f0 + 1
   }
 }
 template <int NT>
@@ -229,7 +230,7 @@ __device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], co
 #pragma unroll
     for (int i = 0; i < 4; ++i) d[n][i] = 0.f;
   if (head == MRL_HEAD_GAUSS) {
-    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 8) : 0.f;
+    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 1) : 0.f;
     float ac[NT][4], m0[NT][4], s0[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
@@ -277,8 +278,8 @@ __device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], co
         }
       }
   } else if (head == MRL_HEAD_CAT) {
-    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 8) : 0.f;
-    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 8) : -1;
+    const float adv0 = valid0 ? __ldg(auxb) : 0.f, adv1 = valid1 ? __ldg(auxb + 1) : 0.f;
+    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 1) : -1;
     float p0[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n) ldfrag(p0[n], auxb + 2 * MRL_LDT, 8 * n + 2 * t, dL, ok);
@@ -318,7 +319,7 @@ __device__ __forceinline__ void head_grad(int head, const float (&ho)[NT][4], co
   } else {   // value head: d/dpred of (y - pred)^2
     if (t == 0) {
       if (valid0) d[0][0] = 2.f * (ho[0][0] - __ldg(auxb));
-      if (valid1) d[0][2] = 2.f * (ho[0][2] - __ldg(auxb + 8));
+      if (valid1) d[0][2] = 2.f * (ho[0][2] - __ldg(auxb + 1));
     }
   }
 }
@@ -440,14 +441,16 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
       }
     }
     if (ok && 8 * (nb + n) < nu) {
+      // dg -> the warp's first timestep group.  This thread's timesteps 2g, 2g+1 are adjacent inside a group of 4:
+      // one 64-bit store per feature and precision part.
+      float* p0 = dg + (size_t)(g >> 2) * (2 * nu * 8) + ((g >> 1) & 1) * (nu * 4) + (nb + n) * 32 + (2 * t) * 4 + 2 * (g & 1);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t hi, lo;
-        split_tf32(v[i], hi, lo);
-        // dg -> this warp's first timestep group; row g + 8 (i >> 1) of the warp's 16 timesteps
-        float* p = dg + (size_t)(i >> 1) * (2 * nu * 8) + (g >> 2) * (nu * 4) + (nb + n) * 32 + (2 * t + (i & 1)) * 4 + (g & 3);
-        p[0] = __uint_as_float(hi);
-        p[nu * 8] = __uint_as_float(lo);
+      for (int b = 0; b < 2; ++b) {   // features 2t, 2t+1 of the n-tile
+        uint32_t h0, l0, h1_, l1_;
+        split_tf32(v[b], h0, l0);
+        split_tf32(v[b + 2], h1_, l1_);
+        *reinterpret_cast<float2*>(p0 + b * 4) = make_float2(__uint_as_float(h0), __uint_as_float(h1_));
+        *reinterpret_cast<float2*>(p0 + b * 4 + nu * 8) = make_float2(__uint_as_float(l0), __uint_as_float(l1_));
       }
     }
   }
@@ -573,9 +576,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
     {
       const int ctile = ct0 + (warp >> 2);
       const bool ok = ctile < t1;
-      const int rr = ((warp & 3) << 4) + gq;
+      const int rr = ((warp & 3) << 4) + 2 * gq;   // this thread's rows: timesteps rr and rr + 1 of the cache tile
       const long long ts = (long long)ctile * MRL_TILE + rr;
-      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
+      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 1 < a.N;
       const float* cb = a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr;
       if (ct0 + CH_TILES < t1 && lane == 0) {   // pull the next chain tile into L2 while this one computes (bulk prefetch, one share per warp)
         const int nt2 = min(CH_TILES, t1 - ct0 - CH_TILES);
@@ -873,8 +876,8 @@ cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_s
 #define CH_LOG_2PIE 2.8378770664093453f
 
 __device__ __forceinline__ void st_cfrag(float* __restrict__ p, const float (&v)[4], int f0, int dmax, bool ok) {
-  if (ok && f0 < dmax) { p[f0 * MRL_LDT] = v[0]; p[f0 * MRL_LDT + 8] = v[2]; }
-  if (ok && f0 + 1 < dmax) { p[(f0 + 1) * MRL_LDT] = v[1]; p[(f0 + 1) * MRL_LDT + 8] = v[3]; }
+  if (ok && f0 < dmax) *reinterpret_cast<float2*>(p + f0 * MRL_LDT) = make_float2(v[0], v[2]);
+  if (ok && f0 + 1 < dmax) *reinterpret_cast<float2*>(p + (f0 + 1) * MRL_LDT) = make_float2(v[1], v[3]);
 }
 // hidden-layer epilogue: h = act(acc + b) -> cache, fragments of the next GEMM
 template <int ACT, int NT>
@@ -943,7 +946,7 @@ __device__ __forceinline__ void head_forward(int head, float (&o)[NT][4], const 
     }
     if (t == 0) {
       if (valid0) { s_surr += (double)(expf(dl0) * __ldg(auxb)); s_kl += (double)kl0; s_ent += (double)ent_row; }
-      if (valid1) { s_surr += (double)(expf(dl1) * __ldg(auxb + 8)); s_kl += (double)kl1; s_ent += (double)ent_row; }
+      if (valid1) { s_surr += (double)(expf(dl1) * __ldg(auxb + 1)); s_kl += (double)kl1; s_ent += (double)ent_row; }
     }
   } else if (head == MRL_HEAD_CAT) {
     float m0_ = -INFINITY, m1_ = -INFINITY;
@@ -972,7 +975,7 @@ __device__ __forceinline__ void head_forward(int head, float (&o)[NT][4], const 
 #pragma unroll
     for (int n = 0; n < NT; ++n) { o[n][0] *= i0; o[n][1] *= i0; o[n][2] *= i1; o[n][3] *= i1; }
     if (auxb == nullptr) return;
-    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 8) : -1;
+    const int ai0 = ok ? (int)__ldg(auxb + MRL_LDT) : -1, ai1 = ok ? (int)__ldg(auxb + MRL_LDT + 1) : -1;
     float pa0 = 0.f, pa1 = 0.f, qa0 = 0.f, qa1 = 0.f, kl0 = 0.f, kl1 = 0.f, en0 = 0.f, en1 = 0.f;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
@@ -1001,12 +1004,12 @@ __device__ __forceinline__ void head_forward(int head, float (&o)[NT][4], const 
     }
     if (t == 0) {
       if (valid0) { s_surr += (double)((pa0 / qa0) * __ldg(auxb)); s_kl += (double)kl0; s_ent += (double)en0; }
-      if (valid1) { s_surr += (double)((pa1 / qa1) * __ldg(auxb + 8)); s_kl += (double)kl1; s_ent += (double)en1; }
+      if (valid1) { s_surr += (double)((pa1 / qa1) * __ldg(auxb + 1)); s_kl += (double)kl1; s_ent += (double)en1; }
     }
   } else {   // value head: squared error against the target row
     if (auxb != nullptr && t == 0) {
       if (valid0) { const float df = __ldg(auxb) - o[0][0]; s_surr += (double)df * (double)df; }
-      if (valid1) { const float df = __ldg(auxb + 8) - o[0][2]; s_surr += (double)df * (double)df; }
+      if (valid1) { const float df = __ldg(auxb + 1) - o[0][2]; s_surr += (double)df * (double)df; }
     }
   }
 }
@@ -1054,9 +1057,9 @@ __global__ void __launch_bounds__(FW_THREADS, 2) chain_fwd_kernel(NetGeom g, Mid
     for (int ct0 = t0; ct0 < t1; ct0 += 2) {
       const int ctile = ct0 + (warp >> 2);
       const bool ok = ctile < t1;
-      const int rr = ((warp & 3) << 4) + gq;
+      const int rr = ((warp & 3) << 4) + 2 * gq;   // this thread's rows: timesteps rr and rr + 1 of the cache tile
       const long long ts = (long long)ctile * MRL_TILE + rr;
-      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 8 < a.N;
+      const bool valid0 = ok && ts < a.N, valid1 = ok && ts + 1 < a.N;
       const float* zb = a.Zt + (size_t)ctile * g.d[1] * MRL_LDT + rr;
       float* cb = a.cache ? a.cache + (size_t)ctile * g.act_rows * MRL_LDT + rr : nullptr;
       const float* auxb = a.aux ? a.aux + (size_t)ctile * g.naux * MRL_LDT + rr : nullptr;
@@ -1126,7 +1129,7 @@ __global__ void __launch_bounds__(FW_THREADS, 2) chain_fwd_kernel(NetGeom g, Mid
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = 8 * n + 2 * t + (i & 1);
-            if (j < dL && (i < 2 ? valid0 : valid1)) a.head_out[(size_t)(ts + (i < 2 ? 0 : 8)) * dL + j] = o[n][i];
+            if (j < dL && (i < 2 ? valid0 : valid1)) a.head_out[(size_t)(ts + (i < 2 ? 0 : 1)) * dL + j] = o[n][i];
           }
       }
     }
