@@ -1,21 +1,24 @@
-// Fisher-vector product through layers >= 2 as a register-resident per-warp chain (trpo.py:45-58).
+// Layers >= 2 of the MLP as register-resident per-warp chains: forward (losses, activation cache),
+// gradient and Fisher-vector product (trpo.py:37-63; ppo.py:35-49; core.py:613-617).
 //
-// One CTA (8 warps) owns a slab of <= 1024 timesteps and walks it in chain tiles of 128 timesteps.
+// Backward kernel (gradient / Fvp): one CTA of 12 warps owns a slab of <= 1024 timesteps and walks it in
+// chain tiles of 192 timesteps (3 cache tiles).
 //
 //   chain phase  Each warp owns 16 timesteps and carries them through the whole R-forward (Pearlmutter)
 //                and reverse sweep WITHOUT block barriers: the m16n8 accumulator fragment of one layer is
 //                the A fragment of the next (k-slot t <-> feature 2t, slot t+4 <-> feature 2t+1, so no
 //                shuffle is needed), weights are read from shared memory in an 8x8-block layout that is
 //                bank-conflict free for both W (R-forward) and W^T (delta) fragment reads, cached
-//                activations come straight from HBM/L2 in fragment order.  Every product is 3xTF32
-//                (mma_tf32.cuh).  delta_l (l >= 2) is left in shared memory pre-split as (hi, lo) pairs,
-//                delta_1 goes to HBM as the tcgen05 operand of l1_grad_tc_kernel.
-//   grad phase   After ONE barrier the weight gradients G_l = h_{l-1}^T delta_l (K = the 128 timesteps)
-//                are accumulated by a static (layer, m-tile, n-tiles) -> warp assignment, so every
-//                accumulator block lives in registers for the whole slab and is flushed once as the
+//                activations come straight from HBM/L2 in fragment order (a thread's two fragment rows are
+//                adjacent timesteps: 64-bit accesses).  Every product is 3xTF32 (mma_tf32.cuh).  delta_l
+//                (l >= 2) is left in shared memory as fp32 rows, delta_1 goes to HBM as the pre-split
+//                tcgen05 operand of l1_grad_tc_kernel.
+//   grad phase   After ONE barrier the weight gradients G_l = h_{l-1}^T delta_l (K = the 192 timesteps)
+//                are accumulated by a static (layer, m-tile, n-tiles) -> warp assignment: every accumulator
+//                block has one owner, lives in shared memory between chain tiles and is flushed once as the
 //                fp32 slab partial that reduce_partials_kernel sums in fp64.
 //
-// Two barriers per 128 timesteps (the job-list kernel in mlp_mid.cu needs ~10 per 64) and ~3x fewer
+// Two barriers per 192 timesteps (the job-list kernel in mlp_mid.cu needs ~10 per 64) and ~2x fewer
 // issued instructions per timestep; see DESIGN.md section 4 for the measured effect.
 #include "common.cuh"
 #include "kernels.h"
@@ -872,7 +875,8 @@ cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_s
 // ====================================================================================================
 // Forward chain: h1 = act(Z1 + b1), ..., head -> surr / kl / ent (or squared error) sums, activation cache,
 // row-major head output (trpo.py:37-42,60-63; core.py:339-365,402-438,613-617).  Same per-warp register
-// chain as above (16 timesteps per warp, no block barriers inside a slab), 8 warps = 128 timesteps per pass.
+// chain as above (16 timesteps per warp, no block barriers inside a slab), 8 warps = 128 timesteps per pass,
+// 2 CTAs per SM.
 #define CH_LOG_2PIE 2.8378770664093453f
 
 __device__ __forceinline__ void st_cfrag(float* __restrict__ p, const float (&v)[4], int f0, int dmax, bool ok) {
