@@ -111,4 +111,8 @@ class PpoSgdAgent(AgentWithPolicy):
     options = MLP_OPTIONS + PG_OPTIONS + PpoSgdUpdater.options + FILTER_OPTIONS
 
     def __init__(self, ob_space, ac_space, usercfg):
-        PpoSgdUpdater(None, usercfg)
+        cfg = update_default_config(self.options, usercfg)
+        policy, self.baseline = make_mlps(ob_space, ac_space, cfg)
+        obfilter, rewfilter = make_filters(cfg, ob_space)
+        self.updater = PpoSgdUpdater(policy, cfg)
+        AgentWithPolicy.__init__(self, policy, obfilter, rewfilter)

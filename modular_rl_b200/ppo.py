@@ -6,7 +6,9 @@ on the host - the one the reference calls (ppo.py:85) - and each of its evaluati
 set_params + fused forward / reverse sweep on the device (mrl_net_ppo_lossgrad), where the chain-rule
 coefficient of the KL term is computed from the batch-wide KL without a host round trip.
 
-PpoSgdUpdater (ppo.py:115-258) is out of this path's scope.
+PpoSgdUpdater (ppo.py:115-258) reuses the same device loss/gradient entry point on
+minibatches of 128 gathered rows; Adam (adam_updates, ppo.py:231-258) runs on the host in float32 like the
+reference's floatX shared variables.
 """
 from collections import OrderedDict
 
@@ -104,7 +106,12 @@ class PpoLbfgsUpdater(EzFlat, EzPickle):
         return info
 
 
-class PpoSgdUpdater(object):
+class PpoSgdUpdater(EzFlat, EzPickle):
+    """ppo.py:115-228.  Differences from PpoLbfgsUpdater that matter: the old policy's probabilities are a
+    forward pass at the parameters the call starts from (not path["prob"]), KL is always kl[old, new], each
+    minibatch's `train` returns the losses BEFORE its Adam step, and kl_coeff adapts on the last epoch's mean
+    minibatch KL."""
+
     options = [
         ("kl_target", float, 1e-2, ""),
         ("epochs", int, 10, ""),
@@ -112,7 +119,99 @@ class PpoSgdUpdater(object):
         ("do_split", int, 0, "do train/test split"),
         ("kl_cutoff_coeff", float, 1000.0, ""),
     ]
+    batchsize = 128
 
     def __init__(self, stochpol, usercfg):
-        raise NotImplementedError("PpoSgdUpdater is outside the accelerated path (SURVEY 8f); "
-                                  "use TrpoUpdater or PpoLbfgsUpdater")
+        EzPickle.__init__(self, stochpol, usercfg)
+        cfg = update_default_config(self.options, usercfg)
+        print("PPOUpdater", cfg)
+        if cfg["kl_cutoff_coeff"] != 1000.0:
+            raise NotImplementedError("the device penalty kernel fixes kl_cutoff_coeff at 1000 (ppo.py:20)")
+        self.stochpol = stochpol
+        self.cfg = cfg
+        self.kl_coeff = 1.0
+        EzFlat.__init__(self, stochpol.net)
+        self.loss_names = ["surr", "kl", "ent"]
+        self._full = DeviceBatch(stochpol.dims[0], with_time_feature=True)
+        self._mb = DeviceBatch(stochpol.dims[0], with_time_feature=True)
+        P = stochpol.net.P
+        self._t = 0                                   # adam_updates' shared step counter
+        self._m = np.zeros(P, np.float32)
+        self._v = np.zeros(P, np.float32)
+
+    def _bind(self, batch, ob, act, adv, prob):
+        batch.set_obs(np.asarray(ob).reshape(len(ob), -1))
+        batch.set_policy_inputs(self.stochpol.probtype.head, self.stochpol.dims[-1], act, adv, prob)
+        return batch
+
+    def _adam(self, theta, g, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        f = np.float32
+        self._t += 1
+        a_t = f(self.cfg["stepsize"]) * np.sqrt(f(1) - f(beta2) ** self._t) / (f(1) - f(beta1) ** self._t)
+        g = g.astype(f)
+        self._m = f(beta1) * self._m + f(1 - beta1) * g
+        self._v = f(beta2) * self._v + f(1 - beta2) * g * g
+        return (theta - a_t * self._m / (np.sqrt(self._v) + f(epsilon))).astype(f)
+
+    def __call__(self, paths):
+        cfg = self.cfg
+        net = self.stochpol.net
+        ob_no = concat([path["observation"] for path in paths])
+        action_na = concat([path["action"] for path in paths])
+        advantage_n = concat([path["advantage"] for path in paths])
+        ob_no = np.asarray(ob_no).reshape(len(ob_no), -1)
+        N = ob_no.shape[0]
+        bs = self.batchsize
+        kl_cutoff = cfg["kl_target"] * 2.0
+
+        # update_old_net (ppo.py:174): the old policy is the current one; one forward pass gives its rows
+        self._full.set_obs(ob_no)
+        oldprob_np = self.stochpol.output_from_head(net.forward(self._full))
+
+        def losses_of(sl):
+            b = self._bind(self._full, ob_no[sl], action_na[sl], advantage_n[sl], oldprob_np[sl])
+            return net.ppo_lossgrad(b, 0.0, 1e300, False, want_grad=False)[2]
+
+        if cfg["do_split"]:
+            train_stop = (int(.75 * N) // bs) * bs
+            test_losses_before = losses_of(slice(train_stop, None))
+        else:
+            train_stop = N
+        train_losses_before = losses_of(slice(0, train_stop))
+
+        theta = self.get_params_flat().astype(np.float32)
+        train_losses = train_losses_before
+        for _ in range(cfg["epochs"]):
+            sortinds = np.random.permutation(train_stop)
+            losses = []
+            for istart in range(0, train_stop, bs):
+                idx = sortinds[istart:istart + bs]
+                mb = self._bind(self._mb, ob_no[idx], action_na[idx], advantage_n[idx], oldprob_np[idx])
+                _, g, ls = net.ppo_lossgrad(mb, self.kl_coeff, kl_cutoff, False)
+                losses.append(ls)
+                theta = self._adam(theta, g)
+                self.set_params_flat(theta)
+            train_losses = np.mean(losses, axis=0)
+            if cfg["do_split"]:
+                test_losses = losses_of(slice(train_stop, None))
+
+        klafter = train_losses[self.loss_names.index("kl")]
+        if klafter > 1.3 * cfg["kl_target"]:
+            self.kl_coeff *= 1.5
+            print("Got KL=%.3f (target %.3f). Increasing penalty coeff => %.3f." % (klafter, cfg["kl_target"], self.kl_coeff))
+        elif klafter < 0.7 * cfg["kl_target"]:
+            self.kl_coeff /= 1.5
+            print("Got KL=%.3f (target %.3f). Decreasing penalty coeff => %.3f." % (klafter, cfg["kl_target"], self.kl_coeff))
+        else:
+            print("KL=%.3f is close enough to target %.3f." % (klafter, cfg["kl_target"]))
+        info = OrderedDict()
+        for (name, lossbefore, lossafter) in zipsame(self.loss_names, train_losses_before, train_losses):
+            info[name + "_before"] = lossbefore
+            info[name + "_after"] = lossafter
+            info[name + "_change"] = lossafter - lossbefore
+        if cfg["do_split"]:
+            for (name, lossbefore, lossafter) in zipsame(self.loss_names, test_losses_before, test_losses):
+                info["test_" + name + "_before"] = lossbefore
+                info["test_" + name + "_after"] = lossafter
+                info["test_" + name + "_change"] = lossafter - lossbefore
+        return info

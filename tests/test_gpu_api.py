@@ -199,3 +199,34 @@ def test_act_batch_matches_act(kind):
     assert np.allclose(a_batch[0], a_one)
     det, _ = pol.act_batch(fobs, stochastic=False)
     assert len(det) == 37
+
+
+@pytest.mark.parametrize("kind", ["box", "discrete"])
+def test_ppo_sgd_updater_matches_oracle(kind):
+    """PpoSgdUpdater (ppo.py:115-228): minibatch-128 Adam on the penalised surrogate, against the oracle
+    restatement with the same numpy permutation stream."""
+    from modular_rl_b200 import agentzoo, spaces
+    from oracle.ppo_sgd import Adam, ppo_sgd_update
+    rng = np.random.default_rng(2)
+    ob_space = spaces.Box(-np.ones(6), np.ones(6))
+    ac_space = spaces.Box(-np.ones(2), np.ones(2)) if kind == "box" else spaces.Discrete(3)
+    agent = agentzoo.PpoSgdAgent(ob_space, ac_space, dict(hid_sizes=[16, 8], timestep_limit=60, epochs=2,
+                                                            stepsize=1e-3))
+    paths = _make_paths(rng, 12, 6, agent.policy)
+    for p in paths:
+        p["advantage"] = rng.standard_normal(len(p["reward"]))
+    theta = agent.policy.get_flat().astype(np.float64)
+    spec = _oracle_spec(agent.policy)
+    cat = lambda k: np.concatenate([p[k] for p in paths])
+    np.random.seed(7)
+    out = agent.updater(paths)
+    np.random.seed(7)
+    oinfo, oth, oklc, n_mb = ppo_sgd_update(theta, spec, cat("observation"), cat("action"), cat("advantage"),
+                                            Adam(theta.size, 1e-3), epochs=2)
+    assert list(out) == list(oinfo)
+    for k in out:
+        assert np.isclose(out[k], oinfo[k], rtol=2e-3, atol=2e-5), (k, out[k], oinfo[k])
+    assert agent.updater.kl_coeff == oklc
+    # Adam normalises the gradient, so float32 noise in near-zero components moves a parameter by O(stepsize)
+    th = agent.policy.get_flat()
+    assert np.abs(th - oth).max() < 5e-3 and relerr(th, oth) < 2e-3

@@ -229,3 +229,54 @@ def test_data_parallel_algebra_gloo_world2(tmp_path):
     mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     x0, x1 = np.load(tmp_path / "x0.npy"), np.load(tmp_path / "x1.npy")
     assert np.array_equal(x0, x1)          # bit-identical replicas
+
+
+# ----------------------------------------------------------------------------- PpoSgdUpdater oracle (ppo.py:115-258)
+def test_oracle_adam_matches_independent_adam():
+    """adam_updates' recurrences (ppo.py:231-258) against torch.optim.Adam; the two differ only in where epsilon
+    sits, so they must agree to rounding with epsilon = 0."""
+    import torch
+    from oracle.ppo_sgd import Adam
+    rng = np.random.default_rng(0)
+    th = rng.standard_normal(40)
+    A = rng.standard_normal((40, 40))
+    A = A @ A.T / 40
+    o = Adam(40, 1e-2, epsilon=0.0)
+    t = torch.tensor(th.copy(), dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([t], lr=1e-2, eps=0.0)
+    x = th.copy()
+    for _ in range(15):
+        x = o.step(x, A @ x)
+        opt.zero_grad()
+        (0.5 * (t @ torch.tensor(A) @ t)).backward()
+        opt.step()
+    assert np.abs(x - t.detach().numpy()).max() < 1e-13
+    # with the reference's epsilon the first step is lr * g / (|g| + eps * ...) ~ lr * sign(g)
+    o2 = Adam(3, 1e-3)
+    x2 = o2.step(np.zeros(3), np.array([2.0, -0.5, 1e-3]))
+    assert np.allclose(x2, [-1e-3, 1e-3, -1e-3], rtol=1e-3)
+    want = -1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * 1e-3) / (np.sqrt(0.001) * 1e-3 + 1e-8)   # eps is not bias-corrected
+    assert np.isclose(x2[2], want, rtol=1e-12)
+
+
+def test_oracle_ppo_sgd_update_runs_and_adapts_kl_coeff():
+    from oracle import policy_math as pm
+    from oracle.ppo_sgd import Adam, ppo_sgd_update
+    from modular_rl_b200 import synth
+    rng = np.random.default_rng(3)
+    dims = (5, 8, 3)
+    spec = pm.NetSpec(dims, pm.GAUSS)
+    theta = synth.init_params(dims, synth.GAUSS, rng)
+    ob = rng.standard_normal((300, 5))
+    prob = np.concatenate([pm.forward(theta, spec, ob)[1], np.ones((300, 3))], 1)
+    act = prob[:, :3] + rng.standard_normal((300, 3))
+    adv = rng.standard_normal(300)
+    np.random.seed(1)
+    info, th_new, klc, n_mb = ppo_sgd_update(theta, spec, ob, act, adv, Adam(theta.size), epochs=3)
+    assert n_mb == 3 * 3 and th_new.shape == theta.shape and not np.allclose(th_new, theta)
+    assert list(info)[:3] == ["surr_before", "surr_after", "surr_change"]
+    assert abs(info["kl_before"]) < 1e-12 and info["kl_after"] > 0          # old net == net at entry
+    assert klc in (1.5, 1.0, 1.0 / 1.5)
+    np.random.seed(1)
+    info2, *_ = ppo_sgd_update(theta, spec, ob, act, adv, Adam(theta.size), epochs=3, do_split=True)
+    assert "test_kl_after" in info2
