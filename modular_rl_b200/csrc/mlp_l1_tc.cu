@@ -631,7 +631,7 @@ static bool l1g_plan(const NetGeom& g, int* acc_stride, int* nts, int* nss, int*
   *tmem_cols = 32;
   while (*tmem_cols < ftiles * nu + *nts * ftiles * 16) *tmem_cols *= 2;
   *smem = 512 + (size_t)*nss * stage_bytes;
-  return nu <= 256 && *nts >= 2 && *nss >= 2 && *tmem_cols <= 512;
+  return nu <= 256 && *nts >= 1 && *nss >= 2 && *tmem_cols <= 512;   // one A slot still works (serialised)
 }
 
 cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,

@@ -109,6 +109,10 @@ SHAPES = {
     "cartpole": ((4, 64, 64, 2), 1, 777),
     "linear": ((6, 4), 0, 100),
     "one_hidden": ((9, 33, 5), 1, 257),
+    # first hidden layer wider than 128: single (not double-buffered) TMEM accumulator in the layer-1 forward
+    # kernel, wide rows in the layer-1 gradient kernel, generic job-list kernels for the rest
+    "wide": ((20, 160, 16, 4), 0, 1500),
+    "wide_in": ((300, 136, 24, 5), 1, 900),
 }
 
 
