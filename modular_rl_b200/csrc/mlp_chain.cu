@@ -30,6 +30,12 @@
 #define CH_T (16 * CH_WARPS)        // timesteps per chain tile
 #define CH_LDE (CH_T + 8)           // floats between consecutive delta rows in shared memory (= 8 mod 32: the
                                     // 64-bit fragment reads of the grad phase are bank-conflict free)
+#ifndef MRL_CACHED_EARLY
+#define MRL_CACHED_EARLY 0   // request h2 / h3 / head rows before the layer-2 loop (1) or after it (0)
+#endif
+#ifndef MRL_PF_DIST
+#define MRL_PF_DIST 2
+#endif
 #define FW_WARPS 8                  // forward chain kernel: 256 threads, 2 CTAs per SM
 #define FW_THREADS (32 * FW_WARPS)
 
@@ -334,30 +340,32 @@ __device__ __forceinline__ void rfwd_layer2(float (&acc)[N2][4], const float* __
                                             const float* __restrict__ vb1, const float* __restrict__ W,
                                             const float* __restrict__ V, int lane) {
   const int t = lane & 3;
-  float zc[4], hc[4], z1[4], h1[4];     // k-steps ks and ks+1; ks+2 is requested at the top of the loop
-  ldfrag(zc, zp, 2 * t, d1, ok);
-  ldfrag(hc, hp, 2 * t, d1, ok);
-  ldfrag(z1, zp, 8 + 2 * t, d1, ok && N1 > 1);
-  ldfrag(h1, hp, 8 + 2 * t, d1, ok && N1 > 1);
+  constexpr int D = MRL_PF_DIST;          // k-steps requested ahead of use (register prefetch)
+  float zq[D + 1][4], hq[D + 1][4];       // [0] = current k-step
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    ldfrag(zq[i], zp, 8 * i + 2 * t, d1, ok && i < N1);
+    ldfrag(hq[i], hp, 8 * i + 2 * t, d1, ok && i < N1);
+  }
 #pragma unroll 1
   for (int ks = 0; ks < N1; ++ks) {
-    float zn[4], hn[4];
-    const bool more = ks + 2 < N1;
-    ldfrag(zn, zp, 8 * (ks + 2) + 2 * t, d1, ok && more);
-    ldfrag(hn, hp, 8 * (ks + 2) + 2 * t, d1, ok && more);
+    ldfrag(zq[D], zp, 8 * (ks + D) + 2 * t, d1, ok && ks + D < N1);
+    ldfrag(hq[D], hp, 8 * (ks + D) + 2 * t, d1, ok && ks + D < N1);
     const float2 b = *reinterpret_cast<const float2*>(vb1 + 8 * ks + 2 * t);
     float r[4];
-    r[0] = dact_from_h<ACT>(hc[0]) * (zc[0] + b.x);
-    r[1] = dact_from_h<ACT>(hc[1]) * (zc[1] + b.y);
-    r[2] = dact_from_h<ACT>(hc[2]) * (zc[2] + b.x);
-    r[3] = dact_from_h<ACT>(hc[3]) * (zc[3] + b.y);
+    r[0] = dact_from_h<ACT>(hq[0][0]) * (zq[0][0] + b.x);
+    r[1] = dact_from_h<ACT>(hq[0][1]) * (zq[0][1] + b.y);
+    r[2] = dact_from_h<ACT>(hq[0][2]) * (zq[0][2] + b.x);
+    r[3] = dact_from_h<ACT>(hq[0][3]) * (zq[0][3] + b.y);
     uint32_t ah[4], al[4];
     to_frag(r, ah, al);
     kstep<N2, false>(acc, ah, al, W, ks, 0, N2, lane);
-    to_frag(hc, ah, al);
+    to_frag(hq[0], ah, al);
     kstep<N2, false>(acc, ah, al, V, ks, 0, N2, lane);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { zc[i] = z1[i]; hc[i] = h1[i]; z1[i] = zn[i]; h1[i] = hn[i]; }
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { zq[i][c] = zq[i + 1][c]; hq[i][c] = hq[i + 1][c]; }
   }
 }
 // R-forward of layer l >= 3: A = Rh_{l-1} (fragments) with W_l, and A = h_{l-1} with V_l
@@ -599,16 +607,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pz), "r"(zn) : "memory");
       }
       float h2[N2][4];
-#pragma unroll
-      for (int n = 0; n < N2; ++n) ldfrag(h2[n], cb + g.off_act[2] * MRL_LDT, 8 * n + 2 * t, g.d[2], ok);
       float h3[L == 4 ? N3 : 1][4];
-      if constexpr (L == 4) {
-#pragma unroll
-        for (int n = 0; n < N3; ++n) ldfrag(h3[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok);
-      }
       float ph[NL][4];   // cached head output: probabilities (Fvp, Categorical) / mean | probs | value (gradient)
+      auto load_cached = [&]() {
 #pragma unroll
-      for (int n = 0; n < NL; ++n) ldfrag(ph[n], cb + g.off_act[L] * MRL_LDT, 8 * n + 2 * t, g.d[L], ok && (cat || !FVP));
+        for (int n = 0; n < N2; ++n) ldfrag(h2[n], cb + g.off_act[2] * MRL_LDT, 8 * n + 2 * t, g.d[2], ok);
+        if constexpr (L == 4) {
+#pragma unroll
+          for (int n = 0; n < N3; ++n) ldfrag(h3[n], cb + g.off_act[3] * MRL_LDT, 8 * n + 2 * t, g.d[3], ok);
+        }
+#pragma unroll
+        for (int n = 0; n < NL; ++n) ldfrag(ph[n], cb + g.off_act[L] * MRL_LDT, 8 * n + 2 * t, g.d[L], ok && (cat || !FVP));
+      };
+      if (MRL_CACHED_EARLY || !FVP) load_cached();
       float dL[NL][4];   // delta_L (accumulator order)
       if constexpr (FVP) {
         // ---- R-forward (Pearlmutter) and the Fisher metric
@@ -616,6 +627,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         float acc2[N2][4];
         zero_acc(acc2);
         rfwd_layer2<ACT, N1, N2>(acc2, zb, cb, g.d[1], ok, vb + S::vboff(1), Ws + S::woff(2), Vs + S::woff(2), lane);
+        if (!MRL_CACHED_EARLY) load_cached();
         uint32_t r2h[N2][4], r2l[N2][4];
         epi_rhidden<ACT, N2>(acc2, h2, vb + S::vboff(2), r2h, r2l, lane);
         float acc3[N3][4];
