@@ -33,6 +33,9 @@
 #ifndef MRL_CACHED_EARLY
 #define MRL_CACHED_EARLY 0   // request h2 / h3 / head rows before the layer-2 loop (1) or after it (0)
 #endif
+#ifndef MRL_H1_LATE
+#define MRL_H1_LATE 0
+#endif
 #ifndef MRL_PF_DIST
 #define MRL_PF_DIST 2
 #endif
@@ -73,6 +76,27 @@ struct ChainShape {
            (size_t)gblocks() * 128 + (size_t)erows() * CH_LDE;
   }
 };
+
+// split barriers between the chain and grad phases (one arrive per warp): a warp signals as soon as ITS part is
+// done and only waits where it really needs the others' data, so the skew between warps is absorbed by work
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > (1u << 26)) __trap();   // a protocol bug becomes an error, never a hung GPU
+  }
+}
 
 // row of feature j' (0..7) inside an 8x8 weight block: conflict-free for the 64-bit W reads (lanes g = 0..3 /
 // 4..7 of a half-warp hit rows with distinct (row mod 4)) and for the 32-bit W^T reads (rows 2t / 2t+1).
@@ -429,11 +453,17 @@ __device__ __forceinline__ void delta1_block(const uint32_t (&dhi)[NO][4], const
                                              int lane) {
   const int g = lane >> 2, t = lane & 3;
   float h1[NH][4];
+#if !MRL_H1_LATE
 #pragma unroll
   for (int n = 0; n < NH; ++n) ldfrag(h1[n], hp, 8 * (nb + n) + 2 * t, d1, ok);
+#endif
   float acc[NH][4];
   zero_acc(acc);
   delta_layer<NH, NO>(acc, dhi, dlo, W2, nb, lane);
+#if MRL_H1_LATE
+#pragma unroll
+  for (int n = 0; n < NH; ++n) ldfrag(h1[n], hp, 8 * (nb + n) + 2 * t, d1, ok);
+#endif
 #pragma unroll
   for (int n = 0; n < NH; ++n) {
     float v[4];
@@ -541,9 +571,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
   float* glss = gb1s + CH_WARPS * 8 * N1;              // [warp][8 NL] logstd partials (gradient mode)
   float* Gs = glss + CH_WARPS * 8 * NL;                // weight-gradient accumulator blocks of all entries
   float* E = Gs + S::gblocks() * 128;                  // delta rows [row][CH_LDE]
+  __shared__ uint64_t e_full, e_free;   // delta rows of the current chain tile: all stored / all consumed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
   const bool cat = g.head == MRL_HEAD_CAT, gauss = g.head == MRL_HEAD_GAUSS;
+  if (tid == 0) {
+    mbar_init(&e_full, CH_WARPS);
+    mbar_init(&e_free, CH_WARPS);
+    fence_barrier_init();
+  }
+  uint32_t tile_no = 0;                 // chain tiles processed by this CTA (barrier phase = tile_no & 1)
 
   // ---- weights of theta (W) and of the tangent (V) into the 8x8-block layout, tangent biases, sigma, 1/sigma^2
 #pragma unroll
@@ -648,6 +685,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         head_grad<NL>(g.head, ph, auxb, g.d[L], sig, ivar, cs, ck, a.reverse_kl, valid0, valid1, ok, gls, dL, lane);
       }
       // ---- reverse sweep
+      bar_wait(&e_free, (tile_no & 1) ^ 1);   // the previous tile's grad phase has read its delta rows (passes at once for tile 0)
       store_E<NL>(E + (size_t)S::eoff(L) * CH_LDE, dL, warp, lane);
       uint32_t d2h[N2][4], d2l[N2][4];
       {
@@ -673,6 +711,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         store_E<N2>(E + (size_t)S::eoff(2) * CH_LDE, d2, warp, lane);
         to_frags<N2>(d2, d2h, d2l);
       }
+      warp_arrive(&e_full, lane);           // this warp's delta rows are complete; delta_1 below needs nobody else
       float* dg = a.DG + (size_t)(ct0 * 8 + 2 * warp) * (2 * a.nu * 8);
       constexpr int NA = (N1 + 1) / 2, NB = N1 - NA;
       delta1_block<ACT, NA, 0, N1, N2>(d2h, d2l, Ws + S::woff(2), cb, g.d[1], ok, gb1s + warp * 8 * N1, dg, a.nu, lane);
@@ -684,7 +723,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         for (int k = 0; k < 8; ++k) dgz[(size_t)k * (a.nu * 4)] = 0.f;   // [tg 2][hi|lo 2][khalf 2] x 32 floats
       }
     }
-    __syncthreads();
+    bar_wait(&e_full, tile_no & 1);
     // ================= grad phase: G_l += h_{l-1}^T delta_l over the CH_T timesteps of this chain tile
     {
       const int tiles_here = min(CH_TILES, t1 - ct0);
@@ -713,7 +752,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(NetGeom g, Mid
         if (lane == j) gbe += s;
       }
     }
-    __syncthreads();
+    warp_arrive(&e_free, lane);
+    ++tile_no;
   }
 
   // ================= flush the slab partial
