@@ -144,6 +144,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def chain_mma_flops_per_timestep(dims):
+    """TF32 tensor-core flops the backward chain kernel ISSUES per timestep for an Fvp (3xTF32, widths padded to 8,
+    weight-gradient m-tiles padded to 16): chain phase 3 GEMM passes over the (k-step, n-tile) pairs (W and V in the
+    R-forward, W^T in the reverse sweep), grad phase one m16n8k8 block per 8 timesteps."""
+    nt = [-(-d // 8) for d in dims]
+    pairs = sum(nt[l - 1] * nt[l] for l in range(2, len(dims)))
+    blocks = sum(-(-dims[l - 1] // 16) * nt[l] for l in range(2, len(dims)))
+    return 3 * (3 * pairs) * 2048 / 16 + blocks * 3 * 2048 / 8
+
+
 def algorithmic_flops_per_timestep(dims):
     d0d1 = dims[0] * dims[1]
     S = sum(dims[l - 1] * dims[l] for l in range(2, len(dims)))
@@ -281,8 +291,9 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        fp32 = C.c_double()
+        fp32, mma32 = C.c_double(), C.c_double()
         L.check(lib.mrl_measure_fp32_tflops(local_rank, C.byref(fp32)))
+        L.check(lib.mrl_measure_mma_tf32_tflops(local_rank, C.byref(mma32)))
         flops = algorithmic_flops_per_timestep(wl.dims)
         kernels = {}
         for k in range(nk):
@@ -316,10 +327,13 @@ def main():
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
                                 "fallback 1.4 PFLOP/s sustained (of fallback)"),
                 "pipe": pipes.get(top, ""), "flops_counted": "algorithmic FP32 flops; each costs 3 TF32 MMAs",
-                "tf32_mma_tflops_issued": 3.0 * kernels[top]["algo_tflops"],
+                "tf32_mma_tflops_issued": (chain_mma_flops_per_timestep(wl.dims) * n_local / (kernels[top]["avg_ms"] * 1e-3) / 1e12
+                                           if top == "mid_backward_fvp" else 3.0 * kernels[top]["algo_tflops"]),
+                "mma_sync_tf32_peak_tflops": mma32.value,
                 "fp32_fma_peak_tflops": fp32.value,
                 "frac_of_fp32_fma_peak": kernels[top]["algo_tflops"] / fp32.value,
                 "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
+        roof["frac_of_mma_sync_tf32_peak"] = roof["tf32_mma_tflops_issued"] / mma32.value if mma32.value else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))

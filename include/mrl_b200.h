@@ -54,6 +54,8 @@ int mrl_profile_kinds(void);
 const char* mrl_profile_kind_name(int kind);
 int mrl_profile_read(double* ms_out, long long* count_out);
 int mrl_measure_fp32_tflops(int device, double* tflops_out);
+/* measured mma.sync m16n8k8 TF32 throughput (dense TFLOP/s): the pipe of the register-chain kernels */
+int mrl_measure_mma_tf32_tflops(int device, double* tflops_out);
 
 /* ---------------------------------------------------------------- batch (paths, flattened)
  * Replaces the `concat([path[k] for path in paths])` host copies of trpo.py:74-77,

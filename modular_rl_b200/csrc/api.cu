@@ -322,6 +322,57 @@ extern "C" int mrl_measure_fp32_tflops(int device, double* tflops_out) {
   return 0;
 }
 
+// mma.sync m16n8k8 TF32 throughput of this GPU (the pipe the register-chain kernels are bound by): 8 independent
+// accumulators per warp, 16 warps per SM, for the roofline report.
+__global__ void mma_peak_kernel(float* out, int iters) {
+  float c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  const unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 * 3, b1 = a0 * 5;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += c[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" int mrl_measure_mma_tf32_tflops(int device, double* tflops_out) {
+  if (!tflops_out) return fail("mrl_measure_mma_tf32_tflops: null out");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms, threads = 512, iters = 8192;
+  float* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    mma_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1, 0);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * (threads / 32) * iters * 8.0 * (16.0 * 8.0 * 8.0 * 2.0);
+    best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  g_launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
+  return 0;
+}
+
 __global__ void mix_target_kernel(const double* __restrict__ ret, const double* __restrict__ base, double mix,
                                   long long N, float* __restrict__ aux) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
