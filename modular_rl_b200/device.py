@@ -86,6 +86,13 @@ class DeviceBatch:
         self.ob_dim, self.device, self.with_time = int(ob_dim), device, bool(with_time_feature)
         self.N = 0
 
+    def __getstate__(self):
+        # snapshots (run_pg.py:141-142) carry no batch data: an empty batch of the same shape comes back
+        return dict(ob_dim=self.ob_dim, with_time=self.with_time, device=self.device)
+
+    def __setstate__(self, d):
+        self.__init__(d["ob_dim"], d["with_time"], d["device"])
+
     def close(self):
         if getattr(self, "_h", None):
             L.lib().mrl_batch_destroy(self._h)
@@ -182,9 +189,19 @@ class DeviceNet:
         self._h = C.c_void_p()
         L.check(L.lib().mrl_net_create(C.byref(self._h), device, len(self.dims) - 1, arr, head,
                                        L.ACTIVATIONS[activation]))
-        self.head, self.device = head, device
+        self.head, self.device, self.activation = head, device, activation
         self.P = int(L.lib().mrl_net_num_params(self._h))
         self.dout = self.dims[-1]
+
+    def __getstate__(self):
+        # the device handle is rebuilt on load; theta travels as the flat float32 vector of SURVEY A.1.
+        # A communicator is not part of a snapshot: re-attach it with set_comm after loading.
+        return dict(dims=self.dims, head=self.head, activation=self.activation, device=self.device,
+                    theta=self.get_params())
+
+    def __setstate__(self, d):
+        self.__init__(d["dims"], d["head"], d["activation"], d["device"])
+        self.set_params(d["theta"])
 
     def close(self):
         if getattr(self, "_h", None):

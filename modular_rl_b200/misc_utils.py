@@ -4,6 +4,7 @@ agents and run_pg.py are built on, EzPickle, flatten/unflatten, explained varian
 from __future__ import print_function
 
 import atexit
+import os
 import os.path as osp
 import sys
 from collections import defaultdict
@@ -126,6 +127,44 @@ def prepare_h5_file(args):
     hdf["cmd"] = " ".join(sys.argv)
     atexit.register(save)
     return hdf, diagnostics
+
+
+def save_agent_snapshot(agent, dirname, counter):
+    """Pickled agent written as <dirname>/agent_snapshots/<%04i>.pkl - the same bytes run_pg.py:141-142
+    stores under /agent_snapshots/%0.4i of the hdf5 file, for boxes without h5py."""
+    import pickle
+    d = osp.join(dirname, "agent_snapshots")
+    os.makedirs(d, exist_ok=True)
+    fname = osp.join(d, "%0.4i.pkl" % counter)
+    with open(fname, "wb") as f:
+        f.write(pickle.dumps(agent, -1))
+    return fname
+
+
+def load_agent_snapshot(path, snapname=None):
+    """Agent from a snapshot: a .pkl written by save_agent_snapshot, a directory of them, or an hdf5
+    results file with /agent_snapshots (sim_agent.py:41-52; snapname None = the last one)."""
+    import pickle
+    if osp.isdir(path):
+        d = osp.join(path, "agent_snapshots") if osp.isdir(osp.join(path, "agent_snapshots")) else path
+        names = sorted(n for n in os.listdir(d) if n.endswith(".pkl"))
+        if not names:
+            raise ValueError("no snapshots under %s" % d)
+        name = (snapname + ".pkl") if snapname else names[-1]
+        if name not in names:
+            raise ValueError("Invalid snapshot name %s" % snapname)
+        path = osp.join(d, name)
+    if path.endswith(".pkl"):
+        with open(path, "rb") as f:
+            return pickle.loads(f.read())
+    import h5py  # optional dependency
+    with h5py.File(path, "r") as hdf:
+        snapnames = sorted(hdf["agent_snapshots"].keys())
+        if snapname is None:
+            snapname = snapnames[-1]
+        elif snapname not in snapnames:
+            raise ValueError("Invalid snapshot name %s" % snapname)
+        return pickle.loads(hdf["agent_snapshots"][snapname][()].tobytes())
 
 
 # ================================================================

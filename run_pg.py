@@ -43,7 +43,13 @@ def main():
         args.timestep_limit = env_spec.max_episode_steps
     cfg = args.__dict__
     np.random.seed(args.seed)
-    agent = agent_ctor(env.observation_space, env.action_space, cfg)
+    if args.load_snapshot:
+        # the reference declares the flag (misc_utils.py:102) without reading it; here it resumes from a
+        # pickled agent (.pkl / directory written below, or an hdf5 results file as sim_agent.py:41-52 reads)
+        agent = load_agent_snapshot(args.load_snapshot)
+        assert isinstance(agent, agent_ctor), "snapshot holds a %s" % type(agent).__name__
+    else:
+        agent = agent_ctor(env.observation_space, env.action_space, cfg)
     if args.use_hdf:
         hdf, diagnostics = prepare_h5_file(args)
 
@@ -62,6 +68,8 @@ def main():
                     diagnostics[stat].extend(val)
             if args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
                 hdf['/agent_snapshots/%0.4i' % counter[0]] = np.array(pickle.dumps(agent, -1))
+        elif args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
+            save_agent_snapshot(agent, mondir, counter[0])      # same bytes, one file per snapshot
         if args.plot:
             animate_rollout(env, agent, min(500, args.timestep_limit))
 

@@ -161,6 +161,70 @@ def test_coverage_smoke_pendulum():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "pol_surr_after" in out.stdout and "vf_EV_after" in out.stdout
+    # --snapshot_every: the pickled agent lands next to the results (the reference stores the same bytes in
+    # its hdf5 file, run_pg.py:141-142) and --load_snapshot resumes from it
+    snap = "/tmp/mrl_test_b.h5.dir/agent_snapshots/0001.pkl"
+    assert os.path.exists(snap)
+    from modular_rl_b200.misc_utils import load_agent_snapshot
+    agent = load_agent_snapshot(snap)
+    assert type(agent).__name__ == "TrpoAgent" and agent.policy.dims == [3, 10, 5, 1]
+    os.rename(snap, "/tmp/mrl_test_snapshot.pkl")
+    out = subprocess.run(cmd + ["--load_snapshot", "/tmp/mrl_test_snapshot.pkl"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "pol_surr_after" in out.stdout
+
+
+@pytest.mark.parametrize("agent_name", ["TrpoAgent", "PpoLbfgsAgent", "PpoSgdAgent"])
+def test_agent_pickle_roundtrip(agent_name):
+    """Agent snapshots (EzPickle, misc_utils.py:163-189; run_pg.py:141-142): a pickled agent comes back with
+    the same policy and value parameters, filter state and configuration, on fresh device handles, and its
+    updater still runs."""
+    import pickle
+    from modular_rl_b200 import agentzoo, spaces
+    from modular_rl_b200.core import compute_advantage
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    ob_space = spaces.Box(-np.ones(6), np.ones(6))
+    ac_space = spaces.Box(-np.ones(2), np.ones(2))
+    cfg = {"hid_sizes": [16, 8], "timestep_limit": 50, "max_kl": 0.02, "gamma": 0.97}
+    agent = getattr(agentzoo, agent_name)(ob_space, ac_space, cfg)
+    for _ in range(30):
+        agent.obfilt(rng.standard_normal(6))
+        agent.rewfilt(rng.standard_normal())
+    agent.policy.set_params_flat(agent.policy.get_params_flat() + 0.01 * rng.standard_normal(agent.policy.net.P))
+    blob = pickle.dumps(agent, -1)
+    twin = pickle.loads(blob)
+    assert type(twin) is type(agent) and twin.updater.stochpol is twin.policy
+    np.testing.assert_array_equal(twin.policy.get_params_flat(), agent.policy.get_params_flat())
+    np.testing.assert_array_equal(twin.baseline.reg.net.get_params(), agent.baseline.reg.net.get_params())
+    assert twin.updater.cfg == agent.updater.cfg and twin.baseline.timestep_limit == 50
+    assert twin.obfilter.rs.n == agent.obfilter.rs.n
+    np.testing.assert_array_equal(twin.obfilter.rs.mean, agent.obfilter.rs.mean)
+    ob = rng.standard_normal(6)
+    np.testing.assert_array_equal(twin.policy.act(ob, stochastic=False)[1]["prob"],
+                                  agent.policy.act(ob, stochastic=False)[1]["prob"])
+
+    def make_paths(a):
+        r = np.random.default_rng(9)
+        paths = []
+        for T in (20, 33, 50):
+            obs = r.standard_normal((T, 6))
+            prob = a.policy._act_prob(obs) if hasattr(a.policy, "_act_prob") else None
+            act = prob[:, :2] + prob[:, 2:] * r.standard_normal((T, 2))
+            paths.append(dict(observation=obs, action=act.astype(np.float32), prob=prob,
+                              reward=r.standard_normal(T), terminated=bool(T < 50)))
+        return paths
+
+    stats = []
+    for a in (agent, twin):
+        paths = make_paths(a)
+        compute_advantage(a.baseline, paths, gamma=0.97, lam=0.95)
+        np.random.seed(11)                                    # PpoSgd shuffles minibatches with numpy's RNG
+        stats.append(a.updater(paths))
+    for k in stats[0]:
+        assert stats[0][k] == stats[1][k], (k, stats[0][k], stats[1][k])
+    np.testing.assert_array_equal(twin.policy.get_params_flat(), agent.policy.get_params_flat())
 
 
 def test_multi_gpu_parity_two_ranks():

@@ -280,3 +280,22 @@ def test_oracle_ppo_sgd_update_runs_and_adapts_kl_coeff():
     np.random.seed(1)
     info2, *_ = ppo_sgd_update(theta, spec, ob, act, adv, Adam(theta.size), epochs=3, do_split=True)
     assert "test_kl_after" in info2
+
+
+def test_snapshot_files_roundtrip(tmp_path):
+    """save_agent_snapshot / load_agent_snapshot: one pickle per snapshot, named like the reference's hdf5
+    keys (run_pg.py:141-142); a directory resolves to its last snapshot or to a named one (sim_agent.py:41-52)."""
+    from modular_rl_b200.misc_utils import load_agent_snapshot, save_agent_snapshot
+    from modular_rl_b200.filters import ZFilter
+    f = ZFilter((3,), clip=5)
+    for i in range(4):
+        f(np.arange(3.0) * i)
+    p1 = save_agent_snapshot(f, str(tmp_path), 20)
+    f(np.ones(3))
+    save_agent_snapshot(f, str(tmp_path), 40)
+    assert p1.endswith("agent_snapshots/0020.pkl")
+    assert load_agent_snapshot(p1).rs.n == 4
+    assert load_agent_snapshot(str(tmp_path)).rs.n == 5
+    assert load_agent_snapshot(str(tmp_path), "0020").rs.n == 4
+    with pytest.raises(ValueError):
+        load_agent_snapshot(str(tmp_path), "0030")
