@@ -4,3 +4,4 @@ reference's modular_rl/__init__.py:1-6 (core, distributions, filters)."""
 from modular_rl_b200.core import *           # noqa: F401,F403
 from modular_rl_b200.distributions import *  # noqa: F401,F403
 from modular_rl_b200.filters import *        # noqa: F401,F403
+from modular_rl_b200.cem import *            # noqa: F401,F403

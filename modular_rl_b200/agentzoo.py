@@ -33,8 +33,54 @@ def make_mlps(ob_space, ac_space, cfg):
     return policy, baseline
 
 
+class DeterministicPolicy(StochPolicyMLP):
+    """The net of make_deterministic_mlp (agentzoo.py:63-81): Dense(h, tanh) per hidden size, then a linear
+    Dense(outdim) with kernel*0.1, acted on through probtype.maxprob - the output itself for Box actions, the
+    argmax for Discrete ones (softmax is monotone, so the argmax of the probabilities is the argmax of the
+    reference's logits; the "prob" row holds probabilities here, logits there, and nothing reads it).
+    The flat parameter vector is the Dense kernels and biases only: the device net of the Box case carries a
+    logstd block (pinned to 0, never used by maxprob) that get/set_params_flat hide, so the search space of
+    the cross-entropy method has the reference's dimension."""
+
+    def __init__(self, ob_dim, hid_sizes, probtype, activation="tanh", theta=None):
+        self._nlogstd = probtype.d if isinstance(probtype, DiagGauss) else 0
+        StochPolicyMLP.__init__(self, ob_dim, hid_sizes, probtype, activation, theta)
+
+    def set_params_flat(self, theta):
+        import numpy as np
+        theta = np.asarray(theta)
+        if theta.size == self.net.P - self._nlogstd:
+            theta = np.concatenate([theta.ravel(), np.zeros(self._nlogstd, theta.dtype)])
+        StochPolicyMLP.set_params_flat(self, theta)
+
+    def get_params_flat(self):
+        th = StochPolicyMLP.get_params_flat(self)
+        return th[:th.size - self._nlogstd] if self._nlogstd else th
+
+    def output_from_head(self, out):
+        return out          # the reference's prob row here is the bare net output (no ConcatFixedStd layer)
+
+    def act(self, ob, stochastic=False):
+        if stochastic:
+            raise ValueError("DeterministicPolicy has no sampling distribution; use set_stochastic(False)")
+        return StochPolicyMLP.act(self, ob, stochastic=False)
+
+    def act_batch(self, ob_no, stochastic=False):
+        if stochastic:
+            raise ValueError("DeterministicPolicy has no sampling distribution; use set_stochastic(False)")
+        return StochPolicyMLP.act_batch(self, ob_no, stochastic=False)
+
+
 def make_deterministic_mlp(ob_space, ac_space, cfg):
-    raise NotImplementedError("DeterministicAgent / CEM is outside the accelerated path (SURVEY 2.1 #16)")
+    """agentzoo.py:63-81 (hidden activation is tanh there regardless of --activation)."""
+    assert is_box(ob_space)
+    if is_box(ac_space):
+        probtype = DiagGauss(ac_space.shape[0])
+    elif is_discrete(ac_space):
+        probtype = Categorical(ac_space.n)
+    else:
+        raise NotImplementedError("action space %r" % (ac_space,))
+    return DeterministicPolicy(ob_space.shape[0], list(cfg["hid_sizes"]), probtype, "tanh")
 
 
 FILTER_OPTIONS = [
@@ -82,7 +128,11 @@ class DeterministicAgent(AgentWithPolicy):
     options = MLP_OPTIONS + FILTER_OPTIONS
 
     def __init__(self, ob_space, ac_space, usercfg):
-        make_deterministic_mlp(ob_space, ac_space, usercfg)
+        cfg = update_default_config(self.options, usercfg)
+        policy = make_deterministic_mlp(ob_space, ac_space, cfg)
+        obfilter, rewfilter = make_filters(cfg, ob_space)
+        AgentWithPolicy.__init__(self, policy, obfilter, rewfilter)
+        self.set_stochastic(False)
 
 
 class TrpoAgent(AgentWithPolicy):

@@ -445,7 +445,41 @@ def gen_vf(out):
     out["vf_grad"] = g
 
 
+def gen_cem(out):
+    """The reference's cem generator (cem.py:10-50), executed unmodified.  Its pool=None branch wraps a py2
+    `map` in np.array and cannot run on Python 3, so the population is evaluated through the `pool.map`
+    branch with an in-process stand-in for the pool."""
+    ns = dict(np=np)
+    exec(cut(os.path.join(REF, "cem.py"), ["cem"]), ns)
+
+    class Pool(object):
+        def map(self, f, xs):
+            return list(map(f, xs))
+
+    c = np.linspace(-2.0, 3.0, 7)
+    f = lambda th: -np.sum((th - c) ** 2) + 0.1 * np.sin(th).sum()
+    np.random.seed(77)
+    with quiet():
+        infos = list(ns["cem"](f, np.zeros(7, np.float32), 40, 6, 0.2, initial_std=1.5, extra_std=0.4,
+                               std_decay_time=3.0, pool=Pool()))
+    out["cem_center"] = c
+    out["cem_th"] = np.array([i["th"] for i in infos])
+    out["cem_ys"] = np.array([i["ys"] for i in infos])
+    out["cem_std"] = np.array([i["std"] for i in infos])
+    out["cem_ymean"] = np.array([i["ymean"] for i in infos])
+
+
+def main_cem():
+    out = OrderedDict()
+    gen_cem(out)
+    path = os.path.join(OUT, "cem_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+
+
 def main():
+    if sys.argv[1:] == ["cem"]:       # the CEM fixture lives in its own file (added after the main one)
+        return main_cem()
     mods = ref_package()
     out = OrderedDict()
     gen_discount(mods, out)

@@ -227,6 +227,61 @@ def test_agent_pickle_roundtrip(agent_name):
     np.testing.assert_array_equal(twin.policy.get_params_flat(), agent.policy.get_params_flat())
 
 
+@pytest.mark.parametrize("kind", ["box", "discrete"])
+def test_deterministic_agent_and_cem(kind):
+    """DeterministicAgent (agentzoo.py:63-81,117-123): linear-output MLP acted on through maxprob; its flat
+    vector has no logstd; run_cem_algorithm (cem.py:63-98) drives it and leaves the elite mean loaded."""
+    import pickle
+    from oracle import policy_math as pm
+    from modular_rl_b200 import agentzoo, spaces
+    from modular_rl_b200.cem import run_cem_algorithm
+    from modular_rl_b200.envs import make
+    rng = np.random.default_rng(3)
+    np.random.seed(3)
+    ob_space = spaces.Box(-np.ones(5), np.ones(5))
+    ac_space = spaces.Box(-np.ones(2), np.ones(2)) if kind == "box" else spaces.Discrete(3)
+    agent = agentzoo.DeterministicAgent(ob_space, ac_space, {"hid_sizes": [12, 6], "filter": 0})
+    dout = 2 if kind == "box" else 3
+    th = agent.get_flat()
+    assert th.size == 5 * 12 + 12 + 12 * 6 + 6 + 6 * dout + dout and agent.stochastic is False
+    th = (0.5 * rng.standard_normal(th.size)).astype(np.float32)
+    agent.set_from_flat(th)
+    np.testing.assert_array_equal(agent.get_flat(), th)
+    spec = pm.NetSpec((5, 12, 6, dout), pm.CAT)      # a head without logstd: the bare Dense stack
+    obs = rng.standard_normal((9, 5))
+    _, z = pm.forward(th.astype(np.float64), spec, obs)
+    for i in range(9):
+        a, info = agent.act(obs[i])
+        if kind == "box":
+            assert relerr(a, z[i]) < 1e-5 and info["prob"].shape == (2,)
+        else:
+            assert a == int(np.argmax(z[i]))
+    twin = pickle.loads(pickle.dumps(agent, -1))
+    np.testing.assert_array_equal(twin.get_flat(), th)
+    with pytest.raises(ValueError):
+        agent.policy.act(obs[0], stochastic=True)
+
+    env = make("Pendulum" if kind == "box" else "CartPole-v0")
+    agent = agentzoo.DeterministicAgent(env.observation_space, env.action_space, {"hid_sizes": [8]})
+    infos = []
+    np.random.seed(0)
+    run_cem_algorithm(env, agent, usercfg=dict(batch_size=24, n_iter=4, elite_frac=0.25, timestep_limit=100,
+                                               extra_std=0.01), callback=infos.append)
+    assert len(infos) == 4 and infos[0]["ys"].shape == (24,)
+    np.testing.assert_allclose(agent.get_flat(), infos[-1]["th"].astype(np.float32))
+    assert max(i["ymean"] for i in infos[1:]) > infos[0]["ymean"]
+
+
+def test_run_cem_cli():
+    cmd = [sys.executable, os.path.join(ROOT, "run_cem.py"), "--env=CartPole-v0",
+           "--agent=modular_rl.agentzoo.DeterministicAgent", "--n_iter=2", "--batch_size=10", "--hid_sizes=8",
+           "--snapshot_every=2", "--outfile", "/tmp/mrl_test_cem.h5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Iteration 1" in out.stdout and "ymean" in out.stdout
+    assert os.path.exists("/tmp/mrl_test_cem.h5.dir/agent_snapshots/0002.pkl")
+
+
 def test_multi_gpu_parity_two_ranks():
     """Sharded batch over 2 GPUs == full batch (skipped on a 1-GPU box; the CPU-side algebra is
     covered by tests/test_host_logic.py with gloo)."""

@@ -299,3 +299,22 @@ def test_snapshot_files_roundtrip(tmp_path):
     assert load_agent_snapshot(str(tmp_path), "0020").rs.n == 4
     with pytest.raises(ValueError):
         load_agent_snapshot(str(tmp_path), "0030")
+
+
+def test_cem_matches_reference_golden():
+    """modular_rl_b200.cem.cem against the vectors the reference's own generator produced
+    (tests/golden/make_golden.py cem): same numpy random stream, same elite selection, bit-exact."""
+    import contextlib
+    import io
+    from modular_rl_b200.cem import cem
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "cem_vectors.npz"))
+    c = G["cem_center"]
+    f = lambda th: -np.sum((th - c) ** 2) + 0.1 * np.sin(th).sum()
+    np.random.seed(77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        infos = list(cem(f, np.zeros(7, np.float32), 40, 6, 0.2, initial_std=1.5, extra_std=0.4, std_decay_time=3.0))
+    np.testing.assert_array_equal(np.array([i["ys"] for i in infos]), G["cem_ys"])
+    np.testing.assert_array_equal(np.array([i["th"] for i in infos]), G["cem_th"])
+    np.testing.assert_array_equal(np.array([i["std"] for i in infos]), G["cem_std"])
+    np.testing.assert_array_equal(np.array([i["ymean"] for i in infos]), G["cem_ymean"])
+    assert infos[-1]["ymean"] > infos[0]["ymean"]
