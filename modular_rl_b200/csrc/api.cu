@@ -640,11 +640,11 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   R(n->out32, P * 4); R(n->out64, P * 8); R(n->g32, P * 4);
   R(n->cg_b, P * 8); R(n->cg_x, P * 8); R(n->cg_r, P * 8); R(n->cg_p, P * 8);
   R(n->p32, P * 4); R(n->x32, P * 4); R(n->fullstep, P * 8);
-  R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8); R(n->cgscratch, 80 * 8);
+  R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8); R(n->cgscratch, CG_SCRATCH_DOUBLES * 8);
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_scal, 32 * 8);
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_cg, sizeof(CgState));
   if (e == cudaSuccess) e = cudaMemset(n->theta.p, 0, P * 4);
-  if (e == cudaSuccess) e = cudaMemset(n->cgscratch.p, 0, 80 * 8);
+  if (e == cudaSuccess) e = cudaMemset(n->cgscratch.p, 0, CG_SCRATCH_DOUBLES * 8);
   if (e != cudaSuccess) {
     mrl_net_destroy(n);
     return fail("mrl_net_create: %s", cudaGetErrorString(e));
@@ -1023,7 +1023,7 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
                       n->out64.as<double>(), st));
     CKP(PK_CG, launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
                        n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(),
-                       n->cgscratch.as<double>(), st), 3);
+                       n->cgscratch.as<double>(), st), 1);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
   RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),

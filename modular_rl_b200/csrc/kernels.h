@@ -86,8 +86,11 @@ struct CgState {   // device-resident scalars
 };
 cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* r, double* p, float* p32,
                            CgState* s, cudaStream_t st);
+#define CG_CTAS 32                              // co-resident CTAs of the CG iteration kernel
+#define CG_SCRATCH_DOUBLES (2 * CG_CTAS + 40)   // two partial-sum rows + the grid barrier words
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
-                           float* p32, CgState* s, double* scratch /* >= 72 doubles, zeroed once */, cudaStream_t st);
+                           float* p32, CgState* s, double* scratch /* CG_SCRATCH_DOUBLES, zeroed once */,
+                           cudaStream_t st);
 cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st);
 cudaError_t launch_cg_finish(int P, const float* z32, double damping, double max_kl, const float* g,
                              const double* x, double* fullstep, CgState* s, cudaStream_t st);

@@ -7,6 +7,8 @@
 // bit-identical to a loop that stopped.  dot products by warp shuffles, fp64.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
+#include <cooperative_groups.h>
 
 #define VEC_THREADS 1024
 
@@ -36,51 +38,69 @@ __global__ void __launch_bounds__(VEC_THREADS) cg_init_kernel(int P, const float
   }
 }
 
-// One CG iteration (trpo.py:179-193) as three small multi-CTA kernels.  A single CTA is bound by one
-// SM's L2 bandwidth (~30 us for the 44 484-parameter Humanoid vectors); CG_CTAS CTAs cut that to a few
-// microseconds each.  Dot products: per-CTA partials, then EVERY CTA sums the partials in the same fixed
-// order, so all CTAs (and all ranks) derive bit-identical alpha / beta without atomics.
+// One CG iteration (trpo.py:179-193), general P: ONE multi-CTA kernel with two grid barriers.  Dot products:
+// per-CTA partials, then EVERY CTA sums the partials in the same fixed order, so all CTAs (and all ranks)
+// derive bit-identical alpha / beta without atomics on the values.
 //   z32 = Fvp(p32) without damping (already all-reduced); A p = z + damping * p  (trpo.py:86-92)
-#define CG_CTAS 32
+// The barrier is a generation barrier (arrive counter + generation word on separate lines, zero-initialised
+// once, self-resetting).  Its cost grows with the CTA count (measured per iteration, Humanoid P = 44 484:
+// 8 CTAs 47 us, 16: 32, 32: 27, 64: 33, 128: 64), hence CG_CTAS = 32; the time is a chain of ~15 dependent L2
+// round trips, not bandwidth - the cluster kernel below removes most of them for the sizes that fit it.
+// 32 CTAs of 256 threads are always co-resident on a 148-SM part; a kernel of another stream holding SMs only
+// delays the stragglers' start, it cannot wait on this kernel.
 #define CG_THREADS 256
 
 __device__ __forceinline__ void cg_span(int P, int& lo, int& hi) {
-  const int per = (P + CG_CTAS - 1) / CG_CTAS;
+  const int per = (P + gridDim.x - 1) / gridDim.x;
   lo = blockIdx.x * per;
   hi = min(P, lo + per);
 }
-__device__ __forceinline__ double cg_sum_parts(const double* __restrict__ parts) {
+__device__ __forceinline__ double cg_sum_parts(const double* parts) {
   double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < CG_CTAS; ++i) s += parts[i];
+#pragma unroll 8
+  for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(parts + i);   // written by other CTAs of this launch: L2, not L1
   return s;
 }
+__device__ __forceinline__ void cg_grid_barrier(unsigned int* arrive, unsigned int* gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int g = *reinterpret_cast<volatile unsigned int*>(gen);   // cannot advance before this CTA arrives
+    __threadfence();
+    if (atomicAdd(arrive, 1u) == gridDim.x - 1) {
+      *reinterpret_cast<volatile unsigned int*>(arrive) = 0u;
+      __threadfence();
+      atomicAdd(gen, 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned int*>(gen) == g) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 
-__global__ void __launch_bounds__(CG_THREADS) cg_dot_pz_kernel(int P, const float* __restrict__ z32, double damping,
-                                                               const double* __restrict__ p, const CgState* s,
-                                                               double* __restrict__ parts) {
+__global__ void __launch_bounds__(CG_THREADS) cg_step_kernel(int P, const float* __restrict__ z32, double damping,
+                                                             double tol, double* __restrict__ x,
+                                                             double* __restrict__ r, double* __restrict__ p,
+                                                             float* __restrict__ p32, CgState* s,
+                                                             double* parts_pz, double* parts_rr,
+                                                             unsigned int* arrive, unsigned int* gen) {
   __shared__ double scratch[32];
-  if (s->done) return;
+  if (s->done) return;                 // uniform over the grid: nobody enters a barrier
+  const double rdotr = s->rdotr;       // the state is rewritten only after the second barrier
   int lo, hi;
   cg_span(P, lo, hi);
+  // z = A p; v = rdotr / (p.z)
   double pz = 0.0;
   for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pi = p[i];
     pz += pi * ((double)z32[i] + damping * pi);
   }
   pz = block_sum(pz, scratch);
-  if (threadIdx.x == 0) parts[blockIdx.x] = pz;
-}
-__global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int P, const float* __restrict__ z32, double damping,
-                                                                  double* __restrict__ x, double* __restrict__ r,
-                                                                  const double* __restrict__ p, const CgState* s,
-                                                                  const double* __restrict__ parts_pz,
-                                                                  double* __restrict__ parts_rr) {
-  __shared__ double scratch[32];
-  if (s->done) return;
-  const double alpha = s->rdotr / cg_sum_parts(parts_pz);
-  int lo, hi;
-  cg_span(P, lo, hi);
+  if (threadIdx.x == 0) parts_pz[blockIdx.x] = pz;
+  cg_grid_barrier(arrive, gen);
+  pz = cg_sum_parts(parts_pz);
+  const double alpha = rdotr / pz;
+  // x += v p; r -= v z; newrdotr = r.r
   double nr = 0.0;
   for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pi = p[i];
@@ -90,36 +110,108 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int P, const f
     r[i] = ri;
     nr += ri * ri;
   }
+  __syncthreads();                     // scratch is reused
   nr = block_sum(nr, scratch);
   if (threadIdx.x == 0) parts_rr[blockIdx.x] = nr;
-}
-// p = r + (newrdotr/rdotr) p ; the scalar state is advanced by the LAST CTA to finish reading it
-__global__ void __launch_bounds__(CG_THREADS) cg_update_p_kernel(int P, double tol, const double* __restrict__ r,
-                                                                 double* __restrict__ p, float* __restrict__ p32,
-                                                                 CgState* s, const double* __restrict__ parts_pz,
-                                                                 const double* __restrict__ parts_rr,
-                                                                 unsigned int* __restrict__ ticket) {
-  if (s->done) return;
-  const double rdotr = s->rdotr;
-  const double pz = cg_sum_parts(parts_pz), nr = cg_sum_parts(parts_rr);
+  cg_grid_barrier(arrive, gen);
+  nr = cg_sum_parts(parts_rr);
+  // p = r + (newrdotr / rdotr) p   (each thread re-reads the r entries it wrote itself)
   const double beta = nr / rdotr;
-  int lo, hi;
-  cg_span(P, lo, hi);
   for (int i = lo + threadIdx.x; i < hi; i += CG_THREADS) {
     const double pn = r[i] + beta * p[i];
     p[i] = pn;
     p32[i] = (float)pn;
   }
-  __syncthreads();   // every thread of this CTA has read s->rdotr / s->done
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // every CTA read the state before the first barrier
+    s->pz = pz; s->alpha = alpha; s->beta = beta; s->rdotr = nr;
+    s->iters += 1;
+    if (nr < tol) s->done = 1;
+  }
+}
+
+// The same iteration for P <= CGC_CTAS * CGC_THREADS * CGC_K as ONE thread-block cluster: every vector element
+// lives in a register of one thread for the whole iteration, the two dot products are exchanged through
+// distributed shared memory and the cluster's hardware barrier, so the dependent global-memory round trips of
+// the grid-barrier version (~15 of them, 17-27 us) shrink to one load and one store wave (measured 11.6 us
+// for Hopper's P = 5 126 and 16.9 us for Humanoid's 44 484, against 17.1 and 27.3).
+#define CGC_CTAS 8
+#define CGC_THREADS 1024
+#define CGC_K 6
+namespace cgx = cooperative_groups;
+
+__device__ __forceinline__ double cgc_cluster_sum(cgx::cluster_group& cl, double v, double* wsum, double* slot,
+                                                  double* tot) {
+  // block sum (fixed order) -> this CTA's slot -> every CTA adds the CGC_CTAS slots in rank order
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = wsum[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *slot = t;
+  }
+  cl.sync();
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(ticket, 1u) == CG_CTAS - 1) {   // all CTAs are past their reads of the state
-      *ticket = 0;
-      s->pz = pz; s->alpha = rdotr / pz; s->beta = beta; s->rdotr = nr;
-      s->iters += 1;
-      if (nr < tol) s->done = 1;
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < CGC_CTAS; ++j) a += *cl.map_shared_rank(slot, j);
+    *tot = a;
+  }
+  __syncthreads();
+  return *tot;
+}
+
+__global__ void __cluster_dims__(CGC_CTAS, 1, 1) __launch_bounds__(CGC_THREADS)
+cg_step_cluster_kernel(int P, const float* __restrict__ z32, double damping, double tol, double* __restrict__ x,
+                       double* __restrict__ r, double* __restrict__ p, float* __restrict__ p32, CgState* s) {
+  cgx::cluster_group cl = cgx::this_cluster();
+  __shared__ double wsum[32];
+  __shared__ double slots[2], tots[2];
+  if (s->done) return;                 // uniform over the cluster
+  const double rdotr = s->rdotr;
+  const int t0 = (int)cl.block_rank() * CGC_THREADS + threadIdx.x;
+  double pi[CGC_K], ri[CGC_K];
+  float zf[CGC_K];
+#pragma unroll
+  for (int k = 0; k < CGC_K; ++k) {
+    const int i = t0 + k * (CGC_CTAS * CGC_THREADS);
+    const bool in = i < P;
+    pi[k] = in ? p[i] : 0.0;
+    zf[k] = in ? z32[i] : 0.f;
+    ri[k] = in ? r[i] : 0.0;
+  }
+  double pz = 0.0;
+#pragma unroll
+  for (int k = 0; k < CGC_K; ++k) {
+    pz += pi[k] * ((double)zf[k] + damping * pi[k]);          // z = A p  (trpo.py:86-92)
+  }
+  pz = cgc_cluster_sum(cl, pz, wsum, &slots[0], &tots[0]);
+  const double alpha = rdotr / pz;
+  double nr = 0.0;
+#pragma unroll
+  for (int k = 0; k < CGC_K; ++k) {
+    const int i = t0 + k * (CGC_CTAS * CGC_THREADS);
+    if (i < P) x[i] += alpha * pi[k];          // in flight during the second reduction
+    ri[k] -= alpha * ((double)zf[k] + damping * pi[k]);
+    nr += ri[k] * ri[k];
+  }
+  nr = cgc_cluster_sum(cl, nr, wsum, &slots[1], &tots[1]);
+  const double beta = nr / rdotr;
+#pragma unroll
+  for (int k = 0; k < CGC_K; ++k) {
+    const int i = t0 + k * (CGC_CTAS * CGC_THREADS);
+    if (i < P) {
+      const double pn = ri[k] + beta * pi[k];
+      r[i] = ri[k]; p[i] = pn;
+      p32[i] = (float)pn;
     }
   }
+  if (cl.block_rank() == 0 && threadIdx.x == 0) {
+    s->pz = pz; s->alpha = alpha; s->beta = beta; s->rdotr = nr;
+    s->iters += 1;
+    if (nr < tol) s->done = 1;
+  }
+  cl.sync();                           // no CTA leaves while a peer may still read its slots
 }
 
 __global__ void cast_f64_f32_kernel(int P, const double* __restrict__ x, float* __restrict__ x32) {
@@ -180,13 +272,17 @@ cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* 
 }
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
                            float* p32, CgState* s, double* scratch, cudaStream_t st) {
-  // scratch: [CG_CTAS] pz partials, [CG_CTAS] rr partials, then one uint32 ticket (zero-initialised by the caller)
+  // scratch: [CG_CTAS] pz partials, [CG_CTAS] rr partials, then the barrier's arrive counter and generation
+  // word (zero-initialised once by the caller; the barrier leaves arrive at 0)
   double* parts_pz = scratch;
   double* parts_rr = scratch + CG_CTAS;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 2 * CG_CTAS);
-  cg_dot_pz_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, p, s, parts_pz);
-  cg_update_xr_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, x, r, p, s, parts_pz, parts_rr);
-  cg_update_p_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, tol, r, p, p32, s, parts_pz, parts_rr, ticket);
+  unsigned int* bar = reinterpret_cast<unsigned int*>(scratch + 2 * CG_CTAS);   // arrive and generation on separate lines
+  // MRL_CG_GRID=1 forces the grid-barrier kernel (the path of P > 49 152), so the tests can cover it on small nets
+  if (P <= CGC_CTAS * CGC_THREADS * CGC_K && !getenv("MRL_CG_GRID")) {
+    cg_step_cluster_kernel<<<CGC_CTAS, CGC_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s);
+    return cudaGetLastError();
+  }
+  cg_step_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s, parts_pz, parts_rr, bar, bar + 32);
   return cudaGetLastError();
 }
 cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st) {

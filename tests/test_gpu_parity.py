@@ -101,6 +101,28 @@ def test_golden_trpo_step(dev, golden, tag, cfg):
     assert np.allclose(stats[1::2], golden[key + "after"], rtol=(5e-2 if cfg == "d" else 1e-4), atol=1e-6)
 
 
+def test_cg_iteration_kernels_agree(dev, golden, monkeypatch):
+    """The CG iteration has two kernels: one thread-block cluster with the vectors in registers (P <= 49 152) and
+    the grid-barrier kernel for longer vectors.  MRL_CG_GRID=1 forces the second on a small net: same iteration
+    count and the same step to fp64 rounding of the partial-sum grouping."""
+    spec, head, th, ob, act, adv, oldp = _golden_case(golden, "tg")
+    damping, max_kl = golden["tg_b_cfg"]
+    res = []
+    for force_grid in (False, True):
+        if force_grid:
+            monkeypatch.setenv("MRL_CG_GRID", "1")
+        net, batch = _bind(dev, spec.dims, head, ob, act, adv, oldp, th)
+        for _ in range(2):                      # twice: the barrier words must come back to their rest state
+            net.set_params(th)
+            stats, info = net.trpo_step(batch, cg_damping=damping, max_kl=max_kl)
+        res.append((np.array(stats), info, net.trpo_vectors()[0].copy(), net.get_params().copy()))
+    monkeypatch.delenv("MRL_CG_GRID")
+    (s0, i0, d0, t0), (s1, i1, d1, t1) = res
+    assert i0["cg_iters_run"] == i1["cg_iters_run"] and i0["success"] == i1["success"]
+    assert relerr(d1, d0) < 1e-9 and relerr(t1, t0) < 1e-6
+    assert np.allclose(s0, s1, rtol=1e-6, atol=1e-9)
+
+
 SHAPES = {
     "hopper": ((11, 64, 64, 3), 0, 5000),
     "humanoid": ((376, 100, 50, 25, 17), 0, 3001),
