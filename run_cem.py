@@ -32,6 +32,8 @@ def main():
     args, _ = parser.parse_known_args([arg for arg in sys.argv[1:] if arg not in ('-h', '--help')])
     env = make(args.env)
     env_spec = env.spec
+    # read the snapshot before the results directory of a previous run (which may hold it) is cleared
+    snapshot_agent = load_agent_snapshot(args.load_snapshot) if args.load_snapshot else None
     mondir = args.outfile + ".dir"
     if os.path.exists(mondir):
         shutil.rmtree(mondir)
@@ -44,8 +46,7 @@ def main():
         args.timestep_limit = env_spec.max_episode_steps
     cfg = args.__dict__
     np.random.seed(args.seed)
-    agent = load_agent_snapshot(args.load_snapshot) if args.load_snapshot else \
-        agent_ctor(env.observation_space, env.action_space, cfg)
+    agent = snapshot_agent if args.load_snapshot else agent_ctor(env.observation_space, env.action_space, cfg)
     if args.use_hdf:
         hdf, diagnostics = prepare_h5_file(args)
 

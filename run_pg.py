@@ -32,6 +32,8 @@ def main():
     args, _ = parser.parse_known_args([arg for arg in sys.argv[1:] if arg not in ('-h', '--help')])
     env = make(args.env)
     env_spec = env.spec
+    # read the snapshot before the results directory of a previous run (which may hold it) is cleared
+    snapshot_agent = load_agent_snapshot(args.load_snapshot) if args.load_snapshot else None
     mondir = args.outfile + ".dir"
     if os.path.exists(mondir):
         shutil.rmtree(mondir)
@@ -46,7 +48,7 @@ def main():
     if args.load_snapshot:
         # the reference declares the flag (misc_utils.py:102) without reading it; here it resumes from a
         # pickled agent (.pkl / directory written below, or an hdf5 results file as sim_agent.py:41-52 reads)
-        agent = load_agent_snapshot(args.load_snapshot)
+        agent = snapshot_agent
         assert isinstance(agent, agent_ctor), "snapshot holds a %s" % type(agent).__name__
     else:
         agent = agent_ctor(env.observation_space, env.action_space, cfg)

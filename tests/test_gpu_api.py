@@ -168,8 +168,8 @@ def test_coverage_smoke_pendulum():
     from modular_rl_b200.misc_utils import load_agent_snapshot
     agent = load_agent_snapshot(snap)
     assert type(agent).__name__ == "TrpoAgent" and agent.policy.dims == [3, 10, 5, 1]
-    os.rename(snap, "/tmp/mrl_test_snapshot.pkl")
-    out = subprocess.run(cmd + ["--load_snapshot", "/tmp/mrl_test_snapshot.pkl"], capture_output=True, text=True,
+    # same --outfile: the snapshot is read before the previous run's results directory is cleared
+    out = subprocess.run(cmd + ["--load_snapshot", "/tmp/mrl_test_b.h5.dir"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "pol_surr_after" in out.stdout
