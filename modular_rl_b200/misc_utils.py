@@ -129,16 +129,35 @@ def prepare_h5_file(args):
     return hdf, diagnostics
 
 
-def save_agent_snapshot(agent, dirname, counter):
+def save_agent_snapshot(agent, dirname, counter, env_id=None):
     """Pickled agent written as <dirname>/agent_snapshots/<%04i>.pkl - the same bytes run_pg.py:141-142
-    stores under /agent_snapshots/%0.4i of the hdf5 file, for boxes without h5py."""
+    stores under /agent_snapshots/%0.4i of the hdf5 file, for boxes without h5py.  env_id (run_pg.py:147's
+    hdf['env_id']) goes to <dirname>/env_id.txt for sim_agent.py."""
     import pickle
     d = osp.join(dirname, "agent_snapshots")
     os.makedirs(d, exist_ok=True)
+    if env_id is not None:
+        with open(osp.join(dirname, "env_id.txt"), "w") as f:
+            f.write(str(env_id))
     fname = osp.join(d, "%0.4i.pkl" % counter)
     with open(fname, "wb") as f:
         f.write(pickle.dumps(agent, -1))
     return fname
+
+
+def snapshot_env_id(path):
+    """The environment id stored next to the snapshots (hdf['env_id'], sim_agent.py:50), or None."""
+    if osp.isdir(path) or path.endswith(".pkl"):
+        d = path if osp.isdir(path) else osp.dirname(path)
+        for cand in (d, osp.dirname(d.rstrip("/"))):
+            f = osp.join(cand, "env_id.txt")
+            if osp.exists(f):
+                return open(f).read().strip()
+        return None
+    import h5py  # optional dependency
+    with h5py.File(path, "r") as hdf:
+        v = hdf["env_id"][()]
+        return v.decode() if isinstance(v, bytes) else str(v)
 
 
 def load_agent_snapshot(path, snapname=None):

@@ -66,7 +66,7 @@ def main():
             if args.use_hdf:
                 hdf['/agent_snapshots/%0.4i' % counter[0]] = np.array(pickle.dumps(agent, -1))
             else:
-                save_agent_snapshot(agent, mondir, counter[0])
+                save_agent_snapshot(agent, mondir, counter[0], env_id=env_spec.id)
 
     run_cem_algorithm(env, agent, callback=callback, usercfg=cfg)
 

@@ -71,7 +71,7 @@ def main():
             if args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
                 hdf['/agent_snapshots/%0.4i' % counter[0]] = np.array(pickle.dumps(agent, -1))
         elif args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
-            save_agent_snapshot(agent, mondir, counter[0])      # same bytes, one file per snapshot
+            save_agent_snapshot(agent, mondir, counter[0], env_id=env_spec.id)      # same bytes, one file per snapshot
         if args.plot:
             animate_rollout(env, agent, min(500, args.timestep_limit))
 

@@ -318,3 +318,30 @@ def test_cem_matches_reference_golden():
     np.testing.assert_array_equal(np.array([i["std"] for i in infos]), G["cem_std"])
     np.testing.assert_array_equal(np.array([i["ymean"] for i in infos]), G["cem_ymean"])
     assert infos[-1]["ymean"] > infos[0]["ymean"]
+
+
+class _PushLeftRightAgent(object):
+    """Stand-in agent for the sim_agent test: picklable, no device."""
+    stochastic = True
+
+    def obfilt(self, ob):
+        return ob
+
+    def act(self, ob):
+        return int(ob[2] > 0), {}          # push towards the side the pole leans to
+
+
+def test_sim_agent_replays_snapshot(tmp_path, capsys):
+    """sim_agent.py: snapshot directory + stored environment id -> deterministic replays with reward totals."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import sim_agent
+    from modular_rl_b200.misc_utils import save_agent_snapshot, snapshot_env_id
+    save_agent_snapshot(_PushLeftRightAgent(), str(tmp_path), 7, env_id="CartPole-v0")
+    assert snapshot_env_id(str(tmp_path)) == "CartPole-v0"
+    assert snapshot_env_id(str(tmp_path / "agent_snapshots" / "0007.pkl")) == "CartPole-v0"
+    np.random.seed(0)
+    totals = sim_agent.main([str(tmp_path), "--episodes", "2", "--delay", "0", "--timestep_limit", "60"])
+    assert len(totals) == 2 and all(t > 5 for t in totals)
+    assert "reward:" in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        sim_agent.main([str(tmp_path), "--snapname", "0001", "--episodes", "1", "--delay", "0"])
