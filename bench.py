@@ -25,6 +25,14 @@ import sys
 import threading
 import time
 
+HOST_CORES = len(os.sched_getaffinity(0))
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank.  The CPU legs of this file (the reference arm and
+# rank 0's oracle checks) run while the other ranks idle, so they get the box's cores back - set BEFORE numpy loads
+# its BLAS; the thread count actually in use is read back with threadpoolctl and reported.
+if int(os.environ.get("RANK", "0")) == 0:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(HOST_CORES)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -43,7 +51,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="humanoid")
     ap.add_argument("--timesteps", type=int, default=0, help="total timesteps (default: the workload's)")
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="timesteps of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="timesteps of the CPU baseline sample (b200 arm)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget of the K+W sampled steps")
+    ap.add_argument("--verify", default="quick", choices=["none", "quick", "full"],
+                    help="parity legs outside the timed region, on the FULL batch against the fp64 oracle: "
+                         "quick = losses, gradient, one Fvp, advantages; full = + the oracle's whole update (step direction, stats)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--nccl-only", action="store_true", help="sum over ranks with NCCL instead of the NVLink peer-memory push")
@@ -58,42 +70,85 @@ def workload_desc(wl, n_total):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_update_rate(wl, n_sample, steps, warmup):
-    """The oracle port of the reference's CPU path (float32 = the fork's floatX), timed on this box's
-    host cores with all BLAS threads: GAE (scipy lfilter per path, as the reference) + one TRPO update."""
-    from modular_rl_b200 import synth
-    from oracle import advantage as oadv, natgrad, policy_math as pm
-    spec = pm.NetSpec(wl.dims, pm.GAUSS if wl.head == 0 else pm.CAT)
+def blas_threads():
+    """BLAS threads numpy really uses (threadpoolctl), not the affinity mask."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(i.get("num_threads", 0)) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else None
+    except Exception:
+        return None
 
-    def fwd(th, ob):
-        _, z = pm.forward(th, spec, ob, np.float32)
-        return z if wl.head == 0 else pm.softmax(z)
-    data = synth.policy_batch(wl, fwd, N=n_sample)
-    base = np.tanh(data["ob"][:, 0]).astype(np.float32)
-    times = []
-    for i in range(warmup + steps):
+
+class CpuArm:
+    """The oracle port of the reference's CPU path (float32 = the fork's floatX), timed on this box's host cores with
+    all BLAS threads: GAE (scipy lfilter per path, as the reference) + one TRPO update (1 gradient, 10 CG
+    Fisher-vector products + 1, line search).  The Fvp is the oracle's CLOSED FORM (forward + R-forward + reverse
+    sweep), which does less arithmetic than the reverse-over-reverse graph Theano differentiates: the port is a
+    conservative (fast) stand-in for the reference."""
+
+    def __init__(self, wl, n_max):
+        from modular_rl_b200 import synth
+        from oracle import policy_math as pm
+        self.wl, self.pm = wl, pm
+        self.spec = pm.NetSpec(wl.dims, pm.GAUSS if wl.head == 0 else pm.CAT)
+
+        def fwd(th, ob):
+            _, z = pm.forward(th, self.spec, ob, np.float32)
+            return z if wl.head == 0 else pm.softmax(z)
+        self.data = synth.policy_batch(wl, fwd, N=n_max)
+        self.base = np.tanh(self.data["ob"][:, 0]).astype(np.float32)
+        self.n_max = n_max
+
+    def step(self, n):
+        """one update on the first n timesteps (whole trajectories are not needed by the arithmetic) -> seconds"""
+        from oracle import advantage as oadv, natgrad
+        d = self.data
+        k = int(np.searchsorted(d["offsets"], n, side="right"))
+        off = np.concatenate([d["offsets"][:k], [n]]) if d["offsets"][k - 1] != n else d["offsets"][:k]
+        term = d["terminated"][:len(off) - 1]
         t0 = time.perf_counter()
-        ret, adv = oadv.gae_flat(data["reward"], base, data["offsets"], data["terminated"], CFG["gamma"], CFG["lam"])
+        ret, adv = oadv.gae_flat(d["reward"][:n], self.base[:n], off, term, CFG["gamma"], CFG["lam"])
         adv = oadv.standardize(adv).astype(np.float32)
-        natgrad.trpo_update(data["theta"], spec, data["ob"], data["act"], adv, data["oldprob"],
+        natgrad.trpo_update(d["theta"], self.spec, d["ob"][:n], d["act"][:n], adv, d["oldprob"][:n],
                             CFG["cg_damping"], CFG["max_kl"], dtype=np.float32)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+
+def cpu_update_rate(wl, n_sample, steps, warmup):
+    arm = CpuArm(wl, n_sample)
+    times = [arm.step(n_sample) for _ in range(warmup + steps)][warmup:]
     return n_sample * len(times) / sum(times), float(np.mean(times))
 
 
 def run_reference(args, wl, n_total, rank, world):
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    n_sample = min(args.cpu_sample, n_total)
-    rate, sec = cpu_update_rate(wl, n_sample, args.steps, args.warmup)
-    sample = f"{n_sample} of {n_total} timesteps per step, oracle port (numpy float32 + scipy lfilter), {cores} BLAS threads"
+    arm = CpuArm(wl, n_total)
+    threads = blas_threads()
+    # sample size: one calibration step, then the largest sample whose K+W steps fit the budget; one step on the FULL
+    # batch shows that the rate does not depend on the sample size
+    n_cal = min(n_total, 50_000)
+    sec_cal = arm.step(n_cal)
+    rates = {n_cal: n_cal / sec_cal}
+    reps = args.steps + args.warmup
+    n_sample = int(min(n_total, max(n_cal, rates[n_cal] * args.ref_budget_s / max(reps, 1))))
+    if n_sample < n_total:
+        rates[n_total] = n_total / arm.step(n_total)
+    times = [arm.step(n_sample) for _ in range(reps)][args.warmup:]
+    rate, sec = n_sample * len(times) / sum(times), float(np.mean(times))
+    rates[n_sample] = rate
+    sample = (f"{n_sample} of {n_total} timesteps per step (sample_fraction {n_sample / n_total:.3f}), oracle port "
+              f"(numpy float32, closed-form Fvp, scipy lfilter per path), {threads} BLAS threads on {HOST_CORES} cores; "
+              "rate by sample size: " + ", ".join(f"{n}: {r:.0f}/s" for n, r in sorted(rates.items())))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * n_total / n_sample,
+            "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(wl, n_total), "parallelism": "cpu", **CFG},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_desc(wl, n_total), "timesteps": n_total, "sample_timesteps": n_sample,
+                       "sample_fraction": n_sample / n_total, "parallelism": "cpu", **CFG},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads or HOST_CORES, "kind": "port", "sample": sample,
+                             "rate_by_sample": {str(k): v for k, v in sorted(rates.items())}},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -160,6 +215,89 @@ def algorithmic_flops_per_timestep(dims):
     return {"l1_forward": 2 * d0d1, "l1_grad": 2 * d0d1, "mid_forward": 2 * S, "mid_backward_grad": 4 * S,
             "mid_backward_fvp": 8 * S}
 
+# ----------------------------------------------------------------------------- parity on the full batch
+def run_parity(args, wl, n_total, rank, world, dist, dev, net, vf, batch, comm, reward_d, theta_d, rows, glob, stats_timed):
+    """Outside the timed region: the CUDA path on the FULL bench batch against the float64 oracle (rank 0 holds the
+    global host arrays; every rank takes part in the device calls).  Returns the measured relative errors."""
+    if args.verify == "none":
+        return None
+    import torch
+    from modular_rl_b200 import synth
+    vf.predict_into_baseline(batch)
+    ret_d, adv_d = batch.gae(reward_d, None, CFG["gamma"], CFG["lam"], True, comm)
+    batch.refresh_advantages()
+    net.set_params(theta_d)
+    ls = net.losses(batch)
+    g, _ = net.policy_gradient(batch)
+    v = np.random.default_rng(12345).standard_normal(net.P).astype(np.float32)
+    f = net.fvp(batch, v)
+    full = None
+    if args.verify == "full":
+        st, info = net.trpo_step(batch, CFG["cg_damping"], CFG["max_kl"])
+        sd, fs, sc = net.trpo_vectors()
+        full = (np.array(st), info, sd, fs, net.get_params())
+    # replicated parameters must be bit-identical on every rank
+    th = torch.from_numpy(net.get_params().view(np.int32).astype(np.int64)).to(dev)
+    chk = torch.stack([th.sum(), (th * torch.arange(1, th.numel() + 1, device=dev)).sum()])
+    identical = True
+    if world > 1:
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(bool((c == allc[0]).all()) for c in allc)
+    if rank != 0:
+        return None
+    from oracle import advantage as oadv, natgrad, policy_math as pm
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    t0 = time.perf_counter()
+    spec = pm.NetSpec(wl.dims, pm.GAUSS if wl.head == 0 else pm.CAT)
+    r0, r1 = rows
+    oret, oad = oadv.gae_flat(glob["reward"], glob["base"].astype(np.float64), glob["off"], glob["term"], CFG["gamma"], CFG["lam"])
+    oads = oadv.standardize(oad)
+    adv32 = oads.astype(np.float32)
+    a = (glob["ob"], glob["act"], adv32, glob["oldprob"])
+    th = glob["theta"]
+    ols = pm.losses(th, spec, *a)
+    og = pm.policy_gradient(th, spec, *a)
+    of = pm.fisher_vector_product(th, spec, glob["ob"], v)
+    og32 = pm.policy_gradient(th, spec, *a, dtype=np.float32)
+    of32 = pm.fisher_vector_product(th, spec, glob["ob"], v, dtype=np.float32)
+    out = {"timesteps": n_total, "oracle": "float64 numpy restatement (oracle/policy_math.py, oracle/advantage.py) on the full batch",
+           "tolerance": 1e-5,
+           "losses_rel": [float(abs(x - y) / max(abs(y), 1e-12)) for x, y in zip(ls, ols)],
+           "losses_abs": [float(abs(x - y)) for x, y in zip(ls, ols)],
+           "grad_rel_l2": rel(g, og), "fvp_rel_l2": rel(f, of),
+           "returns_rel_l2": rel(ret_d.cpu().numpy(), oret[r0:r1]),
+           "advantages_max_abs": float(np.max(np.abs(adv_d.cpu().numpy() - oads[r0:r1]))),
+           "reference_fp32_noise_floor": {"grad_rel_l2": rel(og32, og), "fvp_rel_l2": rel(of32, of),
+                                          "what": "the oracle run in float32 (the fork's floatX) against float64"},
+           "theta_identical_across_ranks": identical}
+    if full is not None:
+        st, info, sd, fs, thn = full
+        ostats, oinfo = natgrad.trpo_update(th, spec, *a, CFG["cg_damping"], CFG["max_kl"])
+        want = np.array([ostats[k] for k in ("surr_before", "surr_after", "kl_before", "kl_after", "ent_before", "ent_after")])
+        out.update(stepdir_rel_l2=rel(sd, oinfo["stepdir"]), fullstep_rel_l2=rel(fs, oinfo["fullstep"]),
+                   theta_new_rel_l2=rel(thn, oinfo["theta_new"]),
+                   stats_rel=[float(abs(x - y) / max(abs(y), 1e-12)) for x, y in zip(st, want)],
+                   kl_after_rel=float(abs(st[3] - want[3]) / abs(want[3])),
+                   accepted_index=[int(info["accepted_index"]), int(oinfo["accepted_index"])],
+                   cg_iters=[int(info["cg_iters_run"]), int(oinfo["cg_iters_run"])])
+    # the same global batch at every N: the timed update's statistics against the committed 1-GPU record
+    ref_path = os.path.join(ROOT, "profiles", "n1_stats_%s_%d.json" % (wl.name, n_total))
+    if world == 1 and os.environ.get("MRL_WRITE_N1_STATS"):
+        json.dump({"workload": wl.name, "timesteps": n_total, "cfg": CFG, "stats": [float(x) for x in stats_timed]},
+                  open(ref_path, "w"))
+    try:
+        n1 = json.load(open(ref_path))
+        if n1["cfg"] == CFG:
+            out["stats_vs_1gpu_record_max_rel"] = float(max(abs(x - y) / max(abs(y), 1e-12) for x, y in zip(stats_timed, n1["stats"])))
+    except Exception:
+        pass
+    out["oracle_seconds"] = time.perf_counter() - t0
+    ok = (max(out["grad_rel_l2"], out["fvp_rel_l2"]) < 1e-5 and out["advantages_max_abs"] < 1e-5 and identical and
+          all(r < 1e-5 or d < 2e-7 for r, d in zip(out["losses_rel"], out["losses_abs"])))
+    out["pass"] = bool(ok)
+    return out
+
 
 def main():
     args = parse()
@@ -183,20 +321,50 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
 
-    # ---- this rank's shard of the synthetic batch (strong scaling: n_total is fixed)
-    n_local = n_total // world + (1 if rank < n_total % world else 0)
-    rng = np.random.default_rng(wl.seed * 1000 + rank)
+    # ---- ONE global synthetic batch for every N (seeded once), sharded by WHOLE trajectories (parallel.shard_bounds):
+    # the update statistics of the N = 1, 2, 4, 8 runs are then directly comparable (strong scaling: n_total is fixed)
+    from modular_rl_b200.parallel import shard_bounds
+    d0, dout = wl.dims[0], wl.dims[-1]
+    grng = np.random.default_rng(wl.seed)
     theta = synth.init_params(wl.dims, wl.head, np.random.default_rng(wl.seed))
-    vdims = (wl.dims[0] + 1,) + tuple(wl.dims[1:-1]) + (1,)
+    vdims = (d0 + 1,) + tuple(wl.dims[1:-1]) + (1,)
     vtheta = synth.init_params(vdims, synth.VALUE, np.random.default_rng(wl.seed + 1), last_scale=1.0)
-    pin = lambda a: torch.from_numpy(a).pin_memory()
-    ob_h = pin(synth.make_obs(n_local, wl.dims[0], rng))
-    offsets, terminated = synth.make_paths(n_local, wl.t_max, rng)
-    reward_h = pin(rng.standard_normal(n_local))
+    ob_g = synth.make_obs(n_total, d0, grng)
+    off_g, term_g = synth.make_paths(n_total, wl.t_max, grng)
+    reward_g = grng.standard_normal(n_total)
+    noise_g = (grng.standard_normal((n_total, dout), dtype=np.float32) if wl.head == synth.GAUSS
+               else grng.random((n_total, 1), dtype=np.float32))
+    pa, pb = shard_bounds(np.diff(off_g), world)[rank]
+    r0, r1 = int(off_g[pa]), int(off_g[pb])
+    n_local = r1 - r0
+    offsets = (off_g[pa:pb + 1] - off_g[pa]).astype(np.int64)
+    terminated = np.ascontiguousarray(term_g[pa:pb])
 
     net = DeviceNet(wl.dims, wl.head, device=local_rank)
     vf = DeviceNet(vdims, synth.VALUE, device=local_rank)
-    batch = DeviceBatch(wl.dims[0], True, device=local_rank)
+    net.set_params(theta)
+    vf.set_params(vtheta)
+    # the policy's own output on the global batch = path["prob"]; every rank computes it so that all N see the same rows
+    tmp = DeviceBatch(d0, True, device=local_rank)
+    tmp.set_obs(ob_g).set_paths(off_g, term_g, float(wl.t_max))
+    out_g = net.forward(tmp)
+    base_g = vf.forward(tmp)[:, 0].copy() if (rank == 0 and args.verify != "none") else None
+    tmp.close()
+    del tmp
+    if wl.head == synth.GAUSS:
+        oldprob_g = np.concatenate([out_g, np.broadcast_to(np.exp(theta[-dout:])[None], out_g.shape)], 1).astype(np.float32)
+        act_g = (noise_g * oldprob_g[:, dout:] + oldprob_g[:, :dout]).astype(np.float32)     # DiagGauss.sample, core.py:432-435
+    else:
+        oldprob_g = out_g
+        act_g = np.argmax(np.cumsum(oldprob_g, axis=1) > noise_g, axis=1).astype(np.int32)   # distributions.py:3-13
+    del out_g, noise_g
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    ob_h, reward_h = pin(ob_g[r0:r1]), pin(reward_g[r0:r1])
+    act_h, oldprob_h = pin(act_g[r0:r1]), pin(oldprob_g[r0:r1])
+    if not (rank == 0 and args.verify != "none"):
+        del ob_g, act_g, oldprob_g, reward_g            # only rank 0 keeps the global arrays (oracle legs)
+
+    batch = DeviceBatch(d0, True, device=local_rank)
     comm = None
     if world > 1:
         from modular_rl_b200.parallel import comm_from_torch_distributed
@@ -204,23 +372,11 @@ def main():
         net.set_comm(comm)
     batch.set_obs(ob_h.numpy()).set_paths(offsets, terminated, float(wl.t_max))
     batch.set_global_n(n_total)
-    net.set_params(theta)
-    vf.set_params(vtheta)
-    out = net.forward(batch)                                   # the policy's own output = path["prob"]
-    if wl.head == synth.GAUSS:
-        d = wl.dims[-1]
-        oldprob = np.concatenate([out, np.broadcast_to(np.exp(theta[-d:])[None], out.shape)], 1).astype(np.float32)
-    else:
-        oldprob = out
-    act = synth.sample_actions(wl.head, oldprob, rng)
-    act_h, oldprob_h = pin(act), pin(oldprob)
-    theta_h = pin(theta)
     # move the policy slightly off theta_old, as after a few updates, so that ratios/KL are not trivial
     theta_cur = pin(synth.perturb(theta, 0.01, wl.seed + 7))
     reward_d = reward_h.to(dev)
     theta_d = theta_cur.to(dev)
-    batch.set_policy_inputs(wl.head, wl.dims[-1], act_h.numpy(), np.zeros(n_local, np.float32), oldprob_h.numpy())
-    del out
+    batch.set_policy_inputs(wl.head, dout, act_h.numpy(), np.zeros(n_local, np.float32), oldprob_h.numpy())
 
     def step_resident():
         vf.predict_into_baseline(batch)
@@ -289,6 +445,10 @@ def main():
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / args.steps}
 
+    parity = run_parity(args, wl, n_total, rank, world, dist if world > 1 else None, dev, net, vf, batch, comm, reward_d, theta_d,
+                        (r0, r1), dict(ob=ob_g, act=act_g, oldprob=oldprob_g, reward=reward_g, off=off_g, term=term_g,
+                                       base=base_g, theta=theta_cur.numpy()) if (rank == 0 and args.verify != "none") else None,
+                        stats)
     if rank == 0:
         peaks = {}
         try:
@@ -358,7 +518,7 @@ def main():
                            "l2": "inputs larger than L2 (observations %.2f GB per GPU)" % (n_local * wl.dims[0] * 4 / 1e9),
                            **CFG},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "kernels": kernels,
+                "kernels": kernels, "parity": parity,
                 "update": {"stats": [float(s) for s in stats], "info": info}}
         print(json.dumps(line), flush=True)
     if world > 1:

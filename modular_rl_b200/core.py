@@ -79,9 +79,21 @@ class _BatchCache(object):
         self.offsets = None
 
     def get(self, paths, timestep_limit):
+        """timestep_limit=None: the caller ignores the time feature (policy nets read the first ob_dim
+        columns only), so a batch cached for the same paths under ANY limit is reused - the update must not
+        re-upload the observations compute_advantage / NnVf.fit already bound."""
         obs = [path["observation"] for path in paths]
-        key = (tuple(id(o) for o in obs), tuple(o.shape for o in obs), float(timestep_limit))
-        if key != self.key:
+        okey = (tuple(id(o) for o in obs), tuple(o.shape for o in obs))
+        if timestep_limit is None:
+            if self.key is not None and self.key[:2] == okey:
+                return self.batch, self.offsets
+            timestep_limit = 1.0
+        key = okey + (float(timestep_limit),)
+        if key[:2] == (self.key or (None, None))[:2] and key != self.key:
+            # same observations, other limit: only the time feature / path table is rebuilt
+            self.batch.set_paths(self.offsets, self.terminated, float(timestep_limit))
+            self.key = key
+        elif key != self.key:
             lens = np.array([len(o) for o in obs], np.int64)
             offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
             terminated = np.array([bool(path.get("terminated", True)) for path in paths], np.uint8)
@@ -93,6 +105,7 @@ class _BatchCache(object):
             batch.set_obs(ob_no)                     # float64 from the ZFilter is cast to float32 ONCE
             batch.set_paths(offsets, terminated, float(timestep_limit))
             self.key, self.batch, self.keep, self.offsets = key, batch, obs, offsets
+            self.terminated = terminated
         return self.batch, self.offsets
 
 
@@ -101,7 +114,7 @@ _batch_cache = _BatchCache()
 
 def batch_for_paths(paths, timestep_limit=1.0):
     """-> (DeviceBatch with observations + trajectory structure bound, offsets int64[n_paths+1])"""
-    return _batch_cache.get(paths, timestep_limit if timestep_limit else 1.0)
+    return _batch_cache.get(paths, None if timestep_limit is None else (timestep_limit if timestep_limit else 1.0))
 
 
 def _split(flat, offsets):
@@ -417,7 +430,10 @@ class StochPolicyMLP(StochPolicy, EzFlat):
         """net output -> the reference's prob rows: [mean, std] or probabilities."""
         if isinstance(self._probtype, DiagGauss):
             d = self._probtype.d
-            std = np.exp(self.get_params_flat()[-d:])
+            ver = self.net.theta_version          # act() runs per env step: download theta only after it changed
+            if getattr(self, "_std_cache", (None, None))[0] != ver:
+                self._std_cache = (ver, np.exp(self.get_params_flat()[-d:]))
+            std = self._std_cache[1]
             return concat([out, np.broadcast_to(std[None, :], out.shape)], axis=1).astype(floatX)
         return out
 

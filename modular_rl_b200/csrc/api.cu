@@ -15,6 +15,9 @@
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+// Batch contents are identified by a process-wide version number: a freed batch whose address is reused can never
+// match a net's activation cache (the cache key is (batch pointer, version, parameter version)).
+static std::atomic<unsigned long long> g_batch_version{1};
 
 static int fail(const char* fmt, ...) {
   char buf[512];
@@ -159,6 +162,7 @@ extern "C" int mrl_batch_create(mrl_batch** out, int device, int ob_dim, int wit
   b->with_time = with_time_feature ? 1 : 0;
   b->xdim = ob_dim + b->with_time;
   b->d0p = round_up(b->xdim, 8);
+  b->version = g_batch_version.fetch_add(1);
   *out = b;
   return 0;
 }
@@ -188,7 +192,7 @@ extern "C" int mrl_batch_set_obs(mrl_batch* b, const void* ob, int dtype, long l
   b->N = N;
   b->Nglobal = N;
   b->n_tiles = (int)((N + MRL_TILE - 1) / MRL_TILE);
-  b->version++;
+  b->version = g_batch_version.fetch_add(1);
   b->has_baseline = b->has_adv32 = b->has_ret = false;
   b->pol_head = -1;
   const void* src;
@@ -469,13 +473,13 @@ extern "C" int mrl_batch_gae(mrl_batch* b, const void* reward, int reward_dtype,
   CK(b->ret.reserve((size_t)N * 8));
   CK(b->adv.reserve((size_t)N * 8));
   CK(b->adv32.reserve((size_t)N * 4));
-  CK(b->stats.reserve(64));
+  CK(b->stats.reserve(64 + MRL_MOMENTS_SCRATCH_DOUBLES * 8));
   RET(gae_impl(r_dev, reward_dtype, b->baseline.p, MRL_F64, b->offsets.as<long long>(),
                b->terminated.as<unsigned char>(), b->n_paths, N, gamma, lam, b->ret.as<double>(),
                b->adv.as<double>(), st));
   b->has_ret = true;
   if (standardize) {
-    CKL(launch_moments(b->adv.as<double>(), N, b->stats.as<double>(), st), 2);
+    CKL(launch_moments(b->adv.as<double>(), N, b->stats.as<double>(), b->stats.as<double>() + 8, st), 2);
     if (comm && mrl_comm_world(comm) > 1) {
       const int world = mrl_comm_world(comm), rank = mrl_comm_rank(comm);
       CK(b->gather.reserve((size_t)3 * world * 8 + 64));
@@ -539,8 +543,8 @@ extern "C" int mrl_standardize(double* x, long long N, double* stats_out, int lo
     CK(cudaMemcpyAsync(xd.p, x, (size_t)N * 8, cudaMemcpyHostToDevice, st));
     xp = xd.as<double>();
   }
-  CK(sd.reserve(64));
-  CKL(launch_standardize(xp, N, sd.as<double>(), nullptr, st), 3);
+  CK(sd.reserve(64 + MRL_MOMENTS_SCRATCH_DOUBLES * 8));
+  CKL(launch_standardize(xp, N, sd.as<double>(), sd.as<double>() + 8, nullptr, st), 3);
   if (loc == MRL_HOST) CK(cudaMemcpyAsync(x, xp, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
   if (stats_out) CK(cudaMemcpyAsync(stats_out, sd.p, 24, loc == MRL_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
   CK(cudaStreamSynchronize(st));
@@ -718,10 +722,7 @@ struct Plan { int slab_tiles, n_slabs; };
 static Plan plan_for(const mrl_batch* b) {
   // One CTA per slab; a slab is <= MRL_MAX_SLAB_TILES tiles (fp32 accumulation span).  Small batches get
   // one wave of CTAs; large ones the slab size with the fewest tile-rounds on this GPU's SM count.
-  static int sms = 0;
-  if (sms == 0) {
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = mrl_sm_count();   // callers have made b->device current
   Plan p;
   // The backward chain kernel walks 3 tiles per pass (the forward one 2) and clips the last pass of a slab, so
   // any slab size is legal; the cost of a plan is (waves of slabs) x (passes per slab).
@@ -869,6 +870,8 @@ static int d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   CK(cudaStreamSynchronize(st));
   return 0;
 }
+// after a stream synchronisation: did a peer-memory sum of this net time out?
+static int comm_ok(const mrl_net* n) { return n->comm ? mrl_comm_p2p_error(n->comm) : 0; }
 
 extern "C" int mrl_net_forward(mrl_net* n, mrl_batch* b, float* out, int loc, void* stream) {
   RET(check_pair(n, b, false));
@@ -965,6 +968,7 @@ extern "C" int mrl_net_ppo_lossgrad(mrl_net* n, mrl_batch* b, double kl_coeff, d
   if (gout)   // gout == NULL: losses / pensurr only (compute_losses, ppo.py:57)
     RET(pass_backward(n, b, MRL_MODE_GRAD, scal + 8, reverse_kl, nullptr, 0.0, nullptr, n->out64.as<double>(), st));
   RET(d2h_sync(n->h_scal, n->scal.p, 16 * 8, st));
+  RET(comm_ok(n));
   if (losses) { losses[0] = n->h_scal[0]; losses[1] = n->h_scal[1]; losses[2] = n->h_scal[2]; }
   if (pensurr) *pensurr = n->h_scal[10];
   if (gout) RET(d2h_sync(gout, n->out64.p, (size_t)n->g.P * 8, st));
@@ -989,6 +993,7 @@ extern "C" int mrl_net_vf_lossgrad(mrl_net* n, mrl_batch* b, double l2coeff, dou
   CKL(cudaGetLastError(), 1);
   if (gout) RET(pass_backward(n, b, MRL_MODE_GRAD, nullptr, 0, nullptr, 2.0 * l2coeff, nullptr, n->out64.as<double>(), st));
   RET(d2h_sync(n->h_scal, n->scal.p, 8 * 8, st));
+  RET(comm_ok(n));
   const double mse = n->h_scal[0], l2 = n->h_scal[4];
   if (losses) { losses[0] = mse + l2; losses[1] = mse; losses[2] = l2; }
   if (gout) RET(d2h_sync(gout, n->out64.p, (size_t)n->g.P * 8, st));
@@ -1031,6 +1036,7 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   CKL(launch_cg_finish(P, n->out32.as<float>(), cfg->cg_damping, cfg->max_kl, n->g32.as<float>(),
                        n->cg_x.as<double>(), n->fullstep.as<double>(), n->cgstate.as<CgState>(), st), 1);
   CK(cudaStreamSynchronize(st));   // h_scal / h_cg (first snapshot) are valid now
+  RET(comm_ok(n));
   const double before[3] = {-n->h_scal[0], n->h_scal[1], n->h_scal[2]};
   const double gmax = n->h_cg->gmax;
   double after[3] = {before[0], before[1], before[2]};
@@ -1059,6 +1065,7 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
         break;
       }
     }
+    RET(comm_ok(n));
     if (!success) {                // rollback (trpo.py:133 with theta = x)
       CK(cudaMemcpyAsync(n->theta.p, n->theta_prev.p, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
       RET(repack(n, st));

@@ -8,6 +8,7 @@
 #include "../../include/mrl_b200.h"
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -64,6 +65,9 @@ struct P2pState {
   unsigned char* peer[MRL_P2P_MAX_WORLD] = {nullptr}; // every rank's buffer as mapped here (peer[rank] == local)
   unsigned int* counter = nullptr;
   unsigned long long seq = 0;
+  int* h_err = nullptr;                               // mapped pinned host word: set by a gather that timed out
+  int* d_err = nullptr;                               // its device alias
+  unsigned long long timeout_ns = 600ull * 1000000000ull;
 };
 #define P2P_HEADER 256
 static inline unsigned long long* p2p_flags(unsigned char* base, int parity) {
@@ -116,6 +120,7 @@ extern "C" int mrl_comm_destroy(mrl_comm* c) {
       if (q != c->rank && c->p2p.peer[q]) cudaIpcCloseMemHandle(c->p2p.peer[q]);
     cudaFree(c->p2p.local);
     cudaFree(c->p2p.counter);
+    if (c->p2p.h_err) cudaFreeHost(c->p2p.h_err);
   }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
@@ -136,6 +141,14 @@ extern "C" int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char hand
     return mrl_set_error("mrl_comm_p2p_export: out of device memory");
   cudaMemset(p.local, 0, bytes);
   cudaMemset(p.counter, 0, 4);
+  if (cudaHostAlloc((void**)&p.h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&p.d_err, p.h_err, 0) != cudaSuccess)
+    return mrl_set_error("mrl_comm_p2p_export: cannot allocate the mapped error word");
+  *p.h_err = 0;
+  if (const char* t = getenv("MRL_P2P_TIMEOUT_S")) {
+    const double sec = atof(t);
+    if (sec > 0) p.timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   cudaDeviceSynchronize();
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, p.local);
@@ -197,16 +210,24 @@ int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push) {
 // rank's flag for seq+1, which a rank raises after it finished reading the slots of seq.
 __global__ void p2p_gather_kernel(const unsigned long long* __restrict__ flags, const double* __restrict__ slots,
                                   long long cap, int world, unsigned long long seq, long long n,
-                                  double* __restrict__ out64, float* __restrict__ out32) {
+                                  double* __restrict__ out64, float* __restrict__ out32,
+                                  unsigned long long timeout_ns, int* __restrict__ err) {
   if (threadIdx.x < world) {
-    const volatile unsigned long long* f = flags + threadIdx.x;
+    const unsigned long long* f = flags + threadIdx.x;
+    unsigned long long t0 = 0;
     unsigned int spins = 0;
-    while (*f < seq) {
-      if (++spins > (1u << 28)) __trap();   // a lost peer becomes an error, never a hung GPU
+    while (ld_acquire_sys(f) < seq) {
+      // a peer may legitimately be late by seconds (its host is busy); the bound is wall-clock time, and a
+      // lost peer becomes an error word the host checks - never a trap, never a hung GPU
+      if ((++spins & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) { *err = 1; break; }
+      }
     }
   }
   __syncthreads();
-  __threadfence_system();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < world; ++r) s += __ldcg(slots + (size_t)r * cap + i);
@@ -220,9 +241,13 @@ int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, c
   int blocks = (int)((n + 255) / 256);
   if (blocks > 64) blocks = 64;     // all CTAs are resident: they spin on the flags
   p2p_gather_kernel<<<blocks, 256, 0, st>>>(p2p_flags(p.local, parity), p2p_slot(p.local, p.cap, c->world, parity, 0), p.cap,
-                                            c->world, p.seq, n, out64, out32);
+                                            c->world, p.seq, n, out64, out32, p.timeout_ns, p.d_err);
   if (cudaGetLastError() != cudaSuccess) return mrl_set_error("p2p_gather_kernel launch failed");
   return 0;
+}
+int mrl_comm_p2p_error(const mrl_comm* c) {
+  if (!c || !c->p2p.h_err || *c->p2p.h_err == 0) return 0;
+  return mrl_set_error("peer-memory all-reduce: a rank did not deliver within MRL_P2P_TIMEOUT_S; the results of this update are invalid");
 }
 __global__ void p2p_push_kernel(const double* __restrict__ in, long long n, P2pPush push) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

@@ -27,6 +27,19 @@ bool mrl_comm_p2p_ready(const mrl_comm* c, long long n);
 int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push);
 // Wait for all ranks' slots, sum them in rank order -> out64 (and out32 if not null)
 int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st);
+// Non-zero after a peer failed to deliver within the timeout (MRL_P2P_TIMEOUT_S, default 600 s): the sums of that
+// operation are invalid.  Checked by the host after every stream synchronisation of an update.
+int mrl_comm_p2p_error(const mrl_comm* c);
+// Flag hand-off by the PTX memory model: the producer publishes with st.release.sys after its data stores, the
+// consumer polls with ld.acquire.sys before it reads the slots.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) {
 #pragma unroll
   for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q)
@@ -40,9 +53,8 @@ __device__ __forceinline__ void p2p_push_done(const P2pPush& p) {
     const unsigned int total = gridDim.x * gridDim.y;
     if (atomicAdd(p.counter, 1u) == total - 1) {
       *p.counter = 0;
-      __threadfence_system();
-      for (int q = 0; q < p.world; ++q) *reinterpret_cast<volatile unsigned long long*>(p.flag[q]) = p.seq;
-      __threadfence_system();
+      __threadfence_system();   // acquire side of the counter hand-off: every CTA's slot stores are ordered before the flags
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.flag[q], p.seq);
     }
   }
 }

@@ -150,3 +150,5 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 
 // host-side helpers implemented in geom.cu
 void mrl_build_geom(NetGeom* g, int n_layers, const int* dims, int head, int act, int naux);
+int mrl_sm_count();                                          // SMs of the current device (cached per device)
+cudaError_t mrl_func_smem(const void* func, size_t bytes);   // opt in to `bytes` of dynamic shared memory (per device)

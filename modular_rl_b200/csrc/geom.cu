@@ -3,6 +3,42 @@
 //   [W1 (d0 x d1, C order), b1, W2, b2, ..., WL, bL, logstd].
 #include "common.cuh"
 #include <string.h>
+#include <mutex>
+#include <vector>
+
+// SM count of the CURRENT device, cached per device id (one process may drive several GPUs).
+int mrl_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cache[dev] = sms;
+  }
+  return cache[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a function: raise it once per
+// (function, device) and whenever a larger size is asked for.
+cudaError_t mrl_func_smem(const void* func, size_t bytes) {
+  struct Ent { const void* f; int dev; size_t bytes; };
+  static std::vector<Ent> seen;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  for (Ent& en : seen)
+    if (en.f == func && en.dev == dev) {
+      if (bytes <= en.bytes) return cudaSuccess;
+      e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e == cudaSuccess) en.bytes = bytes;
+      return e;
+    }
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) seen.push_back({func, dev, bytes});
+  return e;
+}
 
 void mrl_build_geom(NetGeom* g, int n_layers, const int* dims, int head, int act, int naux) {
   memset(g, 0, sizeof(*g));

@@ -105,9 +105,10 @@ void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st);  // 
 cudaError_t launch_gae(const void* reward, int reward_f64, const void* baseline, int baseline_f64,
                        const long long* offsets, const unsigned char* terminated, int n_paths, long long N,
                        double gamma, double lam, double* ret, double* adv, cudaStream_t st);
-cudaError_t launch_standardize(double* adv, long long N, double* stats /* n, mean, M2 */, float* adv32,
-                               cudaStream_t st);
-cudaError_t launch_moments(const double* x, long long N, double* stats, cudaStream_t st);
+#define MRL_MOMENTS_SCRATCH_DOUBLES 1792   // per-block Welford partials of launch_moments (caller-owned)
+cudaError_t launch_standardize(double* adv, long long N, double* stats /* n, mean, M2 */, double* scratch,
+                               float* adv32, cudaStream_t st);
+cudaError_t launch_moments(const double* x, long long N, double* stats, double* scratch, cudaStream_t st);
 cudaError_t launch_normalize(double* x, long long N, const double* stats, float* x32, cudaStream_t st);
 cudaError_t launch_zfilter_scan(const void* x, int x_f64, long long N, int d, double n0, double* state_dev,
                                 int demean, int destd, double clip, void* y, int y_f64, double* scratch,

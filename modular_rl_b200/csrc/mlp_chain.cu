@@ -883,18 +883,11 @@ static cudaError_t launch_shape(const NetGeom& g, const MidBwdArgs& a, int n_sla
   ChainJobs jobs;
   if (!build_jobs<S>(g, &jobs)) return cudaErrorInvalidConfiguration;
   const size_t sm = S::smem_floats(MODE == MRL_MODE_FVP) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_bwd_kernel<S, MRL_ACT_TANH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  {
+    cudaError_t e = mrl_func_smem((const void*)chain_bwd_kernel<S, MRL_ACT_TANH, MODE>, sm);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = mrl_sm_count();
   chain_bwd_kernel<S, MRL_ACT_TANH, MODE><<<n_slabs < sms ? n_slabs : sms, CH_THREADS, sm, st>>>(g, a, jobs, n_slabs);
   return cudaGetLastError();
 }
@@ -1211,18 +1204,11 @@ static bool fwd_shape_fits(const NetGeom& g) {
 template <class S>
 static cudaError_t launch_fwd_shape(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st) {
   const size_t sm = ((size_t)S::wfloats() + S::vbfloats() + 8 * S::nt(S::L)) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_fwd_kernel<S, MRL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  {
+    cudaError_t e = mrl_func_smem((const void*)chain_fwd_kernel<S, MRL_ACT_TANH>, sm);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = mrl_sm_count();
   chain_fwd_kernel<S, MRL_ACT_TANH><<<n_slabs < 2 * sms ? n_slabs : 2 * sms, FW_THREADS, sm, st>>>(g, a, n_slabs);   // 2 CTAs per SM
   return cudaGetLastError();
 }

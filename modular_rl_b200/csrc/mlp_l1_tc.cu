@@ -580,15 +580,11 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   int tmem_cols = 32;
   while (tmem_cols < n_acc * acc_cols + nstages * kps * 16) tmem_cols *= 2;
   const size_t smem = 512 + (size_t)nstages * stage_bytes;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(l1_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = mrl_func_smem((const void*)l1_forward_tc_kernel, smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = mrl_sm_count();
   const int n_mtiles = (n_tiles + 1) / 2;
   const int grid = n_mtiles < sms ? n_mtiles : sms;
   l1_forward_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XA, WB, Zt, g.d0p / 8, xa_kgroups, nu, g.d[1], n_mtiles, n_tiles,
@@ -641,15 +637,11 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
   int acc_stride, nts, nss, tmem_cols;
   size_t smem;
   if (!l1g_plan(g, &acc_stride, &nts, &nss, &tmem_cols, &smem)) return cudaErrorInvalidConfiguration;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(l1_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = mrl_func_smem((const void*)l1_grad_tc_kernel, smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = mrl_sm_count();
   const int grid = n_slabs < sms ? n_slabs : sms;
   l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
                                                     n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts);

@@ -193,25 +193,22 @@ __global__ void normalize_kernel(double* __restrict__ x, long long N, const doub
 }
 
 #define MOM_BLOCKS 592
-static double* g_mom_parts = nullptr;
+static_assert(MOM_BLOCKS * 3 <= MRL_MOMENTS_SCRATCH_DOUBLES, "moments scratch too small");
 
-cudaError_t launch_moments(const double* x, long long N, double* stats, cudaStream_t st) {
-  if (!g_mom_parts) {
-    cudaError_t e = cudaMalloc(&g_mom_parts, MOM_BLOCKS * 3 * sizeof(double));
-    if (e != cudaSuccess) return e;
-  }
+// `scratch`: MRL_MOMENTS_SCRATCH_DOUBLES doubles owned by the caller (per batch: no process-wide device state)
+cudaError_t launch_moments(const double* x, long long N, double* stats, double* scratch, cudaStream_t st) {
   int blocks = (int)min((long long)MOM_BLOCKS, (N + MOM_THREADS * 8 - 1) / (MOM_THREADS * 8));
   if (blocks < 1) blocks = 1;
-  moments_partial_kernel<<<blocks, MOM_THREADS, 0, st>>>(x, N, g_mom_parts);
-  moments_final_kernel<<<1, 1, 0, st>>>(g_mom_parts, blocks, stats);
+  moments_partial_kernel<<<blocks, MOM_THREADS, 0, st>>>(x, N, scratch);
+  moments_final_kernel<<<1, 1, 0, st>>>(scratch, blocks, stats);
   return cudaGetLastError();
 }
 cudaError_t launch_normalize(double* x, long long N, const double* stats, float* x32, cudaStream_t st) {
   if (N > 0) normalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x, N, stats, x32);
   return cudaGetLastError();
 }
-cudaError_t launch_standardize(double* adv, long long N, double* stats, float* adv32, cudaStream_t st) {
-  cudaError_t e = launch_moments(adv, N, stats, st);
+cudaError_t launch_standardize(double* adv, long long N, double* stats, double* scratch, float* adv32, cudaStream_t st) {
+  cudaError_t e = launch_moments(adv, N, stats, scratch, st);
   if (e != cudaSuccess) return e;
   return launch_normalize(adv, N, stats, adv32, st);
 }

@@ -192,6 +192,7 @@ class DeviceNet:
         self.head, self.device, self.activation = head, device, activation
         self.P = int(L.lib().mrl_net_num_params(self._h))
         self.dout = self.dims[-1]
+        self.theta_version = 0           # bumped by every call that can change the device parameters
 
     def __getstate__(self):
         # the device handle is rebuilt on load; theta travels as the flat float32 vector of SURVEY A.1.
@@ -220,6 +221,7 @@ class DeviceNet:
     def set_params(self, theta, stream=None):
         k, p, dt, loc, shape = _arg(theta, _F)
         assert int(np.prod(shape)) == self.P, (shape, self.P)
+        self.theta_version += 1
         L.check(L.lib().mrl_net_set_params(self._h, p, dt, loc, stream))
 
     def get_params(self) -> np.ndarray:
@@ -272,6 +274,7 @@ class DeviceNet:
         cfg = L.TrpoCfg(cg_damping, max_kl, residual_tol, accept_ratio, cg_iters, max_backtracks)
         stats = np.zeros(6, np.float64)
         info = np.zeros(6, np.int32)
+        self.theta_version += 1
         L.check(L.lib().mrl_net_trpo_step(self._h, batch._h, C.byref(cfg), L.ptr(stats), L.ptr(info), stream))
         keys = ("skipped", "success", "accepted_index", "cg_iters_run", "n_fvp", "n_loss_passes")
         return stats, dict(zip(keys, (int(v) for v in info)))

@@ -41,7 +41,7 @@ class TrpoUpdater(EzFlat, EzPickle):
 
     def bind(self, paths):
         """trpo.py:74-77: concatenate the paths and hand (ob, action, advantage, prob) to the device."""
-        batch, _ = batch_for_paths(paths, 1.0)
+        batch, _ = batch_for_paths(paths, None)   # any cached limit: the policy ignores the time feature
         probtype = self.stochpol.probtype
         prob_np = concat([path["prob"] for path in paths])
         action_na = concat([path["action"] for path in paths])

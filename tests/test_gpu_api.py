@@ -313,6 +313,13 @@ def test_act_batch_matches_act(kind):
     _, info = pol.act_batch(fobs, stochastic=False)
     rows = np.stack([pol.act(o, stochastic=False)[1]["prob"] for o in fobs])
     assert np.allclose(info["prob"], rows, rtol=1e-6, atol=1e-7)
+    # against the oracle's forward (float64) at the device's float32 parameters, not only CUDA against CUDA
+    from oracle import policy_math as pm
+    spec = _oracle_spec(pol)
+    th = pol.get_flat()
+    _, z = pm.forward(th, spec, fobs.astype(np.float32))
+    want = pm.head_prob(th, spec, z)
+    assert np.linalg.norm(info["prob"] - want) / np.linalg.norm(want) < 1e-5
     np.random.seed(5)
     a_batch, _ = pol.act_batch(fobs[:1], stochastic=True)
     np.random.seed(5)

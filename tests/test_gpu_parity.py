@@ -29,8 +29,8 @@ def _oracle():
     return advantage, natgrad, policy_math, ppo_penalty, valuefn, zfilter
 
 
-def _bind(dev, spec_dims, head, ob, act, adv, oldprob, theta, with_time=True):
-    net = dev.DeviceNet(spec_dims, head)
+def _bind(dev, spec_dims, head, ob, act, adv, oldprob, theta, with_time=True, activation="tanh"):
+    net = dev.DeviceNet(spec_dims, head, activation)
     batch = dev.DeviceBatch(spec_dims[0], with_time_feature=with_time)
     batch.set_obs(ob)
     N = ob.shape[0]
@@ -135,15 +135,20 @@ SHAPES = {
     # kernel, wide rows in the layer-1 gradient kernel, generic job-list kernels for the rest
     "wide": ((20, 160, 16, 4), 0, 1500),
     "wide_in": ((300, 136, 24, 5), 1, 900),
+    # --activation relu|sigmoid (agentzoo.py:22,37,58): generic job-list kernels
+    "relu": ((11, 64, 64, 3), 0, 2000, "relu"),
+    "sigmoid": ((17, 32, 16, 5), 1, 1500, "sigmoid"),
+    "relu_humanoid": ((376, 100, 50, 25, 17), 0, 1100, "relu"),
 }
 
 
 def _synth_case(name):
     from modular_rl_b200 import synth
     _, _, pm, *_ = _oracle()
-    dims, head, N = SHAPES[name]
+    dims, head, N = SHAPES[name][:3]
+    act = SHAPES[name][3] if len(SHAPES[name]) > 3 else "tanh"
     wl = synth.Workload(name, dims, head, N, 200, 11)
-    spec = pm.NetSpec(dims, pm.GAUSS if head == 0 else pm.CAT)
+    spec = pm.NetSpec(dims, pm.GAUSS if head == 0 else pm.CAT, act)
 
     def fwd(th, ob):
         _, z = pm.forward(th, spec, ob)
@@ -153,11 +158,29 @@ def _synth_case(name):
     return spec, head, theta, data
 
 
+MEASURED = {}   # name -> measured relative errors, written to gpurun_out/parity_measured.json at session end
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_measured():
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.json"), "w") as f:
+            json.dump(MEASURED, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("name", list(SHAPES))
 def test_synthetic_shapes(dev, name):
     spec, head, theta, d = _synth_case(name)
     _, natgrad, pm, *_ = _oracle()
-    net, batch = _bind(dev, spec.dims, head, d["ob"], d["act"], d["adv"], d["oldprob"], theta)
+    net, batch = _bind(dev, spec.dims, head, d["ob"], d["act"], d["adv"], d["oldprob"], theta,
+                       activation=spec.activation)
     args = (d["ob"], d["act"], d["adv"], d["oldprob"])
     ls = net.losses(batch)
     ols = pm.losses(theta, spec, *args)
@@ -167,7 +190,8 @@ def test_synthetic_shapes(dev, name):
     assert relerr(g, og) < TOL
     v = np.random.default_rng(3).standard_normal(net.P).astype(np.float32)
     f = net.fvp(batch, v)
-    assert relerr(f, pm.fisher_vector_product(theta, spec, d["ob"], v)) < TOL
+    of = pm.fisher_vector_product(theta, spec, d["ob"], v)
+    assert relerr(f, of) < TOL
     # a second Fvp reuses the cached activations and must not depend on call history
     assert np.array_equal(net.fvp(batch, v), f)
     stats, info = net.trpo_step(batch, cg_damping=0.1, max_kl=0.01)
@@ -175,8 +199,17 @@ def test_synthetic_shapes(dev, name):
     assert info["success"] == int(oinfo["success"]) and info["accepted_index"] == oinfo["accepted_index"]
     assert info["cg_iters_run"] == oinfo["cg_iters_run"]
     sd, fs, sc = net.trpo_vectors()
-    assert relerr(sd, oinfo["stepdir"]) < 1e-4, relerr(sd, oinfo["stepdir"])
-    assert relerr(fs, oinfo["fullstep"]) < 1e-4
+    # Step direction (north_star: 1e-5).  CG amplifies rounding by the conditioning of F + damping*I, so the bar is
+    # 1e-5 wherever the REFERENCE's own float32 path (oracle dtype=float32 = the fork's floatX) stays within 1e-5 of
+    # float64; elsewhere the CUDA path must be at least as close to float64 as that float32 path is.  Both numbers
+    # are recorded (gpurun_out/parity_measured.json).
+    _, o32 = natgrad.trpo_update(theta, spec, *args, 0.1, 0.01, dtype=np.float32)
+    e_sd, e_fs = relerr(sd, oinfo["stepdir"]), relerr(fs, oinfo["fullstep"])
+    floor = relerr(o32["stepdir"], oinfo["stepdir"])
+    MEASURED[name] = dict(grad=relerr(g, og), fvp=relerr(f, of), stepdir=e_sd, fullstep=e_fs,
+                          stepdir_reference_float32=floor, theta_new=relerr(net.get_params(), oinfo["theta_new"]))
+    assert e_sd < max(TOL, 1.5 * floor), (e_sd, floor)
+    assert e_fs < max(TOL, 1.5 * floor), (e_fs, floor)
     assert relerr(net.get_params(), oinfo["theta_new"]) < 1e-5
     want = np.array([ostats[k] for k in ("surr_before", "surr_after", "kl_before", "kl_after",
                                          "ent_before", "ent_after")])
