@@ -597,6 +597,8 @@ extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, 
 struct mrl_net {
   int device = 0;
   NetGeom g;
+  DevBuf WC, VC, dbg;      // tcgen05 Fisher-vector chain: weight images of theta / of the tangent, debug dump
+  bool tc_fvp = false;
   DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, img, imgv, vflat, Z1, cache, part1, partm, loss_part, out32,
       out64, g32, cg_b, cg_x, cg_r, cg_p, p32, x32, fullstep, cgstate, cgscratch, scal, headout, stage;
   unsigned long long params_version = 1, cache_params_version = 0, cache_batch_version = 0;
@@ -645,6 +647,15 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
   R(n->cg_b, P * 8); R(n->cg_x, P * 8); R(n->cg_r, P * 8); R(n->cg_p, P * 8);
   R(n->p32, P * 4); R(n->x32, P * 4); R(n->fullstep, P * 8);
   R(n->cgstate, sizeof(CgState)); R(n->scal, 32 * 8); R(n->cgscratch, CG_SCRATCH_DOUBLES * 8);
+  {
+    const char* off = getenv("MRL_FVP_TC");
+    n->tc_fvp = fvp_tc_supported(n->g) && !(off && off[0] == '0');
+    if (n->tc_fvp) {
+      R(n->WC, fvp_tc_image_floats(n->g, 0) * 4);
+      R(n->VC, fvp_tc_image_floats(n->g, 1) * 4);
+      if (getenv("MRL_FVP_TC_DEBUG")) R(n->dbg, (size_t)8 * 128 * 128 * 4);
+    }
+  }
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_scal, 32 * 8);
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_cg, sizeof(CgState));
   if (e == cudaSuccess) e = cudaMemset(n->theta.p, 0, P * 4);
@@ -660,7 +671,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
+  DevBuf* bufs[] = {&n->WC, &n->VC, &n->dbg, &n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->cgscratch, &n->scal,
                     &n->headout, &n->stage};
@@ -688,6 +699,7 @@ void cast_f64_f32(const double* x, float* y, long long N, cudaStream_t st) {
 
 static int repack(mrl_net* n, cudaStream_t st) {
   CKP(PK_PACK, launch_pack_params(n->g, n->theta.as<float>(), n->img.as<float>(), n->WBt.as<float>(), st), 1);
+  if (n->tc_fvp) CKP(PK_PACK, launch_fvp_tc_pack(n->g, n->theta.as<float>(), n->WC.as<float>(), 0, st), 1);
   n->params_version++;
   return 0;
 }
@@ -719,11 +731,28 @@ extern "C" int mrl_net_get_params(mrl_net* n, float* theta, int loc, void* strea
 
 // ------------------------------------------------------------------------ passes
 struct Plan { int slab_tiles, n_slabs; };
-static Plan plan_for(const mrl_batch* b) {
+static Plan plan_for(const mrl_batch* b, bool pairs = false) {
   // One CTA per slab; a slab is <= MRL_MAX_SLAB_TILES tiles (fp32 accumulation span).  Small batches get
   // one wave of CTAs; large ones the slab size with the fewest tile-rounds on this GPU's SM count.
   const int sms = mrl_sm_count();   // callers have made b->device current
   Plan p;
+  if (pairs) {
+    // tcgen05 Fisher-vector chain: 128-timestep MMA tiles = pairs of cache tiles, slabs of 1..8 of them
+    if (b->n_tiles <= sms * 2) {
+      p.slab_tiles = 2;
+    } else {
+      long long best = -1;
+      p.slab_tiles = MRL_MAX_SLAB_TILES;
+      const int smin = b->n_tiles <= sms * MRL_MAX_SLAB_TILES ? 2 : 8;
+      for (int s = MRL_MAX_SLAB_TILES; s >= smin; s -= 2) {
+        const long long slabs = (b->n_tiles + s - 1) / s;
+        const long long cost = (slabs + sms - 1) / sms * (s / 2);
+        if (best < 0 || cost < best) { best = cost; p.slab_tiles = s; }
+      }
+    }
+    p.n_slabs = (b->n_tiles + p.slab_tiles - 1) / p.slab_tiles;
+    return p;
+  }
   // The backward chain kernel walks 3 tiles per pass (the forward one 2) and clips the last pass of a slab, so
   // any slab size is legal; the cost of a plan is (waves of slabs) x (passes per slab).
   if (b->n_tiles <= sms * 3) {
@@ -814,7 +843,8 @@ static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
 static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
                          const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
   const NetGeom& g = n->g;
-  const Plan pl = plan_for(b);
+  const bool tc = mode == MRL_MODE_FVP && n->tc_fvp;
+  const Plan pl = plan_for(b, tc);
   RET(reserve_ws(n, b, pl));
   if (!cache_ok(n, b)) RET(pass_forward(n, b, false, true, nullptr, st));
   MidBwdArgs a;
@@ -838,7 +868,15 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.slab_tiles = pl.slab_tiles;
   a.mode = mode;
   a.reverse_kl = reverse_kl;
-  if (chain_bwd_shape(g, mode) != 0) CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_chain_backward(g, a, pl.n_slabs, st), 1);
+  if (tc) {
+    CKP(PK_PACK, launch_fvp_tc_pack(g, v_dev, n->VC.as<float>(), 1, st), 1);
+    FvpTcArgs x;
+    x.WC = n->WC.as<float>(); x.VC = n->VC.as<float>(); x.vflat = v_dev; x.img = n->img.as<float>();
+    x.Zt = n->Z1.as<float>(); x.cache = n->cache.as<float>(); x.DG = n->DG.as<float>(); x.partm = n->partm.as<float>();
+    x.dbg = n->dbg.as<float>();
+    x.N = b->N; x.n_tiles = b->n_tiles; x.slab_tiles = pl.slab_tiles; x.n_slabs = pl.n_slabs;
+    CKP(PK_MIDB_FVP, launch_fvp_tc(g, x, st), 1);
+  } else if (chain_bwd_shape(g, mode) != 0) CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_chain_backward(g, a, pl.n_slabs, st), 1);
   else CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
                                 pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
@@ -1080,6 +1118,15 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
     info[4] = skipped ? 0 : cg_run + 1;   // Fvp evaluations the reference would make; launches after an early break are no-ops
     info[5] = loss_passes;
   }
+  return 0;
+}
+
+// debug: stage outputs of the first 128-timestep tile of the last tcgen05 Fvp (MRL_FVP_TC_DEBUG=1): [8][128][128] floats
+extern "C" int mrl_debug_fvp_tc_read(mrl_net* n, float* out) {
+  if (!n || !n->dbg.p || !out) return fail("mrl_debug_fvp_tc_read: debug dump not enabled");
+  CK(cudaSetDevice(n->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, n->dbg.p, (size_t)8 * 128 * 128 * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

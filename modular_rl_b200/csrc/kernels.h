@@ -79,6 +79,25 @@ cudaError_t launch_chain_backward(const NetGeom& g, const MidBwdArgs& a, int n_s
 int chain_fwd_shape(const NetGeom& g);
 cudaError_t launch_chain_forward(const NetGeom& g, const MidFwdArgs& a, int n_slabs, cudaStream_t st);
 
+// ---- mlp_fvp_tc.cu  (tcgen05 / TMEM Fisher-vector chain of layers >= 2)
+struct FvpTcArgs {
+  const float* WC;      // chain weight images of theta   (launch_fvp_tc_pack, tangent = 0)
+  const float* VC;      // chain weight images of the tangent (tangent = 1)
+  const float* vflat;   // the tangent, flat
+  const float* img;     // theta image (logstd block)
+  const float* Zt;      // x . V_1, tile-major
+  const float* cache;   // activation cache of theta
+  float* DG;            // out: delta_1 operand of the layer-1 gradient GEMM
+  float* partm;         // out: [n_slabs][pmid]
+  float* dbg;           // debug dump of the first 128-timestep tile or nullptr
+  long long N;
+  int n_tiles, slab_tiles /* even */, n_slabs;
+};
+bool fvp_tc_supported(const NetGeom& g);
+size_t fvp_tc_image_floats(const NetGeom& g, int tangent);
+cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* dst, int tangent, cudaStream_t st);
+cudaError_t launch_fvp_tc(const NetGeom& g, const FvpTcArgs& a, cudaStream_t st);
+
 // ---- vec_kernels.cu  (CG / line-search vector algebra on device-resident fp64 vectors)
 struct CgState {   // device-resident scalars
   double rdotr, pz, alpha, beta, shs, lm, gdots, expected_rate, gmax;
