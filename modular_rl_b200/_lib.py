@@ -17,7 +17,7 @@ GAUSS, CATEGORICAL, VALUE = 0, 1, 2
 ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrl_b200.so")
+LIB_PATH = os.environ.get("MRL_LIB") or os.path.join(_HERE, "libmrl_b200.so")   # MRL_LIB: kernel experiments only
 
 _DT = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
        np.dtype(np.int64): I64}

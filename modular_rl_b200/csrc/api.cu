@@ -793,8 +793,17 @@ static const float* aux_of(const mrl_net* n, const mrl_batch* b) {
 
 static int reserve_ws(mrl_net* n, const mrl_batch* b, const Plan& pl) {
   const NetGeom& g = n->g;
-  CK(n->Z1.reserve((size_t)b->n_tiles * g.d[1] * MRL_LDT * 4));
-  CK(n->cache.reserve((size_t)b->n_tiles * g.act_rows * MRL_LDT * 4));
+  // one tile of slack behind both: the tcgen05 chain reads up to 15 feature rows past a layer's width (see
+  // mlp_fvp_tc.cu); fresh allocations are zeroed so that the slack never holds a NaN pattern
+  for (DevBuf* d : {&n->Z1, &n->cache}) {
+    const size_t rows = d == &n->Z1 ? (size_t)g.d[1] : (size_t)g.act_rows;
+    const size_t bytes = (size_t)(b->n_tiles + 1) * rows * MRL_LDT * 4;
+    if (bytes > d->cap) {
+      CK(d->reserve(bytes));
+      CK(cudaMemsetAsync(d->p, 0, d->cap, 0));
+      CK(cudaStreamSynchronize(0));
+    }
+  }
   CK(n->DG.reserve(l1tc_dg_floats(g, b->n_tiles) * 4));
   CK(n->part1.reserve((size_t)pl.n_slabs * g.d[0] * g.n1p * 4));
   CK(n->partm.reserve((size_t)pl.n_slabs * g.pmid * 4));

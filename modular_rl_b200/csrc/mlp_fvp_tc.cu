@@ -84,6 +84,16 @@ __device__ __forceinline__ void ft_rot8(uint32_t (&v)[8], int r) {   // v[i] <- 
   for (int i = 0; i < 8; ++i) v[i] = a[i];
 }
 __device__ __forceinline__ void ft_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Register redistribution between the warp roles (all four warps of a warpgroup execute the same instruction): the
+// launch gives every thread 128 registers (512 threads = the whole register file); the producer / MMA-issuer warps and
+// the converters hand most of theirs back, the epilogue warps - which keep a slot of prefetched activations in
+// registers to hide the L2 latency - take them.
+#define FT_REGS_CTRL 40
+#define FT_REGS_CONV 96
+#define FT_REGS_EPI 176
+template <int N> __device__ __forceinline__ void ft_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void ft_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+static_assert(4 * 32 * FT_REGS_CTRL + 4 * 32 * FT_REGS_CONV + 8 * 32 * FT_REGS_EPI <= 65536, "register file");
 
 struct FtArgs {
   const float* WC;      // chain weight images of theta
@@ -155,6 +165,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
   const size_t tile_c = (size_t)g.act_rows * MRL_LDT;   // floats per 64-timestep cache tile
   const size_t tile_z = (size_t)g.d[1] * MRL_LDT;
 
+  if (warp < 4) {
+  ft_reg_dec<FT_REGS_CTRL>();
   if (warp == 0) {
     // ================================================================ producer: weight ring + L2 prefetch
     if (lane == 0) {
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc) {
               const int nk = min(2, st.kgs - kg0);
               const int ws = wc % FT_WSTAGES;
-              mbar_wait_guard(&w_empty[ws], ((wc / FT_WSTAGES) & 1) ^ 1);
+              mbar_wait_sleep(&w_empty[ws], ((wc / FT_WSTAGES) & 1) ^ 1);
               float* dst = wring + (size_t)ws * P.wstage_floats;
               const uint32_t bytes = (uint32_t)(nk * kgf * 4);
               mbar_expect_tx(&w_full[ws], st.rfwd ? 2 * bytes : bytes);
@@ -205,8 +217,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc, ++u) {
             const int nk = min(2, st.kgs - kg0);
             const int ws = wc % FT_WSTAGES, e = u & 1;
-            mbar_wait_guard(&w_full[ws], (wc / FT_WSTAGES) & 1);
-            mbar_wait_guard(&a_full[e], (u >> 1) & 1);
+            mbar_wait_sleep(&w_full[ws], (wc / FT_WSTAGES) & 1);
+            mbar_wait_sleep(&a_full[e], (u >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t bw = umma_desc_lo(wring_u32 + (uint32_t)ws * (uint32_t)P.wstage_floats * 4u, lbo);
@@ -246,8 +258,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
     uint32_t kc = 0, tcount = 0, scount = 0;
     for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x, ++scount) {
       const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
-      mbar_wait_guard(gacc_empty, (scount & 1) ^ 1);      // the previous slab's accumulators have been flushed
+      mbar_wait_sleep(gacc_empty, (scount & 1) ^ 1);      // the previous slab's accumulators have been flushed
       tc_fence_after();
+#ifdef FT_NO_K
+      if (elect_one()) tc_commit(gacc_full);
+      __syncwarp();
+      continue;
+#endif
       for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
         for (int p = 0; p < P.n_pass; ++p) {
           const int Np_ = P.pass_N[p];
@@ -255,10 +272,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           const uint32_t d_tmem = tmem_base + P.pass_acc[p];
           const uint32_t bbase = umma_desc_lo(kbuf_u32 + (uint32_t)P.pass_buf[p] * 4u, 128);   // LBO = 128 B: adjacent k-chunks
           const uint32_t lo_off = ((uint32_t)Np_ * 512u) >> 4;                                  // lo half of the buffer
-          mbar_wait_guard(&d_full[p], tcount & 1);          // this tile's delta blocks of the pass are in shared memory
+          mbar_wait_sleep(&d_full[p], tcount & 1);          // this tile's delta blocks of the pass are in shared memory
           for (int ks = 0; ks < 16; ++ks, ++kc) {
             const int sl = kc % FT_KSLOTS;
-            mbar_wait_guard(&kconv[sl], (kc / FT_KSLOTS) & 1);
+            mbar_wait_sleep(&kconv[sl], (kc / FT_KSLOTS) & 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t ta = tmem_base + P.kslot_col + 16 * sl;     // [h^T hi 8 | lo 8]
@@ -276,46 +293,69 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
         }
       }
     }
+  }
   } else if (warp >= 12) {
     // ================================================================ converters: h^T -> tensor memory, slab flush
+    ft_reg_dec<FT_REGS_CONV>();
     const int q = warp & 3, m = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t kc = 0, scount = 0;
     for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x, ++scount) {
       const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
+#ifndef FT_NO_K
       for (int mt = mt0; mt < mt1; ++mt) {
         for (int p = 0; p < P.n_pass; ++p) {
           const int crow = P.row_cache[p][m];
-          for (int ks = 0; ks < 16; ++ks, ++kc) {
-            const int sl = kc % FT_KSLOTS;
-            float x[8];
-            const int t64 = 2 * mt + (ks >> 3);
-            if (crow >= 0 && t64 < a.n_tiles) {
-              const float4* src = reinterpret_cast<const float4*>(a.cache + (size_t)t64 * tile_c + (size_t)crow * MRL_LDT + (ks & 7) * 8);
-              const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
-              x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
-            } else {
-              const float c = crow == -2 ? 1.f : 0.f;
+          // the 16 k-steps (8 timesteps each) of the tile in groups of four; group g + 1 is requested before group g is
+          // converted, so the L2 latency is covered by the conversion of four k-steps
+          float4 xa[4][2], xb[4][2];
+          auto request = [&](int g4, float4 (&x)[4][2]) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) x[k] = c;
+            for (int i = 0; i < 4; ++i) {
+              const int ks = 4 * g4 + i, t64 = 2 * mt + (ks >> 3);
+              if (crow >= 0 && t64 < a.n_tiles) {
+                const float4* src = reinterpret_cast<const float4*>(a.cache + (size_t)t64 * tile_c + (size_t)crow * MRL_LDT + (ks & 7) * 8);
+                x[i][0] = __ldg(src);
+                x[i][1] = __ldg(src + 1);
+              } else {
+                const float c = crow == -2 ? 1.f : 0.f;
+                x[i][0] = make_float4(c, c, c, c);
+                x[i][1] = x[i][0];
+              }
             }
-            uint32_t hi[8], lo[8];
+          };
+          auto convert = [&](const float4 (&xx)[4][2]) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ft_split(x[k], hi[k], lo[k]);
-            mbar_wait_guard(&kempty[sl], ((kc / FT_KSLOTS) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t ta = tlane + P.kslot_col + 16 * sl;
-            tmem_st8(ta, hi);
-            tmem_st8(ta + 8, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&kconv[sl]);
-          }
+            for (int i = 0; i < 4; ++i, ++kc) {
+              const int sl = kc % FT_KSLOTS;
+              const float x[8] = {xx[i][0].x, xx[i][0].y, xx[i][0].z, xx[i][0].w, xx[i][1].x, xx[i][1].y, xx[i][1].z, xx[i][1].w};
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) ft_split(x[k], hi[k], lo[k]);
+              mbar_wait_sleep(&kempty[sl], ((kc / FT_KSLOTS) & 1) ^ 1);
+              tc_fence_after();
+              const uint32_t ta = tlane + P.kslot_col + 16 * sl;
+              tmem_st8(ta, hi);
+              tmem_st8(ta + 8, lo);
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&kconv[sl]);
+            }
+          };
+          request(0, xa);
+          request(1, xb);
+          convert(xa);
+          request(2, xa);
+          convert(xb);
+          request(3, xb);
+          convert(xa);
+          convert(xb);
         }
       }
+#endif
       // ---- slab flush: accumulator rows -> fp32 slab partial (weights of layers >= 2, their biases from the ones row)
-      mbar_wait_guard(gacc_full, scount & 1);
+      mbar_wait_sleep(gacc_full, scount & 1);
       tc_fence_after();
       float* part = a.partm + (size_t)slab * g.pmid;
       for (int p = 0; p < P.n_pass; ++p) {
@@ -340,8 +380,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       __syncwarp();
       if (lane == 0) mbar_arrive(gacc_empty);
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================================================ epilogue groups: one thread = one timestep
+    ft_reg_inc<FT_REGS_EPI>();
     const int e = (warp - 4) >> 2, q = warp & 3, m = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t ring = tlane + P.ring_col + 64 * e;
@@ -356,9 +397,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
         const bool ok = t64 < a.n_tiles;
         const long long T = (long long)mt * 128 + m;
         const bool valid = T < a.N;
-        const float* cb = a.cache + (size_t)t64 * tile_c + r;      // + feature row * LDT
-        const float* zb = a.Zt + (size_t)t64 * tile_z + r;
-        // ---- stages 0 .. S-1: produce the A operand of stage s in slots of 16 features
+        // Loads are unconditional with immediate offsets: a tile beyond the batch reads the last one (its rows are masked
+        // at the head), features beyond a layer's width read the following rows (finite activations; the buffers have
+        // one zeroed tile of slack) and meet zero weight rows / zero accumulator columns.
+        const int t64c = min(t64, a.n_tiles - 1);
+        const float* cb = a.cache + (size_t)t64c * tile_c + r;      // + feature row * LDT
+        const float* zb = a.Zt + (size_t)t64c * tile_z + r;
+        // ---- stages 0 .. S-1: produce the A operand of stage s in slots of 16 features.  The cached activations (and
+        // x.V_1 in stage 0) of a group's NEXT slot are requested before its current slot is processed, and those of the
+        // first slot before the wait for the previous stage's accumulator: the L2 latency hides behind the work.
         for (int s = 0; s < S; ++s) {
           const FtStage st = P.st[s];
           const int ul = st.ul;                      // layer whose units are produced
@@ -366,9 +413,32 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           const float* hrow = cb + (size_t)g.off_act[ul] * MRL_LDT;
           const float* vbl = vb_s + P.vboff[ul];
           const bool is_head = !st.rfwd && ul == L;
+          const bool need_h = !(is_head && !cat);    // the DiagGauss metric needs no cached row
+          const int nslots = (st.kgs + 1) >> 1;
+          int j = (e - (int)(u & 1)) & 1;            // this group's first slot of the stage
+          u += nslots;
+          float hc[16], zc[16], hn[16], zn[16];
+          auto request = [&](int kg0, float (&hb)[16], float (&zb_)[16]) {
+#ifdef FT_NO_LOADS
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { hb[i] = 0.25f + kg0; zb_[i] = 0.5f; }
+#else
+            if (need_h) {
+              const float* ph = hrow + (size_t)(8 * kg0) * MRL_LDT;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+            }
+            if (s == 0) {
+              const float* pz = zb + (size_t)(8 * kg0) * MRL_LDT;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) zb_[i] = __ldg(pz + i * MRL_LDT);
+            }
+#endif
+          };
+          if (j < nslots) request(2 * j, hc, zc);
           uint32_t src_acc = 0;
           if (s > 0) {
-            mbar_wait_guard(&acc_full[s - 1], tcount & 1);
+            mbar_wait_sleep(&acc_full[s - 1], tcount & 1);
             tc_fence_after();
             src_acc = tlane + P.st[s - 1].acc_col;
           }
@@ -378,10 +448,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
               uint32_t v[16];
               tmem_ld16(src_acc + c0, v);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int f = c0 + j;
+              for (int i = 0; i < 16; ++i) {
+                const int f = c0 + i;
                 const float p = (ok && f < du) ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
-                sdot += p * (__uint_as_float(v[j]) + vbl[f]);
+                sdot += p * (__uint_as_float(v[i]) + vbl[f]);
               }
             }
           }
@@ -390,78 +460,76 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           if (!st.rfwd) {
             pass = P.lay_pass[ul];
             kb = kbuf + P.pass_buf[pass] + (size_t)(P.lay_col[ul] >> 3) * 1024 + (m >> 2) * 32 + (m & 3);
-            if (ul == P.pass_first_l[pass]) mbar_wait_guard(&d_free[pass], (tcount & 1) ^ 1);   // previous tile's (k) MMAs are done
+#ifndef FT_NO_K
+            if (ul == P.pass_first_l[pass]) mbar_wait_sleep(&d_free[pass], (tcount & 1) ^ 1);   // previous tile's (k) MMAs are done
+#endif
           }
-          for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++u) {
-            if ((int)(u & 1) != e) continue;
+          for (; j < nslots; j += 2) {
+            const int kg0 = 2 * j;
             const int nk = min(2, st.kgs - kg0);
+            if (j + 2 < nslots) request(kg0 + 4, hn, zn);
             // unit values of features 8 kg0 .. 8 kg0 + 15
-            float val[16], hh[16];
+            float val[16];
             if (s == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int f = 8 * kg0 + j;
-                const bool in = ok && f < du;
-                const float z = in ? __ldg(zb + (size_t)f * MRL_LDT) : 0.f;
-                hh[j] = in ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
-                val[j] = dact_from_h<ACT>(hh[j]) * (z + vbl[f]);
-              }
+              for (int i = 0; i < 16; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (zc[i] + vbl[8 * kg0 + i]);
             } else {
               uint32_t v[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int f = 8 * kg0 + j;
-                hh[j] = (ok && f < du && !(is_head && !cat)) ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
-              }
               tmem_ld16(src_acc + 8 * kg0, v);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int f = 8 * kg0 + j;
-                const float acc = __uint_as_float(v[j]);
+              for (int i = 0; i < 16; ++i) {
+                const int f = 8 * kg0 + i;
+                const float acc = __uint_as_float(v[i]);
                 float o;
-                if (st.rfwd) o = dact_from_h<ACT>(hh[j]) * (acc + vbl[f]);                     // Rh_ul
+                if (st.rfwd) o = dact_from_h<ACT>(hc[i]) * (acc + vbl[f]);                     // Rh_ul
                 else if (is_head) {
                   const float rz = acc + vbl[f];
-                  o = cat ? hh[j] * (rz - sdot) : rz * ivar_s[f < 64 ? f : 63];               // Fisher metric
+                  o = cat ? hc[i] * (rz - sdot) : rz * ivar_s[f < 64 ? f : 63];               // Fisher metric
                   if (!valid) o = 0.f;
-                } else o = acc * dact_from_h<ACT>(hh[j]);                                      // delta_ul
-                val[j] = (f < du) ? o : 0.f;
+                  if (f >= du) o = 0.f;
+                } else o = acc * dact_from_h<ACT>(hc[i]);                                      // delta_ul
+                val[i] = o;                        // padding features: zero accumulator columns and tangent biases
               }
             }
             if (a.dbg && mt == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < 8 * nk) a.dbg[((size_t)s * 128 + m) * 128 + 8 * kg0 + j] = val[j];
+              for (int i = 0; i < 16; ++i)
+                if (i < 8 * nk) a.dbg[((size_t)s * 128 + m) * 128 + 8 * kg0 + i] = val[i];
             }
-            mbar_wait_guard(&a_empty[e], (ue & 1) ^ 1);
+            mbar_wait_sleep(&a_empty[e], (ue & 1) ^ 1);
             tc_fence_after();
             ++ue;
-            for (int c = 0; c < nk; ++c) {
-              uint32_t hi[8], lo[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) ft_split(val[8 * c + k], hi[k], lo[k]);
-              if (st.rfwd) {
-                tmem_st8(ring + 32 * c, hi);
-                tmem_st8(ring + 32 * c + 8, lo);
-                uint32_t h2[8], l2[8];
+            for (int c = 0; c < 2; ++c) {
+              if (c < nk) {
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ft_split(hh[8 * c + k], h2[k], l2[k]);
-                tmem_st8(ring + 32 * c + 16, h2);
-                tmem_st8(ring + 32 * c + 24, l2);
-              } else {
-                tmem_st8(ring + 16 * c, hi);
-                tmem_st8(ring + 16 * c + 8, lo);
-                // the same delta block as the K-major B operand of the (k) GEMM: [n][timestep], rotated so that the
-                // 32 timesteps of a warp hit 32 distinct banks
-                ft_rot8(hi, rot);
-                ft_rot8(lo, rot);
-                float* kp = kb + (size_t)(kg0 + c) * 1024;
-                const int lo_off = P.pass_N[pass] * 128;
+                for (int k = 0; k < 8; ++k) ft_split(val[8 * c + k], hi[k], lo[k]);
+                if (st.rfwd) {
+                  tmem_st8(ring + 32 * c, hi);
+                  tmem_st8(ring + 32 * c + 8, lo);
+                  uint32_t h2[8], l2[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int nn = ((i + rot) & 7) * 4;
-                  kp[nn] = __uint_as_float(hi[i]);
-                  kp[nn + lo_off] = __uint_as_float(lo[i]);
+                  for (int k = 0; k < 8; ++k) ft_split(hc[8 * c + k], h2[k], l2[k]);
+                  tmem_st8(ring + 32 * c + 16, h2);
+                  tmem_st8(ring + 32 * c + 24, l2);
+                } else {
+                  tmem_st8(ring + 16 * c, hi);
+                  tmem_st8(ring + 16 * c + 8, lo);
+                  // the same delta block as the K-major B operand of the (k) GEMM: [n][timestep], rotated so that the
+                  // 32 timesteps of a warp hit 32 distinct banks
+#ifndef FT_NO_KBUF
+                  ft_rot8(hi, rot);
+                  ft_rot8(lo, rot);
+                  float* kp = kb + (size_t)(kg0 + c) * 1024;
+                  const int lo_off = P.pass_N[pass] * 128;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int nn = ((i + rot) & 7) * 4;
+                    kp[nn] = __uint_as_float(hi[i]);
+                    kp[nn + lo_off] = __uint_as_float(lo[i]);
+                  }
+#endif
                 }
               }
             }
@@ -469,6 +537,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[e]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { hc[i] = hn[i]; zc[i] = zn[i]; }
           }
           if (!st.rfwd && ul == P.pass_last_l[pass]) {     // all delta blocks of the pass are written
             fence_proxy_async();
@@ -478,53 +548,62 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
         }
         // ---- final: delta_1 = d_1' * act'(h_1) -> DG (tcgen05 B operand of the layer-1 gradient) + bias partial sums
         {
-          mbar_wait_guard(&acc_full[S - 1], tcount & 1);
-          tc_fence_after();
-          const uint32_t src_acc = tlane + P.st[S - 1].acc_col;
           const float* hrow = cb + (size_t)g.off_act[1] * MRL_LDT;
           const int d1 = g.d[1], nu = a.nu;
-          float* dgp = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + ((T >> 2) & 1) * (nu * 4) + (T & 3);
-          for (int c0 = 0, jj = 0; c0 < nu; c0 += 16, ++jj) {
-            if ((jj & 1) != e) continue;
-            uint32_t v[16];
-            float hh[16];
+          const int nch = nu >> 4;
+          float hc[16], hn[16];
+          auto request = [&](int c0, float (&hb)[16]) {
+            const float* ph = hrow + (size_t)c0 * MRL_LDT;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hh[j] = (ok && c0 + j < d1) ? __ldg(hrow + (size_t)(c0 + j) * MRL_LDT) : 0.f;
+            for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+          };
+          int jj = e;
+          if (jj < nch) request(16 * jj, hc);
+          mbar_wait_sleep(&acc_full[S - 1], tcount & 1);
+          tc_fence_after();
+          const uint32_t src_acc = tlane + P.st[S - 1].acc_col;
+          float* dgp = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + ((T >> 2) & 1) * (nu * 4) + (T & 3);
+          for (; jj < nch; jj += 2) {
+            const int c0 = 16 * jj;
+            if (jj + 2 < nch) request(c0 + 32, hn);
+            uint32_t v[16];
             tmem_ld16(src_acc + c0, v);
             float val[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              val[j] = (c0 + j < d1) ? __uint_as_float(v[j]) * dact_from_h<ACT>(hh[j]) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+              val[i] = __uint_as_float(v[i]) * dact_from_h<ACT>(hc[i]);     // padding columns of the accumulator are zero
+#ifndef FT_NO_DG
               if (ok) {
                 uint32_t hi, lo;
-                ft_split(val[j], hi, lo);
-                float* p = dgp + ((c0 + j) >> 3) * 32 + ((c0 + j) & 7) * 4;
+                ft_split(val[i], hi, lo);
+                float* p = dgp + ((c0 + i) >> 3) * 32 + ((c0 + i) & 7) * 4;
                 p[0] = __uint_as_float(hi);
                 p[nu * 8] = __uint_as_float(lo);
               }
+#endif
             }
             if (a.dbg && mt == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) a.dbg[((size_t)S * 128 + m) * 128 + c0 + j] = val[j];
+              for (int i = 0; i < 16; ++i) a.dbg[((size_t)S * 128 + m) * 128 + c0 + i] = val[i];
             }
             // column sums over the warp's 32 timesteps: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the pair
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float send = (lane & 16) ? val[j] : val[j + 8];
-              const float keep = (lane & 16) ? val[j + 8] : val[j];
-              val[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            for (int i = 0; i < 8; ++i) {
+              const float send = (lane & 16) ? val[i] : val[i + 8];
+              const float keep = (lane & 16) ? val[i + 8] : val[i];
+              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float send = (lane & 8) ? val[j] : val[j + 4];
-              const float keep = (lane & 8) ? val[j + 4] : val[j];
-              val[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            for (int i = 0; i < 4; ++i) {
+              const float send = (lane & 8) ? val[i] : val[i + 4];
+              const float keep = (lane & 8) ? val[i + 4] : val[i];
+              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float send = (lane & 4) ? val[j] : val[j + 2];
-              const float keep = (lane & 4) ? val[j + 2] : val[j];
-              val[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            for (int i = 0; i < 2; ++i) {
+              const float send = (lane & 4) ? val[i] : val[i + 2];
+              const float keep = (lane & 4) ? val[i + 2] : val[i];
+              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
             {
               const float send = (lane & 2) ? val[0] : val[1];
@@ -537,6 +616,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
               const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
               gb1w[col] += val[0];
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hc[i] = hn[i];
           }
           tc_fence_before();
         }
