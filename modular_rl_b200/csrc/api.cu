@@ -597,6 +597,7 @@ extern "C" int mrl_zfilter_scan(const void* x, int x_dtype, long long N, int d, 
 struct mrl_net {
   int device = 0;
   NetGeom g;
+  DevBuf trace;
   DevBuf WC, VC, dbg;      // tcgen05 Fisher-vector chain: weight images of theta / of the tangent, debug dump
   bool tc_fvp = false;
   DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, img, imgv, vflat, Z1, cache, part1, partm, loss_part, out32,
@@ -654,6 +655,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
       R(n->WC, fvp_tc_image_floats(n->g, 0) * 4);
       R(n->VC, fvp_tc_image_floats(n->g, 1) * 4);
       if (getenv("MRL_FVP_TC_DEBUG")) R(n->dbg, (size_t)8 * 128 * 128 * 4);
+      if (getenv("MRL_FVP_TC_TRACE")) { R(n->trace, (size_t)8 * 4096 * 2 * 8); if (e == cudaSuccess) e = cudaMemset(n->trace.p, 0, (size_t)8 * 4096 * 2 * 8); }
     }
   }
   if (e == cudaSuccess) e = cudaMallocHost(&n->h_scal, 32 * 8);
@@ -671,7 +673,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->WC, &n->VC, &n->dbg, &n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
+  DevBuf* bufs[] = {&n->trace, &n->WC, &n->VC, &n->dbg, &n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->cgscratch, &n->scal,
                     &n->headout, &n->stage};
@@ -883,12 +885,13 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
     x.WC = n->WC.as<float>(); x.VC = n->VC.as<float>(); x.vflat = v_dev; x.img = n->img.as<float>();
     x.Zt = n->Z1.as<float>(); x.cache = n->cache.as<float>(); x.DG = n->DG.as<float>(); x.partm = n->partm.as<float>();
     x.dbg = n->dbg.as<float>();
+    x.trace = n->trace.as<long long>();
     x.N = b->N; x.n_tiles = b->n_tiles; x.slab_tiles = pl.slab_tiles; x.n_slabs = pl.n_slabs;
     CKP(PK_MIDB_FVP, launch_fvp_tc(g, x, st), 1);
   } else if (chain_bwd_shape(g, mode) != 0) CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_chain_backward(g, a, pl.n_slabs, st), 1);
   else CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
-                                pl.slab_tiles, b->n_tiles, pl.n_slabs, st), 1);
+                                pl.slab_tiles, b->n_tiles, pl.n_slabs, st, tc ? 1 : 0), 1);
   const int world = world_of(n);
   // terms that are not sums over timesteps are divided by `world` so that the sum over ranks restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;
@@ -1136,6 +1139,15 @@ extern "C" int mrl_debug_fvp_tc_read(mrl_net* n, float* out) {
   CK(cudaSetDevice(n->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, n->dbg.p, (size_t)8 * 128 * 128 * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int mrl_debug_fvp_tc_trace(mrl_net* n, long long* out) {
+  if (!n || !n->trace.p || !out) return fail("mrl_debug_fvp_tc_trace: trace not enabled (MRL_FVP_TC_TRACE=1)");
+  CK(cudaSetDevice(n->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, n->trace.p, (size_t)8 * 4096 * 2 * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(n->trace.p, 0, (size_t)8 * 4096 * 2 * 8));
   return 0;
 }
 

@@ -27,7 +27,7 @@ size_t l1tc_dg_floats(const NetGeom& g, long long n_tiles);
 cudaError_t launch_pack_xg(const void* src, int dtype, long long ld, int ncols, long long N, float* XG, int xg_ftiles,
                            long long n_tiles, cudaStream_t st);
 cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,
-                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st);
+                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st, int dg_mn_major = 0);
 
 // ---- mlp_mid.cu
 struct MidFwdArgs {
@@ -90,6 +90,7 @@ struct FvpTcArgs {
   float* DG;            // out: delta_1 operand of the layer-1 gradient GEMM
   float* partm;         // out: [n_slabs][pmid]
   float* dbg;           // debug dump of the first 128-timestep tile or nullptr
+  long long* trace;     // pipeline trace of CTA 0 or nullptr
   long long N;
   int n_tiles, slab_tiles /* even */, n_slabs;
 };

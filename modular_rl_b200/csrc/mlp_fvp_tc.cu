@@ -34,29 +34,30 @@
 #include <string.h>
 
 #define FT_THREADS 512
-#define FT_WSTAGES 4          // weight ring stages
+#define FT_RSTAGES 6          // weight ring of the R-forward GEMMs (one k-group of W_l and V_l per stage)
+#define FT_DSTAGES 6          // weight ring of the delta GEMMs (one k-group of a W_l^T column chunk per stage)
 #define FT_KSLOTS 4           // (k) A-operand slots (8 timesteps x one tile = 16 TMEM columns each)
-#define FT_MAX_STAGES 6
+#define FT_MAX_R 3
+#define FT_MAX_D 6
 #define FT_MAX_PASS 3
 #define FT_TMEM_COLS 512
 
-struct FtStage {
-  int rfwd;      // 1: Rz_l = [Rh_{l-1} | h_{l-1}] . [W_l ; V_l]     0: d_{l-1}' = delta_l . W_l^T
-  int l;         // layer of W
-  int ul;        // layer whose units form the A operand (l - 1 for R-forward, l for delta stages)
-  int kgs;       // k-groups (8 features) of the A operand
-  int N;         // MMA N (multiple of 16)
-  int acc_col;   // TMEM column of the accumulator
-  int w_off;     // float offset of the stage's B image in WC
-  int v_off;     // float offset of the tangent image in VC (R-forward stages)
+struct FtRStage {   // Rz_l = [Rh_{l-1} | h_{l-1}] . [W_l ; V_l]
+  int l, kgs, N, acc_col, w_off, v_off;
+};
+struct FtDStage {   // d_{l-1}'[:, col0 : col0 + N] = delta_l . W_l^T[:, chunk]
+  int l, kgs, N, col0, acc_col, w_off;
 };
 struct FtPlan {
-  int L, S;                                  // layers, chain stages = 2 (L - 1)
+  int L, nR, nD;
   int Kg[MRL_MAX_LAYERS + 1], Np[MRL_MAX_LAYERS + 1];   // k-groups (round8 / 8) and MMA N (round16) of layers 1..L
   int vboff[MRL_MAX_LAYERS + 1];             // offset of layer l's tangent bias in the shared-memory copy
-  FtStage st[FT_MAX_STAGES];
-  int ring_col, kslot_col;                   // TMEM columns: chain A ring (2 x 64), (k) A slots (FT_KSLOTS x 16)
-  int wstage_floats;                         // floats per weight ring stage
+  FtRStage rs[FT_MAX_R];
+  FtDStage ds[FT_MAX_D];
+  int dstage_of[MRL_MAX_LAYERS + 1];         // first delta stage with A = delta_l
+  int rz_wait_stage;                         // first R stage of a tile that writes the accumulator region of Rz_L
+  int rring_col, dring_col, kslot_col;       // TMEM columns: R ring (2 x 32), delta ring (2 x 16), (k) A slots (FT_KSLOTS x 16)
+  int rstage_floats, dstage_floats;          // floats per weight ring stage
   int n_pass;                                // (k) tiles
   int pass_N[FT_MAX_PASS], pass_acc[FT_MAX_PASS], pass_buf[FT_MAX_PASS];   // N, TMEM column, float offset of the B buffer
   int pass_first_l[FT_MAX_PASS], pass_last_l[FT_MAX_PASS];                 // first / last produced delta layer (max / min l)
@@ -83,17 +84,34 @@ __device__ __forceinline__ void ft_rot8(uint32_t (&v)[8], int r) {   // v[i] <- 
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = a[i];
 }
-__device__ __forceinline__ void ft_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void ft_dbar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 delta-phase warps
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // Register redistribution between the warp roles (all four warps of a warpgroup execute the same instruction): the
-// launch gives every thread 128 registers (512 threads = the whole register file); the producer / MMA-issuer warps and
-// the converters hand most of theirs back, the epilogue warps - which keep a slot of prefetched activations in
-// registers to hide the L2 latency - take them.
+// launch gives every thread 128 registers (512 threads = the whole register file); the control warps and the
+// converters hand most of theirs back, the epilogue warps - which keep prefetched activations in registers to hide
+// the L2 latency - take them.
 #define FT_REGS_CTRL 40
 #define FT_REGS_CONV 96
 #define FT_REGS_EPI 176
 template <int N> __device__ __forceinline__ void ft_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void ft_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 static_assert(4 * 32 * FT_REGS_CTRL + 4 * 32 * FT_REGS_CONV + 8 * 32 * FT_REGS_EPI <= 65536, "register file");
+
+// Pipeline trace of CTA 0 (experiments: MRL_FVP_TC_TRACE=1, tools/micro/fvp_trace.py): per role, (clock64, code) pairs
+#define FT_TRN 4096
+#define FT_TR(role, code)                                                                        \
+  do {                                                                                           \
+    if (a.trace && blockIdx.x == 0 && trn < FT_TRN) {                                            \
+      a.trace[((size_t)(role) * FT_TRN + trn) * 2] = clock64();                                  \
+      a.trace[((size_t)(role) * FT_TRN + trn) * 2 + 1] = (long long)(code);                      \
+      ++trn;                                                                                     \
+    }                                                                                            \
+  } while (0)
 
 struct FtArgs {
   const float* WC;      // chain weight images of theta
@@ -102,9 +120,10 @@ struct FtArgs {
   const float* logstd;  // theta image logstd block (DiagGauss) or nullptr
   const float* Zt;      // x . V_1, tile-major [tile][d1][LDT]
   const float* cache;   // activations of theta, tile-major [tile][act_rows][LDT]
-  float* DG;            // delta_1 operand of the layer-1 gradient GEMM
+  float* DG;            // delta_1 operand of the layer-1 gradient GEMM, MN-major: [t/8][hi | lo][n/4][8 t][4 n]
   float* partm;         // [n_slabs][pmid]
   float* dbg;           // debug dump of the first tile (nullptr: off)
+  long long* trace;     // pipeline trace of CTA 0 (nullptr: off)
   long long N;
   int n_tiles, n_mtiles, slab_mt, n_slabs, nu;
 };
@@ -113,39 +132,52 @@ template <int ACT>
 __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan P, FtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* w_full = bars;                        // [FT_WSTAGES]
-  uint64_t* w_empty = w_full + FT_WSTAGES;        // [FT_WSTAGES]
-  uint64_t* a_full = w_empty + FT_WSTAGES;        // [2]
-  uint64_t* a_empty = a_full + 2;                 // [2]
-  uint64_t* acc_full = a_empty + 2;               // [FT_MAX_STAGES]
-  uint64_t* kconv = acc_full + FT_MAX_STAGES;     // [FT_KSLOTS]
+  uint64_t* rw_full = bars;                       // [FT_RSTAGES] R weight stage landed
+  uint64_t* rw_empty = rw_full + FT_RSTAGES;      // [FT_RSTAGES]
+  uint64_t* dw_full = rw_empty + FT_RSTAGES;      // [FT_DSTAGES]
+  uint64_t* dw_empty = dw_full + FT_DSTAGES;      // [FT_DSTAGES]
+  uint64_t* ra_full = dw_empty + FT_DSTAGES;      // [2] R ring slot written (4 warps)
+  uint64_t* ra_empty = ra_full + 2;               // [2]
+  uint64_t* da_full = ra_empty + 2;               // [2] delta ring slot
+  uint64_t* da_empty = da_full + 2;               // [2]
+  uint64_t* racc_full = da_empty + 2;             // [FT_MAX_R] accumulator of R stage complete (the last one = Rz_L)
+  uint64_t* dacc_full = racc_full + FT_MAX_R;     // [FT_MAX_D]
+  uint64_t* rz_free = dacc_full + FT_MAX_D;       // [1] the head has read Rz_L (4 warps)
+  uint64_t* kconv = rz_free + 1;                  // [FT_KSLOTS]
   uint64_t* kempty = kconv + FT_KSLOTS;           // [FT_KSLOTS]
-  uint64_t* d_full = kempty + FT_KSLOTS;          // [FT_MAX_PASS]
+  uint64_t* d_full = kempty + FT_KSLOTS;          // [FT_MAX_PASS] delta blocks of a (k) pass in shared memory (4 warps)
   uint64_t* d_free = d_full + FT_MAX_PASS;        // [FT_MAX_PASS]
   uint64_t* gacc_full = d_free + FT_MAX_PASS;     // [1]
   uint64_t* gacc_empty = gacc_full + 1;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gacc_empty + 1);
   float* vb_s = reinterpret_cast<float*>(smem_raw + 512);       // tangent biases [vboff[l] + j], 512 floats
   float* ivar_s = vb_s + 512;                                   // 64 floats
-  float* gb1s = ivar_s + 64;                                    // [8 epilogue warps][128] layer-1 bias partials
-  float* wring = reinterpret_cast<float*>(smem_raw + 8192);     // [FT_WSTAGES][wstage_floats]
-  float* kbuf = wring + (size_t)FT_WSTAGES * P.wstage_floats;   // (k) B operands: per pass [hi | lo][ngroup][32 k-chunks][8][4]
+  float* gb1s = ivar_s + 64;                                    // [4 delta-phase warps][128] layer-1 bias partials
+  float* rring = reinterpret_cast<float*>(smem_raw + 8192);     // [FT_RSTAGES][rstage_floats]
+  float* dring = rring + (size_t)FT_RSTAGES * P.rstage_floats;  // [FT_DSTAGES][dstage_floats]
+  float* kbuf = dring + (size_t)FT_DSTAGES * P.dstage_floats;   // (k) B operands: per pass [hi | lo][ngroup][32 k-chunks][8][4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = P.L, S = P.S;
+  const int L = P.L, nR = P.nR, nD = P.nD;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < FT_WSTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < FT_MAX_STAGES; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < FT_RSTAGES; ++i) { mbar_init(&rw_full[i], 1); mbar_init(&rw_empty[i], 1); }
+    for (int i = 0; i < FT_DSTAGES; ++i) { mbar_init(&dw_full[i], 1); mbar_init(&dw_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ra_full[i], 4); mbar_init(&ra_empty[i], 1);
+      mbar_init(&da_full[i], 4); mbar_init(&da_empty[i], 1);
+    }
+    for (int i = 0; i < FT_MAX_R; ++i) mbar_init(&racc_full[i], 1);
+    for (int i = 0; i < FT_MAX_D; ++i) mbar_init(&dacc_full[i], 1);
+    mbar_init(rz_free, 4);
     for (int i = 0; i < FT_KSLOTS; ++i) { mbar_init(&kconv[i], 4); mbar_init(&kempty[i], 1); }
-    for (int i = 0; i < FT_MAX_PASS; ++i) { mbar_init(&d_full[i], 8); mbar_init(&d_free[i], 1); }
+    for (int i = 0; i < FT_MAX_PASS; ++i) { mbar_init(&d_full[i], 4); mbar_init(&d_free[i], 1); }
     mbar_init(gacc_full, 1);
     mbar_init(gacc_empty, 4);
     fence_barrier_init();
   }
   // tangent biases, 1/sigma^2, zeroed bias partials and (k) operand buffers (their padding columns stay zero)
   for (int i = threadIdx.x; i < 512; i += FT_THREADS) vb_s[i] = 0.f;
-  for (int i = threadIdx.x; i < 8 * 128; i += FT_THREADS) gb1s[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 128; i += FT_THREADS) gb1s[i] = 0.f;
   for (int i = threadIdx.x; i < P.kbuf_floats; i += FT_THREADS) kbuf[i] = 0.f;
   __syncthreads();
   for (int l = 1; l <= L; ++l)
@@ -164,107 +196,163 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
   const uint32_t tmem_base = *tmem_slot;
   const size_t tile_c = (size_t)g.act_rows * MRL_LDT;   // floats per 64-timestep cache tile
   const size_t tile_z = (size_t)g.d[1] * MRL_LDT;
+  // tiles of this CTA, in order: slabs blockIdx.x, + gridDim.x, ...; every role walks the same sequence
+#define FT_FOR_TILES(...)                                                                    \
+  for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {                         \
+    const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);                \
+    for (int mt = mt0; mt < mt1; ++mt) { __VA_ARGS__ }                                       \
+  }
 
   if (warp < 4) {
   ft_reg_dec<FT_REGS_CTRL>();
   if (warp == 0) {
-    // ================================================================ producer: weight ring + L2 prefetch
+    // ================================================================ producer: both weight rings + L2 prefetch
+    // The two rings drain at unrelated rates (R phase of tile i + 1 next to the delta phase of tile i), so the one
+    // producer thread never blocks on either: it probes both and refills whichever has a free stage.
     if (lane == 0) {
-      uint32_t wc = 0;
-      for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
-        const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
-        for (int mt = mt0; mt < mt1; ++mt) {
-          if (mt + 1 < mt1) {   // next tile's activations and x.V_1 into L2 while this one computes
-            const int t0 = 2 * (mt + 1), nt = min(2, a.n_tiles - t0);
-            if (nt > 0) {
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.cache + (size_t)t0 * tile_c),
-                           "r"((uint32_t)(nt * tile_c * 4)) : "memory");
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Zt + (size_t)t0 * tile_z),
-                           "r"((uint32_t)(nt * tile_z * 4)) : "memory");
-            }
-          }
-          for (int s = 0; s < S; ++s) {
-            const FtStage st = P.st[s];
-            const int kgf = 2 * st.N * 8;                       // floats per k-group of one image
-            for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc) {
-              const int nk = min(2, st.kgs - kg0);
-              const int ws = wc % FT_WSTAGES;
-              mbar_wait_sleep(&w_empty[ws], ((wc / FT_WSTAGES) & 1) ^ 1);
-              float* dst = wring + (size_t)ws * P.wstage_floats;
-              const uint32_t bytes = (uint32_t)(nk * kgf * 4);
-              mbar_expect_tx(&w_full[ws], st.rfwd ? 2 * bytes : bytes);
-              bulk_g2s(dst, a.WC + st.w_off + (size_t)kg0 * kgf, bytes, &w_full[ws]);
-              if (st.rfwd) bulk_g2s(dst + 2 * kgf, a.VC + st.v_off + (size_t)kg0 * kgf, bytes, &w_full[ws]);
-            }
+      long long total_tiles = 0;
+      for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x)
+        total_tiles += min(slab * a.slab_mt + a.slab_mt, a.n_mtiles) - slab * a.slab_mt;
+      int r_per = 0, d_per = 0;                      // ring stages per tile
+      for (int r = 0; r < nR; ++r) r_per += P.rs[r].kgs;
+      for (int k = 0; k < nD; ++k) d_per += P.ds[k].kgs;
+      long long r_left = total_tiles * r_per, d_left = total_tiles * d_per;
+      uint32_t rc = 0, dc = 0;                       // stages issued so far
+      int rst = 0, rkg = 0, dst_ = 0, dkg = 0;       // position inside the tile
+      // L2 prefetch of the activations, one tile ahead of the R phase
+      int pf_slab = blockIdx.x, pf_mt = blockIdx.x * a.slab_mt;
+      long long r_tiles_done = 0;
+      auto prefetch_next = [&]() {
+        // advance to the tile after the one the R ring is about to work on
+        int mt = pf_mt + 1, slab = pf_slab;
+        if (mt >= min(slab * a.slab_mt + a.slab_mt, a.n_mtiles)) { slab += gridDim.x; mt = slab * a.slab_mt; }
+        pf_slab = slab; pf_mt = mt;
+        if (slab >= a.n_slabs) return;
+        const int t0 = 2 * mt, nt = min(2, a.n_tiles - t0);
+        if (nt <= 0) return;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.cache + (size_t)t0 * tile_c),
+                     "r"((uint32_t)(nt * tile_c * 4)) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Zt + (size_t)t0 * tile_z),
+                     "r"((uint32_t)(nt * tile_z * 4)) : "memory");
+      };
+      (void)r_tiles_done;
+      while (r_left > 0 || d_left > 0) {
+        bool progressed = false;
+        if (r_left > 0) {
+          const int ws = rc % FT_RSTAGES;
+          if (mbar_probe(&rw_empty[ws], ((rc / FT_RSTAGES) & 1) ^ 1)) {
+            const FtRStage st = P.rs[rst];
+            const int kgf = 2 * st.N * 8;                       // floats per k-group of one image (hi | lo)
+            float* dst = rring + (size_t)ws * P.rstage_floats;
+            mbar_expect_tx(&rw_full[ws], 2u * kgf * 4u);
+            bulk_g2s(dst, a.WC + st.w_off + (size_t)rkg * kgf, kgf * 4u, &rw_full[ws]);
+            bulk_g2s(dst + kgf, a.VC + st.v_off + (size_t)rkg * kgf, kgf * 4u, &rw_full[ws]);
+            if (rst == 0 && rkg == 0) prefetch_next();
+            ++rc; --r_left; progressed = true;
+            if (++rkg == st.kgs) { rkg = 0; if (++rst == nR) rst = 0; }
           }
         }
+        if (d_left > 0) {
+          const int ws = dc % FT_DSTAGES;
+          if (mbar_probe(&dw_empty[ws], ((dc / FT_DSTAGES) & 1) ^ 1)) {
+            const FtDStage st = P.ds[dst_];
+            const int kgf = 2 * st.N * 8;
+            mbar_expect_tx(&dw_full[ws], kgf * 4u);
+            bulk_g2s(dring + (size_t)ws * P.dstage_floats, a.WC + st.w_off + (size_t)dkg * kgf, kgf * 4u, &dw_full[ws]);
+            ++dc; --d_left; progressed = true;
+            if (++dkg == st.kgs) { dkg = 0; if (++dst_ == nD) dst_ = 0; }
+          }
+        }
+        if (!progressed) __nanosleep(100);
       }
     }
   } else if (warp == 1) {
-    // ================================================================ chain MMA issuer
+    // ================================================================ R-phase MMA issuer
     const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
-    const uint32_t wring_u32 = smem_u32(wring);
+    const uint32_t ring_u32 = smem_u32(rring);
     uint32_t wc = 0, u = 0, tcount = 0;
-    for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
-      const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
-      for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
-        for (int s = 0; s < S; ++s) {
-          const FtStage st = P.st[s];
-          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(st.N >> 3) << 17) | ((128u >> 4) << 24);
-          const uint32_t lbo = (uint32_t)st.N * 16u;          // bytes between the two K halves of a B k-group
-          const uint32_t kgb = (uint32_t)st.N * 64u;          // bytes per k-group of one image (hi | lo)
-          const uint32_t d_tmem = tmem_base + st.acc_col;
-          for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc, ++u) {
-            const int nk = min(2, st.kgs - kg0);
-            const int ws = wc % FT_WSTAGES, e = u & 1;
-            mbar_wait_sleep(&w_full[ws], (wc / FT_WSTAGES) & 1);
-            mbar_wait_sleep(&a_full[e], (u >> 1) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t bw = umma_desc_lo(wring_u32 + (uint32_t)ws * (uint32_t)P.wstage_floats * 4u, lbo);
-              const uint32_t ta = tmem_base + P.ring_col + 64 * e;
-              for (int c = 0; c < nk; ++c) {
-                const uint32_t first = (kg0 + c) ? 1u : 0u;
-                if (st.rfwd) {
-                  const uint32_t tr = ta + 32 * c, th = tr + 16;                 // [Rh hi 8 | Rh lo 8 | h hi 8 | h lo 8]
-                  const uint32_t bW = bw + ((c * kgb) >> 4), bV = bw + ((2 * kgb + c * kgb) >> 4);
-                  umma_tf32_ts(d_tmem, tr + 8, bW, desc_hi, idesc, first);               // Rh_lo . W_hi
-                  umma_tf32_ts(d_tmem, tr, bW + (kgb >> 5), desc_hi, idesc, 1u);         // Rh_hi . W_lo
-                  umma_tf32_ts(d_tmem, tr, bW, desc_hi, idesc, 1u);                      // Rh_hi . W_hi
-                  umma_tf32_ts(d_tmem, th + 8, bV, desc_hi, idesc, 1u);                  // h_lo . V_hi
-                  umma_tf32_ts(d_tmem, th, bV + (kgb >> 5), desc_hi, idesc, 1u);         // h_hi . V_lo
-                  umma_tf32_ts(d_tmem, th, bV, desc_hi, idesc, 1u);                      // h_hi . V_hi
-                } else {
-                  const uint32_t td = ta + 16 * c;                                       // [delta hi 8 | delta lo 8]
-                  const uint32_t bW = bw + ((c * kgb) >> 4);
-                  umma_tf32_ts(d_tmem, td + 8, bW, desc_hi, idesc, first);
-                  umma_tf32_ts(d_tmem, td, bW + (kgb >> 5), desc_hi, idesc, 1u);
-                  umma_tf32_ts(d_tmem, td, bW, desc_hi, idesc, 1u);
-                }
-              }
-              tc_commit(&a_empty[e]);
-              tc_commit(&w_empty[ws]);
-              if (kg0 + 2 >= st.kgs) tc_commit(&acc_full[s]);
-            }
-            __syncwarp();
+    int trn = 0;
+    FT_FOR_TILES(
+      for (int r = 0; r < nR; ++r) {
+        const FtRStage st = P.rs[r];
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(st.N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t lbo = (uint32_t)st.N * 16u;          // bytes between the two K halves of a B k-group
+        const uint32_t kgb = (uint32_t)st.N * 64u;          // bytes per k-group of one image (hi | lo)
+        const uint32_t d_tmem = tmem_base + st.acc_col;
+        if (r == P.rz_wait_stage) {                         // the previous tile's Rz_L lives in this region until the head has read it
+          mbar_wait_sleep(rz_free, (tcount & 1) ^ 1);
+          tc_fence_after();
+        }
+        for (int kg = 0; kg < st.kgs; ++kg, ++wc, ++u) {
+          const int ws = wc % FT_RSTAGES, e = u & 1;
+          mbar_wait_sleep(&rw_full[ws], (wc / FT_RSTAGES) & 1);
+          if (lane == 0) FT_TR(0, (1 << 24) | (r << 8) | kg);
+          mbar_wait_sleep(&ra_full[e], (u >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) FT_TR(0, (2 << 24) | (r << 8) | kg);
+          if (elect_one()) {
+            const uint32_t bW = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.rstage_floats * 4u, lbo);
+            const uint32_t bV = bW + (kgb >> 4);
+            const uint32_t tr = tmem_base + P.rring_col + 32 * e, th = tr + 16;   // [Rh hi 8 | Rh lo 8 | h hi 8 | h lo 8]
+            umma_tf32_ts(d_tmem, tr + 8, bW, desc_hi, idesc, kg ? 1u : 0u);        // Rh_lo . W_hi
+            umma_tf32_ts(d_tmem, tr, bW + (kgb >> 5), desc_hi, idesc, 1u);         // Rh_hi . W_lo
+            umma_tf32_ts(d_tmem, tr, bW, desc_hi, idesc, 1u);                      // Rh_hi . W_hi
+            umma_tf32_ts(d_tmem, th + 8, bV, desc_hi, idesc, 1u);                  // h_lo . V_hi
+            umma_tf32_ts(d_tmem, th, bV + (kgb >> 5), desc_hi, idesc, 1u);         // h_hi . V_lo
+            umma_tf32_ts(d_tmem, th, bV, desc_hi, idesc, 1u);                      // h_hi . V_hi
+            tc_commit(&ra_empty[e]);
+            tc_commit(&rw_empty[ws]);
+            if (kg + 1 == st.kgs) tc_commit(&racc_full[r]);
           }
+          __syncwarp();
         }
       }
-    }
+      ++tcount;
+    )
   } else if (warp == 2) {
+    // ================================================================ delta-phase MMA issuer
+    const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+    const uint32_t ring_u32 = smem_u32(dring);
+    uint32_t wc = 0, u = 0;
+    int trn = 0;
+    FT_FOR_TILES(
+      for (int k = 0; k < nD; ++k) {
+        const FtDStage st = P.ds[k];
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(st.N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t lbo = (uint32_t)st.N * 16u;
+        const uint32_t kgb = (uint32_t)st.N * 64u;
+        const uint32_t d_tmem = tmem_base + st.acc_col;
+        for (int kg = 0; kg < st.kgs; ++kg, ++wc, ++u) {
+          const int ws = wc % FT_DSTAGES, e = u & 1;
+          mbar_wait_sleep(&dw_full[ws], (wc / FT_DSTAGES) & 1);
+          if (lane == 0) FT_TR(1, (1 << 24) | (k << 8) | kg);
+          mbar_wait_sleep(&da_full[e], (u >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) FT_TR(1, (2 << 24) | (k << 8) | kg);
+          if (elect_one()) {
+            const uint32_t bW = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.dstage_floats * 4u, lbo);
+            const uint32_t td = tmem_base + P.dring_col + 16 * e;                  // [delta hi 8 | delta lo 8]
+            umma_tf32_ts(d_tmem, td + 8, bW, desc_hi, idesc, kg ? 1u : 0u);
+            umma_tf32_ts(d_tmem, td, bW + (kgb >> 5), desc_hi, idesc, 1u);
+            umma_tf32_ts(d_tmem, td, bW, desc_hi, idesc, 1u);
+            tc_commit(&da_empty[e]);
+            tc_commit(&dw_empty[ws]);
+            if (kg + 1 == st.kgs) tc_commit(&dacc_full[k]);
+          }
+          __syncwarp();
+        }
+      }
+    )
+  } else {
     // ================================================================ (k) MMA issuer: G tiles += h^T delta over the slab
     const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 4096) >> 32);   // SBO = 32 k-chunks x 128 B between n-groups
     const uint32_t kbuf_u32 = smem_u32(kbuf);
     uint32_t kc = 0, tcount = 0, scount = 0;
+    int trn = 0;
     for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x, ++scount) {
       const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
       mbar_wait_sleep(gacc_empty, (scount & 1) ^ 1);      // the previous slab's accumulators have been flushed
       tc_fence_after();
-#ifdef FT_NO_K
-      if (elect_one()) tc_commit(gacc_full);
-      __syncwarp();
-      continue;
-#endif
       for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
         for (int p = 0; p < P.n_pass; ++p) {
           const int Np_ = P.pass_N[p];
@@ -273,10 +361,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           const uint32_t bbase = umma_desc_lo(kbuf_u32 + (uint32_t)P.pass_buf[p] * 4u, 128);   // LBO = 128 B: adjacent k-chunks
           const uint32_t lo_off = ((uint32_t)Np_ * 512u) >> 4;                                  // lo half of the buffer
           mbar_wait_sleep(&d_full[p], tcount & 1);          // this tile's delta blocks of the pass are in shared memory
+          if (lane == 0) FT_TR(2, (1 << 24) | (p << 8));
           for (int ks = 0; ks < 16; ++ks, ++kc) {
             const int sl = kc % FT_KSLOTS;
             mbar_wait_sleep(&kconv[sl], (kc / FT_KSLOTS) & 1);
             tc_fence_after();
+            if (lane == 0) FT_TR(2, (2 << 24) | (p << 8) | ks);
             if (elect_one()) {
               const uint32_t ta = tmem_base + P.kslot_col + 16 * sl;     // [h^T hi 8 | lo 8]
               const uint32_t db = bbase + ((uint32_t)ks * 256u >> 4);
@@ -300,12 +390,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
     const int q = warp & 3, m = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t kc = 0, scount = 0;
+    int trn = 0;
     for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x, ++scount) {
       const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
-#ifndef FT_NO_K
       for (int mt = mt0; mt < mt1; ++mt) {
         for (int p = 0; p < P.n_pass; ++p) {
           const int crow = P.row_cache[p][m];
+          if (warp == 12 && lane == 0) FT_TR(5, (1 << 24) | (p << 8));
           // the 16 k-steps (8 timesteps each) of the tile in groups of four; group g + 1 is requested before group g is
           // converted, so the L2 latency is covered by the conversion of four k-steps
           float4 xa[4][2], xb[4][2];
@@ -351,9 +442,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           request(3, xb);
           convert(xa);
           convert(xb);
+          if (warp == 12 && lane == 0) FT_TR(5, (2 << 24) | (p << 8));
         }
       }
-#endif
       // ---- slab flush: accumulator rows -> fp32 slab partial (weights of layers >= 2, their biases from the ones row)
       mbar_wait_sleep(gacc_full, scount & 1);
       tc_fence_after();
@@ -381,263 +472,317 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       if (lane == 0) mbar_arrive(gacc_empty);
     }
   } else {
-    // ================================================================ epilogue groups: one thread = one timestep
     ft_reg_inc<FT_REGS_EPI>();
-    const int e = (warp - 4) >> 2, q = warp & 3, m = q * 32 + lane;
+    const int q = warp & 3, m = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t ring = tlane + P.ring_col + 64 * e;
-    float* gb1w = gb1s + ((warp - 4) * 128);
-    const int rot = (m >> 2) & 7;
-    uint32_t u = 0, ue = 0, tcount = 0;
-    const bool cat = g.head == MRL_HEAD_CAT;
-    for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
-      const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
-      for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
-        const int t64 = 2 * mt + (m >> 6), r = m & 63;
-        const bool ok = t64 < a.n_tiles;
-        const long long T = (long long)mt * 128 + m;
-        const bool valid = T < a.N;
-        // Loads are unconditional with immediate offsets: a tile beyond the batch reads the last one (its rows are masked
-        // at the head), features beyond a layer's width read the following rows (finite activations; the buffers have
-        // one zeroed tile of slack) and meet zero weight rows / zero accumulator columns.
-        const int t64c = min(t64, a.n_tiles - 1);
-        const float* cb = a.cache + (size_t)t64c * tile_c + r;      // + feature row * LDT
-        const float* zb = a.Zt + (size_t)t64c * tile_z + r;
-        // ---- stages 0 .. S-1: produce the A operand of stage s in slots of 16 features.  The cached activations (and
-        // x.V_1 in stage 0) of a group's NEXT slot are requested before its current slot is processed, and those of the
-        // first slot before the wait for the previous stage's accumulator: the L2 latency hides behind the work.
-        for (int s = 0; s < S; ++s) {
-          const FtStage st = P.st[s];
-          const int ul = st.ul;                      // layer whose units are produced
-          const int du = g.d[ul];
+    if (warp < 8) {
+      // ============================================================== R-phase epilogue: one thread = one timestep
+      // Produces the A operand [Rh_ul | h_ul] of R stage r, one k-group (8 features) per ring slot.  The cached
+      // activations (and x.V_1 for layer 1) of the NEXT k-group are requested before the current one is processed,
+      // those of the first k-group before the wait for the previous stage's accumulator.
+      uint32_t u = 0, tcount = 0;
+      int trn = 0;
+      const bool tr_on = warp == 4 && lane == 0;
+      FT_FOR_TILES(
+        const int t64c = min(2 * mt + (m >> 6), a.n_tiles - 1);      // a tile beyond the batch reads the last one (masked at the head)
+        const float* cb = a.cache + (size_t)t64c * tile_c + (m & 63);
+        const float* zb = a.Zt + (size_t)t64c * tile_z + (m & 63);
+        for (int r = 0; r < nR; ++r) {
+          const int ul = r + 1, kgs = P.rs[r].kgs;
           const float* hrow = cb + (size_t)g.off_act[ul] * MRL_LDT;
           const float* vbl = vb_s + P.vboff[ul];
-          const bool is_head = !st.rfwd && ul == L;
-          const bool need_h = !(is_head && !cat);    // the DiagGauss metric needs no cached row
-          const int nslots = (st.kgs + 1) >> 1;
-          int j = (e - (int)(u & 1)) & 1;            // this group's first slot of the stage
-          u += nslots;
-          float hc[16], zc[16], hn[16], zn[16];
-          auto request = [&](int kg0, float (&hb)[16], float (&zb_)[16]) {
-#ifdef FT_NO_LOADS
+          float hc[8], zc[8], hn[8], zn[8];
+          auto request = [&](int kg, float (&hb)[8], float (&zz)[8]) {
+            const float* ph = hrow + (size_t)(8 * kg) * MRL_LDT;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { hb[i] = 0.25f + kg0; zb_[i] = 0.5f; }
-#else
-            if (need_h) {
-              const float* ph = hrow + (size_t)(8 * kg0) * MRL_LDT;
+            for (int i = 0; i < 8; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+            if (r == 0) {
+              const float* pz = zb + (size_t)(8 * kg) * MRL_LDT;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+              for (int i = 0; i < 8; ++i) zz[i] = __ldg(pz + i * MRL_LDT);
             }
-            if (s == 0) {
-              const float* pz = zb + (size_t)(8 * kg0) * MRL_LDT;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) zb_[i] = __ldg(pz + i * MRL_LDT);
-            }
-#endif
           };
-          if (j < nslots) request(2 * j, hc, zc);
+          request(0, hc, zc);
           uint32_t src_acc = 0;
-          if (s > 0) {
-            mbar_wait_sleep(&acc_full[s - 1], tcount & 1);
+          if (tr_on) FT_TR(3, (1 << 24) | (r << 8));
+          if (r > 0) {
+            mbar_wait_sleep(&racc_full[r - 1], tcount & 1);
             tc_fence_after();
-            src_acc = tlane + P.st[s - 1].acc_col;
+            src_acc = tlane + P.rs[r - 1].acc_col;
           }
-          float sdot = 0.f;     // Categorical: p . Rz over the whole row
-          if (is_head && cat) {
-            for (int c0 = 0; c0 < P.Np[L]; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(src_acc + c0, v);
+          if (tr_on) FT_TR(3, (2 << 24) | (r << 8));
+          for (int kg = 0; kg < kgs; ++kg, ++u) {
+            if (kg + 1 < kgs) request(kg + 1, hn, zn);
+            float val[8];
+            if (r == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int f = c0 + i;
-                const float p = (ok && f < du) ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
-                sdot += p * (__uint_as_float(v[i]) + vbl[f]);
-              }
-            }
-          }
-          int pass = -1;
-          float* kb = nullptr;
-          if (!st.rfwd) {
-            pass = P.lay_pass[ul];
-            kb = kbuf + P.pass_buf[pass] + (size_t)(P.lay_col[ul] >> 3) * 1024 + (m >> 2) * 32 + (m & 3);
-#ifndef FT_NO_K
-            if (ul == P.pass_first_l[pass]) mbar_wait_sleep(&d_free[pass], (tcount & 1) ^ 1);   // previous tile's (k) MMAs are done
-#endif
-          }
-          for (; j < nslots; j += 2) {
-            const int kg0 = 2 * j;
-            const int nk = min(2, st.kgs - kg0);
-            if (j + 2 < nslots) request(kg0 + 4, hn, zn);
-            // unit values of features 8 kg0 .. 8 kg0 + 15
-            float val[16];
-            if (s == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (zc[i] + vbl[8 * kg0 + i]);
+              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (zc[i] + vbl[8 * kg + i]);
             } else {
-              uint32_t v[16];
-              tmem_ld16(src_acc + 8 * kg0, v);
+              uint32_t v[8];
+              tmem_ld8(src_acc + 8 * kg, v);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int f = 8 * kg0 + i;
-                const float acc = __uint_as_float(v[i]);
-                float o;
-                if (st.rfwd) o = dact_from_h<ACT>(hc[i]) * (acc + vbl[f]);                     // Rh_ul
-                else if (is_head) {
-                  const float rz = acc + vbl[f];
-                  o = cat ? hc[i] * (rz - sdot) : rz * ivar_s[f < 64 ? f : 63];               // Fisher metric
-                  if (!valid) o = 0.f;
-                  if (f >= du) o = 0.f;
-                } else o = acc * dact_from_h<ACT>(hc[i]);                                      // delta_ul
-                val[i] = o;                        // padding features: zero accumulator columns and tangent biases
-              }
+              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (__uint_as_float(v[i]) + vbl[8 * kg + i]);
             }
             if (a.dbg && mt == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < 8 * nk) a.dbg[((size_t)s * 128 + m) * 128 + 8 * kg0 + i] = val[i];
+              for (int i = 0; i < 8; ++i) a.dbg[((size_t)r * 128 + m) * 128 + 8 * kg + i] = val[i];
             }
-            mbar_wait_sleep(&a_empty[e], (ue & 1) ^ 1);
-            tc_fence_after();
-            ++ue;
+            uint32_t hi[8], lo[8], h2[8], l2[8];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (c < nk) {
+            for (int i = 0; i < 8; ++i) { ft_split(val[i], hi[i], lo[i]); ft_split(hc[i], h2[i], l2[i]); }
+            const int e = u & 1;
+            if (tr_on) FT_TR(3, (3 << 24) | (r << 8) | kg);
+            mbar_wait_sleep(&ra_empty[e], ((u >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (tr_on) FT_TR(3, (4 << 24) | (r << 8) | kg);
+            const uint32_t ring = tlane + P.rring_col + 32 * e;
+            tmem_st8(ring, hi);
+            tmem_st8(ring + 8, lo);
+            tmem_st8(ring + 16, h2);
+            tmem_st8(ring + 24, l2);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ra_full[e]);
+            if (tr_on) FT_TR(3, (5 << 24) | (r << 8) | kg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; zc[i] = zn[i]; }
+          }
+        }
+        ++tcount;
+      )
+    } else {
+      // ============================================================== delta-phase epilogue: one thread = one timestep
+      // head metric -> delta_L, delta_l = d_l' * act'(h_l) (l = L-1 .. 2), delta_1 -> DG + layer-1 bias partial sums.
+      // delta_l (l >= 2) goes to the delta ring (A operand of the next GEMM) and, as the K-major B operand of the (k)
+      // GEMM, to shared memory.  When the last GEMM is split into column chunks, delta_2 is produced once per chunk.
+      const int dw = warp - 8;
+      float* gb1w = gb1s + dw * 128;
+      const int rot = (m >> 2) & 7;
+      const bool cat = g.head == MRL_HEAD_CAT;
+      const int nu = a.nu;
+      uint32_t u = 0, tcount = 0;
+      int trn = 0;
+      const bool tr_on = warp == 8 && lane == 0;
+      for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
+        const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
+        for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
+          const int t64 = 2 * mt + (m >> 6);
+          const bool ok = t64 < a.n_tiles;
+          const int t64c = min(t64, a.n_tiles - 1);
+          const long long T = (long long)mt * 128 + m;
+          const bool valid = T < a.N;
+          const float* cb = a.cache + (size_t)t64c * tile_c + (m & 63);
+          int k = 0;                                           // delta stage index
+          for (int l = L; l >= 2; --l) {
+            // chunks of the GEMM that consumes delta_l: one stage, except for the last layer when N_1 > 64
+            int nchunk = 0;
+            while (k + nchunk < nD && P.ds[k + nchunk].l == l) ++nchunk;
+            const int du = g.d[l], kgs = P.Kg[l];
+            const float* hrow = cb + (size_t)g.off_act[l] * MRL_LDT;
+            const float* vbl = vb_s + P.vboff[l];
+            const bool is_head = l == L;
+            const bool need_h = !(is_head && !cat);
+            const int pass = P.lay_pass[l];
+            float* kb = kbuf + P.pass_buf[pass] + (size_t)(P.lay_col[l] >> 3) * 1024 + (m >> 2) * 32 + (m & 3);
+            const int lo_off = P.pass_N[pass] * 128;
+            for (int c = 0; c < nchunk; ++c, ++k) {
+              float hc[8], hn[8];
+              auto request = [&](int kg, float (&hb)[8]) {
+                if (need_h) {
+                  const float* ph = hrow + (size_t)(8 * kg) * MRL_LDT;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+                }
+              };
+              request(0, hc);
+              uint32_t src_acc;
+              if (tr_on) FT_TR(4, (1 << 24) | (l << 8) | c);
+              if (c == 0) {
+                if (is_head) {
+                  mbar_wait_sleep(&racc_full[nR - 1], tcount & 1);
+                  src_acc = tlane + P.rs[nR - 1].acc_col;
+                } else {
+                  mbar_wait_sleep(&dacc_full[k - 1], tcount & 1);
+                  src_acc = tlane + P.ds[k - 1].acc_col;
+                }
+                tc_fence_after();
+                if (l == P.pass_first_l[pass]) mbar_wait_sleep(&d_free[pass], (tcount & 1) ^ 1);   // previous tile's (k) MMAs are done
+              } else {
+                src_acc = tlane + (is_head ? P.rs[nR - 1].acc_col : P.ds[k - c - 1].acc_col);
+              }
+              if (tr_on) FT_TR(4, (2 << 24) | (l << 8) | c);
+              float sdot = 0.f;     // Categorical: p . Rz over the whole row
+              if (is_head && cat) {
+                for (int c0 = 0; c0 < P.Np[L]; c0 += 16) {
+                  uint32_t v[16];
+                  tmem_ld16(src_acc + c0, v);
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int f = c0 + i;
+                    const float p = f < du ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
+                    sdot += p * (__uint_as_float(v[i]) + vbl[f]);
+                  }
+                }
+              }
+              for (int kg = 0; kg < kgs; ++kg, ++u) {
+                if (kg + 1 < kgs) request(kg + 1, hn);
+                uint32_t v[8];
+                tmem_ld8(src_acc + 8 * kg, v);
+                float val[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int f = 8 * kg + i;
+                  const float acc = __uint_as_float(v[i]);
+                  float o;
+                  if (is_head) {
+                    const float rz = acc + vbl[f];
+                    o = cat ? hc[i] * (rz - sdot) : rz * ivar_s[f < 64 ? f : 63];      // Fisher metric
+                    if (!valid || f >= du) o = 0.f;
+                  } else o = acc * dact_from_h<ACT>(hc[i]);                            // padding columns: zero accumulator
+                  val[i] = o;
+                }
+                if (a.dbg && mt == 0 && c == 0) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) a.dbg[((size_t)(nR + L - l) * 128 + m) * 128 + 8 * kg + i] = val[i];
+                }
                 uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ft_split(val[8 * c + k], hi[k], lo[k]);
-                if (st.rfwd) {
-                  tmem_st8(ring + 32 * c, hi);
-                  tmem_st8(ring + 32 * c + 8, lo);
-                  uint32_t h2[8], l2[8];
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) ft_split(hc[8 * c + k], h2[k], l2[k]);
-                  tmem_st8(ring + 32 * c + 16, h2);
-                  tmem_st8(ring + 32 * c + 24, l2);
-                } else {
-                  tmem_st8(ring + 16 * c, hi);
-                  tmem_st8(ring + 16 * c + 8, lo);
-                  // the same delta block as the K-major B operand of the (k) GEMM: [n][timestep], rotated so that the
-                  // 32 timesteps of a warp hit 32 distinct banks
-#ifndef FT_NO_KBUF
+                for (int i = 0; i < 8; ++i) ft_split(val[i], hi[i], lo[i]);
+                const int e = u & 1;
+                if (tr_on) FT_TR(4, (3 << 24) | (l << 8) | kg);
+                mbar_wait_sleep(&da_empty[e], ((u >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (tr_on) FT_TR(4, (4 << 24) | (l << 8) | kg);
+                const uint32_t ring = tlane + P.dring_col + 16 * e;
+                tmem_st8(ring, hi);
+                tmem_st8(ring + 8, lo);
+                if (c == 0) {
+                  // the same block as the K-major B operand of the (k) GEMM: [n][timestep], rotated so that the 32
+                  // timesteps of a warp hit 32 distinct banks
                   ft_rot8(hi, rot);
                   ft_rot8(lo, rot);
-                  float* kp = kb + (size_t)(kg0 + c) * 1024;
-                  const int lo_off = P.pass_N[pass] * 128;
+                  float* kp = kb + (size_t)kg * 1024;
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const int nn = ((i + rot) & 7) * 4;
                     kp[nn] = __uint_as_float(hi[i]);
                     kp[nn + lo_off] = __uint_as_float(lo[i]);
                   }
-#endif
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&da_full[e]);
+                if (tr_on) FT_TR(4, (5 << 24) | (l << 8) | kg);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hc[i] = hn[i];
+              }
+              if (c == 0) {
+                if (is_head) {                               // Rz_L has been read: the R phase may overwrite its region
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(rz_free);
+                }
+                if (l == P.pass_last_l[pass]) {              // all delta blocks of the pass are written
+                  fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&d_full[pass]);
                 }
               }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[e]);
+              if (l == 2) {
+                // ---- final, chunk c: delta_1 = d_1' * act'(h_1) -> DG (MN-major B operand of the layer-1 gradient GEMM:
+                // four features of one timestep = one 16-byte store, a warp writes 4 x 128 contiguous bytes) + bias sums
+                const FtDStage st = P.ds[k];
+                const float* h1row = cb + (size_t)g.off_act[1] * MRL_LDT;
+                float h1c[16], h1n[16];
+                auto request1 = [&](int c0, float (&hb)[16]) {
+                  const float* ph = h1row + (size_t)c0 * MRL_LDT;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { hc[i] = hn[i]; zc[i] = zn[i]; }
-          }
-          if (!st.rfwd && ul == P.pass_last_l[pass]) {     // all delta blocks of the pass are written
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_full[pass]);
-          }
-        }
-        // ---- final: delta_1 = d_1' * act'(h_1) -> DG (tcgen05 B operand of the layer-1 gradient) + bias partial sums
-        {
-          const float* hrow = cb + (size_t)g.off_act[1] * MRL_LDT;
-          const int d1 = g.d[1], nu = a.nu;
-          const int nch = nu >> 4;
-          float hc[16], hn[16];
-          auto request = [&](int c0, float (&hb)[16]) {
-            const float* ph = hrow + (size_t)c0 * MRL_LDT;
+                  for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+                };
+                request1(st.col0, h1c);
+                if (tr_on) FT_TR(4, (6 << 24) | c);
+                mbar_wait_sleep(&dacc_full[k], tcount & 1);
+                tc_fence_after();
+                if (tr_on) FT_TR(4, (7 << 24) | c);
+                const uint32_t facc = tlane + st.acc_col;
+                float* dgp = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + (T & 7) * 4;
+                for (int j0 = 0; j0 < st.N; j0 += 16) {
+                  const int c0 = st.col0 + j0;
+                  if (j0 + 16 < st.N) request1(c0 + 16, h1n);
+                  uint32_t v[16];
+                  tmem_ld16(facc + j0, v);
+                  float val[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
-          };
-          int jj = e;
-          if (jj < nch) request(16 * jj, hc);
-          mbar_wait_sleep(&acc_full[S - 1], tcount & 1);
-          tc_fence_after();
-          const uint32_t src_acc = tlane + P.st[S - 1].acc_col;
-          float* dgp = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + ((T >> 2) & 1) * (nu * 4) + (T & 3);
-          for (; jj < nch; jj += 2) {
-            const int c0 = 16 * jj;
-            if (jj + 2 < nch) request(c0 + 32, hn);
-            uint32_t v[16];
-            tmem_ld16(src_acc + c0, v);
-            float val[16];
+                  for (int i = 0; i < 16; ++i) val[i] = __uint_as_float(v[i]) * dact_from_h<ACT>(h1c[i]);   // padding columns are zero
+                  if (ok) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              val[i] = __uint_as_float(v[i]) * dact_from_h<ACT>(hc[i]);     // padding columns of the accumulator are zero
-#ifndef FT_NO_DG
-              if (ok) {
-                uint32_t hi, lo;
-                ft_split(val[i], hi, lo);
-                float* p = dgp + ((c0 + i) >> 3) * 32 + ((c0 + i) & 7) * 4;
-                p[0] = __uint_as_float(hi);
-                p[nu * 8] = __uint_as_float(lo);
+                    for (int qd = 0; qd < 4; ++qd) {
+                      uint32_t hi[4], lo[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) ft_split(val[4 * qd + i], hi[i], lo[i]);
+                      float* p = dgp + (size_t)((c0 >> 2) + qd) * 32;
+                      *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                      *reinterpret_cast<uint4*>(p + nu * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                  }
+                  if (a.dbg && mt == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) a.dbg[((size_t)(nR + L - 1) * 128 + m) * 128 + c0 + i] = val[i];
+                  }
+                  // column sums over the warp's 32 timesteps: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the pair
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float send = (lane & 16) ? val[i] : val[i + 8];
+                    const float keep = (lane & 16) ? val[i + 8] : val[i];
+                    val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float send = (lane & 8) ? val[i] : val[i + 4];
+                    const float keep = (lane & 8) ? val[i + 4] : val[i];
+                    val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    const float send = (lane & 4) ? val[i] : val[i + 2];
+                    const float keep = (lane & 4) ? val[i + 2] : val[i];
+                    val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                  }
+                  {
+                    const float send = (lane & 2) ? val[0] : val[1];
+                    const float keep = (lane & 2) ? val[1] : val[0];
+                    val[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                  }
+                  val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+                  // lane holds column c0 + 8 b4 + 4 b3 + 2 b2 + b1 (b4 = bit 4 of the lane, ...)
+                  if ((lane & 1) == 0) {
+                    const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    gb1w[col] += val[0];
+                  }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) h1c[i] = h1n[i];
+                }
+                tc_fence_before();
+                if (tr_on) FT_TR(4, (8 << 24) | c);
               }
-#endif
             }
-            if (a.dbg && mt == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) a.dbg[((size_t)S * 128 + m) * 128 + c0 + i] = val[i];
-            }
-            // column sums over the warp's 32 timesteps: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the pair
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = (lane & 16) ? val[i] : val[i + 8];
-              const float keep = (lane & 16) ? val[i + 8] : val[i];
-              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = (lane & 8) ? val[i] : val[i + 4];
-              const float keep = (lane & 8) ? val[i + 4] : val[i];
-              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = (lane & 4) ? val[i] : val[i + 2];
-              const float keep = (lane & 4) ? val[i + 2] : val[i];
-              val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            {
-              const float send = (lane & 2) ? val[0] : val[1];
-              const float keep = (lane & 2) ? val[1] : val[0];
-              val[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
-            // lane holds column c0 + 8 b4 + 4 b3 + 2 b2 + b1 (b4 = bit 4 of the lane, ...)
-            if ((lane & 1) == 0) {
-              const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              gb1w[col] += val[0];
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) hc[i] = hn[i];
           }
-          tc_fence_before();
         }
+        // ---- slab end: layer-1 bias partial (fixed order over the 4 delta-phase warps), logstd block = 0 (set by the reduce)
+        ft_dbar();
+        float* part = a.partm + (size_t)slab * g.pmid;
+        const int et = threadIdx.x - 256;              // 0..127 over the delta-phase warps
+        for (int f = et; f < g.d[1]; f += 128) part[g.off_b[1] + f] = (gb1s[f] + gb1s[128 + f]) + (gb1s[256 + f] + gb1s[384 + f]);
+        for (int j = et; j < g.d[L]; j += 128) part[g.off_pm_logstd + j] = 0.f;
+        ft_dbar();
+        for (int f = et; f < 4 * 128; f += 128) gb1s[f] = 0.f;
+        ft_dbar();
       }
-      // ---- slab end: layer-1 bias partial (fixed order over the 8 epilogue warps), logstd block = 0 (set by the reduce)
-      ft_epi_bar();
-      float* part = a.partm + (size_t)slab * g.pmid;
-      const int et = threadIdx.x - 128;              // 0..255 over the epilogue warps
-      for (int f = et; f < g.d[1]; f += 256) {
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { sum += gb1s[w * 128 + f]; }
-        part[g.off_b[1] + f] = sum;
-      }
-      for (int j = et; j < g.d[L]; j += 256) part[g.off_pm_logstd + j] = 0.f;
-      ft_epi_bar();
-      for (int f = et; f < 8 * 128; f += 256) gb1s[f] = 0.f;
-      ft_epi_bar();
     }
   }
+#undef FT_FOR_TILES
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -649,9 +794,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
 
 // ------------------------------------------------------------------------------------ operand images
 // src (flat parameter or tangent vector) -> the B images of the chain stages: per stage [k-group][hi | lo][khalf][n-group
-// N/8][8 n][4 k]; R-forward stages hold W_l as B[n = out][k = in], delta stages W_l^T as B[n = in][k = out].
-struct FtPackJob { int off, N, kgs, l, transposed, end; };
-struct FtPackJobs { FtPackJob j[FT_MAX_STAGES]; int n; };
+// N/8][8 n][4 k]; R-forward stages hold W_l as B[n = out][k = in], delta stages a column chunk of W_l^T as
+// B[n = in - col0][k = out].
+struct FtPackJob { int off, N, kgs, l, transposed, col0, end; };
+struct FtPackJobs { FtPackJob j[FT_MAX_R + FT_MAX_D]; int n; };
 __global__ void ft_pack_kernel(NetGeom g, FtPackJobs jobs, const float* __restrict__ src, float* __restrict__ dst, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -664,8 +810,8 @@ __global__ void ft_pack_kernel(NetGeom g, FtPackJobs jobs, const float* __restri
   float x = 0.f;
   if (!jb.transposed) {          // n = out unit, k = in unit
     if (n < g.d[l] && k < g.d[l - 1]) x = src[g.off_flat_W[l] + k * g.d[l] + n];
-  } else {                       // n = in unit, k = out unit
-    if (n < g.d[l - 1] && k < g.d[l]) x = src[g.off_flat_W[l] + n * g.d[l] + k];
+  } else {                       // n + col0 = in unit, k = out unit
+    if (n + jb.col0 < g.d[l - 1] && k < g.d[l]) x = src[g.off_flat_W[l] + (n + jb.col0) * g.d[l] + k];
   }
   const float h = tf32_rna(x);
   float* p = dst + jb.off + (size_t)(k >> 3) * (2 * jb.N * 8) + ((k & 7) >> 2) * (jb.N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);
@@ -681,37 +827,45 @@ static bool ft_build_plan(const NetGeom& g, FtPlan* P) {
   if (g.head != MRL_HEAD_GAUSS && g.head != MRL_HEAD_CAT) return false;
   if (g.d[L] > 64) return false;
   P->L = L;
-  P->S = 2 * (L - 1);
   int vb = 0;
   for (int l = 1; l <= L; ++l) {
     if (g.d[l] > 128) return false;
+    if (l >= 2 && g.d[l] > 64) return false;      // accumulators of the inner GEMMs are at most 64 columns wide
     P->Kg[l] = (g.d[l] + 7) / 8;
     P->Np[l] = round_up(g.d[l], 16);
     P->vboff[l] = vb;
-    vb += round_up(g.d[l], 16) + 16;      // the epilogue reads up to 16 k-group-padded entries past d[l]
+    vb += round_up(g.d[l], 16) + 16;      // the epilogue reads k-group-padded entries past d[l]
   }
   if (vb > 512) return false;
   if (P->Np[1] != l1tc_nu(g)) return false;
-  // chain stages and their B images
-  int s = 0, wc = 0, vc = 0, maxstage = 0;
-  for (int l = 2; l <= L; ++l, ++s) {
-    FtStage& st = P->st[s];
-    st.rfwd = 1; st.l = l; st.ul = l - 1; st.kgs = P->Kg[l - 1]; st.N = P->Np[l];
+  // R-forward stages and delta stages (the last GEMM, N = N_1, in column chunks of at most 64) with their B images
+  int wc = 0, vc = 0;
+  P->nR = L - 1;
+  for (int l = 2; l <= L; ++l) {
+    FtRStage& st = P->rs[l - 2];
+    st.l = l; st.kgs = P->Kg[l - 1]; st.N = P->Np[l];
     st.w_off = wc; st.v_off = vc;
     wc += st.kgs * 2 * st.N * 8;
     vc += st.kgs * 2 * st.N * 8;
-    maxstage = maxstage > 2 * 2 * 2 * st.N * 8 ? maxstage : 2 * 2 * 2 * st.N * 8;   // 2 k-groups x (W, V) x (hi, lo)
+    if (2 * 2 * st.N * 8 > P->rstage_floats) P->rstage_floats = 2 * 2 * st.N * 8;     // (W, V) x (hi, lo) of one k-group
   }
-  for (int l = L; l >= 2; --l, ++s) {
-    FtStage& st = P->st[s];
-    st.rfwd = 0; st.l = l; st.ul = l; st.kgs = P->Kg[l]; st.N = P->Np[l - 1];
-    st.w_off = wc; st.v_off = -1;
-    wc += st.kgs * 2 * st.N * 8;
-    maxstage = maxstage > 2 * 2 * st.N * 8 ? maxstage : 2 * 2 * st.N * 8;
+  int nD = 0;
+  for (int l = L; l >= 2; --l) {
+    P->dstage_of[l] = nD;
+    const int Nout = P->Np[l - 1];
+    for (int col0 = 0; col0 < Nout; col0 += 64) {
+      if (nD == FT_MAX_D) return false;
+      if (col0 > 0 && l != 2) return false;
+      FtDStage& st = P->ds[nD++];
+      st.l = l; st.kgs = P->Kg[l]; st.N = Nout - col0 < 64 ? Nout - col0 : 64; st.col0 = col0;
+      st.w_off = wc;
+      wc += st.kgs * 2 * st.N * 8;
+      if (2 * st.N * 8 > P->dstage_floats) P->dstage_floats = 2 * st.N * 8;
+    }
   }
+  P->nD = nD;
   P->wc_floats = wc;
   P->vc_floats = vc;
-  P->wstage_floats = maxstage;
   // (k) tiles: layers are produced in the order delta_L, ..., delta_2; a tile takes consecutive layers while their input
   // rows plus one row of ones fit into 128 lanes
   int np = 0;
@@ -745,23 +899,31 @@ static bool ft_build_plan(const NetGeom& g, FtPlan* P) {
     l = lo_l - 1;
   }
   P->n_pass = np;
-  // tensor memory: (k) accumulators | chain accumulators (two alternating regions) | chain A ring | (k) A slots
+  // tensor memory: (k) accumulators | (k) A slots | R accumulators (two alternating regions) | delta accumulators
+  // (alternating by layer; the chunks of the last GEMM reuse one region) | R ring | delta ring
   int col = 0;
   for (int p = 0; p < np; ++p) { P->pass_acc[p] = col; col += P->pass_N[p]; }
-  int reg[2] = {0, 0};
-  for (int i = 0; i < P->S; ++i) reg[i & 1] = reg[i & 1] > P->st[i].N ? reg[i & 1] : P->st[i].N;
-  for (int i = 0; i < P->S; ++i) P->st[i].acc_col = col + ((i & 1) ? reg[0] : 0);
-  col += reg[0] + reg[1];
-  P->ring_col = col;
-  col += 128;
   P->kslot_col = col;
   col += 16 * FT_KSLOTS;
+  int reg[2] = {0, 0};
+  for (int r = 0; r < P->nR; ++r) if (P->rs[r].N > reg[r & 1]) reg[r & 1] = P->rs[r].N;
+  for (int r = 0; r < P->nR; ++r) P->rs[r].acc_col = col + ((r & 1) ? reg[0] : 0);
+  col += reg[0] + reg[1];
+  P->rz_wait_stage = (P->nR - 1) & 1;      // first stage of a tile in the same region as the last one
+  int dreg[2] = {0, 0};
+  for (int k = 0; k < nD; ++k) { const int par = (L - P->ds[k].l) & 1; if (P->ds[k].N > dreg[par]) dreg[par] = P->ds[k].N; }
+  for (int k = 0; k < nD; ++k) { const int par = (L - P->ds[k].l) & 1; P->ds[k].acc_col = col + (par ? dreg[0] : 0); }
+  col += dreg[0] + dreg[1];
+  P->rring_col = col;
+  col += 64;
+  P->dring_col = col;
+  col += 32;
   if (col > FT_TMEM_COLS) return false;
-  // shared memory: barriers + small (8 KB) | weight ring | (k) B buffers
+  // shared memory: barriers + small (8 KB) | R weight ring | delta weight ring | (k) B buffers
   int kb = 0;
   for (int p = 0; p < np; ++p) { P->pass_buf[p] = kb; kb += 2 * P->pass_N[p] * 128; }
   P->kbuf_floats = kb;
-  P->smem_bytes = 8192 + (FT_WSTAGES * P->wstage_floats + kb) * 4;
+  P->smem_bytes = 8192 + (FT_RSTAGES * P->rstage_floats + FT_DSTAGES * P->dstage_floats + kb) * 4;
   if (P->smem_bytes > 227 * 1024) return false;
   return true;
 }
@@ -781,15 +943,19 @@ cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* d
   FtPackJobs jobs;
   memset(&jobs, 0, sizeof(jobs));
   int total = 0;
-  for (int s = 0; s < P.S; ++s) {
-    const FtStage& sg = P.st[s];
-    if (tangent && !sg.rfwd) continue;
+  for (int r = 0; r < P.nR; ++r) {
+    const FtRStage& sg = P.rs[r];
     FtPackJob& jb = jobs.j[jobs.n++];
     jb.off = tangent ? sg.v_off : sg.w_off;
-    jb.N = sg.N;
-    jb.kgs = sg.kgs;
-    jb.l = sg.l;
-    jb.transposed = sg.rfwd ? 0 : 1;
+    jb.N = sg.N; jb.kgs = sg.kgs; jb.l = sg.l; jb.transposed = 0; jb.col0 = 0;
+    total += sg.N * sg.kgs * 8;
+    jb.end = total;
+  }
+  for (int k = 0; k < P.nD && !tangent; ++k) {
+    const FtDStage& sg = P.ds[k];
+    FtPackJob& jb = jobs.j[jobs.n++];
+    jb.off = sg.w_off;
+    jb.N = sg.N; jb.kgs = sg.kgs; jb.l = sg.l; jb.transposed = 1; jb.col0 = sg.col0;
     total += sg.N * sg.kgs * 8;
     jb.end = total;
   }
@@ -804,7 +970,7 @@ cudaError_t launch_fvp_tc(const NetGeom& g, const FvpTcArgs& x, cudaStream_t st)
   FtArgs a;
   a.WC = x.WC; a.VC = x.VC; a.vflat = x.vflat;
   a.logstd = g.head == MRL_HEAD_GAUSS ? x.img + g.off_pm_logstd : nullptr;
-  a.Zt = x.Zt; a.cache = x.cache; a.DG = x.DG; a.partm = x.partm; a.dbg = x.dbg;
+  a.Zt = x.Zt; a.cache = x.cache; a.DG = x.DG; a.partm = x.partm; a.dbg = x.dbg; a.trace = x.trace;
   a.N = x.N;
   a.n_tiles = x.n_tiles;
   a.n_mtiles = (x.n_tiles + 1) / 2;

@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
                                                                    float* __restrict__ part1, int ftiles,
                                                                    int xg_ftiles, int nu, int d0, int n1p,
                                                                    int slab_tiles, int n_tiles, int n_slabs,
-                                                                   int acc_stride, int tmem_cols, int nss, int nts) {
+                                                                   int acc_stride, int tmem_cols, int nss, int nts,
+                                                                   int dg_mn) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // two rings: nss shared-memory stages (raw A blocks + B) cover the HBM latency; nts tensor-memory slots hold
   // the converted A operand (hi, lo) of the stages the MMA thread is working on - tensor memory is mostly taken
@@ -309,8 +310,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
       }
     }
   } else if (warp == 1) {   // MMA issuer: the whole warp walks the loop, one elected lane issues
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24);
-    const uint32_t lboB = nu * 4 * 4;
+    // delta_1 as the B operand comes in one of two layouts (both nu x 8 timesteps per stage, hi block then lo block):
+    //   K-major  [khalf][ngroup nu/8][8 n][4 t]   (mlp_chain.cu / mlp_mid.cu writers: LBO = the K halves, SBO = 8-row groups)
+    //   MN-major [n/4][8 t][4 n]                   (mlp_fvp_tc.cu: a timestep thread stores 4 features = 16 bytes at once;
+    //                                               core matrix = 8 k x 16 bytes along N, SBO = stride between N chunks)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nu >> 3) << 17) | ((TC_M >> 4) << 24) |
+                           (dg_mn ? (1u << 16) : 0u);
+    const uint32_t lboB = dg_mn ? nu * 32 : nu * 4 * 4;
     const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
     const uint32_t dB0 = umma_desc_lo(smem_u32(stages) + offB, lboB);
     int s = 0, a = 0, aph = 0;
@@ -530,7 +536,7 @@ static bool l1g_plan(const NetGeom& g, int* acc_stride, int* nts, int* nss, int*
 }
 
 cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, const float* DG, float* part1,
-                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st) {
+                              int slab_tiles, int n_tiles, int n_slabs, cudaStream_t st, int dg_mn_major) {
   const int nu = l1tc_nu(g);
   const int ftiles = (g.d[0] + TC_M - 1) / TC_M;
   int acc_stride, nts, nss, tmem_cols;
@@ -543,7 +549,7 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
   const int sms = mrl_sm_count();
   const int grid = n_slabs < sms ? n_slabs : sms;
   l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
-                                                    n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts);
+                                                    n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts, dg_mn_major);
   return cudaGetLastError();
 }
 
