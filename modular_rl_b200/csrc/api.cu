@@ -891,7 +891,7 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   } else if (chain_bwd_shape(g, mode) != 0) CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_chain_backward(g, a, pl.n_slabs, st), 1);
   else CKP(mode == MRL_MODE_FVP ? PK_MIDB_FVP : PK_MIDB_GRAD, launch_mid_backward(g, a, pl.n_slabs, st), 1);
   CKP(PK_L1G, launch_l1_grad_tc(g, b->XG.as<float>(), (b->xdim + 127) / 128, n->DG.as<float>(), n->part1.as<float>(),
-                                pl.slab_tiles, b->n_tiles, pl.n_slabs, st, tc ? 1 : 0), 1);
+                                pl.slab_tiles, b->n_tiles, pl.n_slabs, st, 0), 1);
   const int world = world_of(n);
   // terms that are not sums over timesteps are divided by `world` so that the sum over ranks restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;

@@ -33,9 +33,9 @@
 #include "tc_common.cuh"
 #include <string.h>
 
-#define FT_THREADS 512
-#define FT_RSTAGES 6          // weight ring of the R-forward GEMMs (one k-group of W_l and V_l per stage)
-#define FT_DSTAGES 6          // weight ring of the delta GEMMs (one k-group of a W_l^T column chunk per stage)
+#define FT_THREADS 768        // 24 warps: 4 control, 8 R-phase epilogue, 8 delta-phase epilogue, 4 converters
+#define FT_RSTAGES 3          // weight ring of the R-forward GEMMs (two k-groups of W_l and V_l per stage)
+#define FT_DSTAGES 3          // weight ring of the delta GEMMs (two k-groups of a W_l^T column chunk per stage)
 #define FT_KSLOTS 4           // (k) A-operand slots (8 timesteps x one tile = 16 TMEM columns each)
 #define FT_MAX_R 3
 #define FT_MAX_D 6
@@ -84,7 +84,32 @@ __device__ __forceinline__ void ft_rot8(uint32_t (&v)[8], int r) {   // v[i] <- 
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = a[i];
 }
-__device__ __forceinline__ void ft_dbar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 delta-phase warps
+__device__ __forceinline__ void ft_dbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 delta-phase warps
+// one non-blocking try_wait issued EARLY: its result is consumed after the independent work that follows
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done;
+}
+// in: a[i] = feature i at this lane's timestep (tq = lane & 3) -> out: a[i] = feature tq at timestep i of the quad
+__device__ __forceinline__ void ft_quad_transpose(float (&a)[4], int lane) {
+  const bool up = lane & 2;
+  const float s0 = up ? a[0] : a[2], s1 = up ? a[1] : a[3];
+  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+  if (!up) { a[2] = r0; a[3] = r1; }   // [f0@t, f1@t, f0@t+2, f1@t+2]
+  else { a[0] = r0; a[1] = r1; }       // [f2@t-2, f3@t-2, f2@t, f3@t]
+  const bool odd = lane & 1;
+  const float q0 = odd ? a[0] : a[1], q1 = odd ? a[2] : a[3];
+  const float p0 = __shfl_xor_sync(0xffffffffu, q0, 1), p1 = __shfl_xor_sync(0xffffffffu, q1, 1);
+  if (!odd) { a[1] = p0; a[3] = p1; }                          // [F@0, F@1, F@2, F@3]
+  else { a[0] = p0; const float t = a[1]; a[1] = t; a[2] = p1; }   // [F@0 (recv), F@1 (own a[1]), F@2 (recv), F@3 (own a[3])]
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -95,15 +120,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 // launch gives every thread 128 registers (512 threads = the whole register file); the control warps and the
 // converters hand most of theirs back, the epilogue warps - which keep prefetched activations in registers to hide
 // the L2 latency - take them.
-#define FT_REGS_CTRL 40
-#define FT_REGS_CONV 96
-#define FT_REGS_EPI 176
+#define FT_REGS_CTRL 32
+#define FT_REGS_CONV 72
+#define FT_REGS_EPI 88
 template <int N> __device__ __forceinline__ void ft_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void ft_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-static_assert(4 * 32 * FT_REGS_CTRL + 4 * 32 * FT_REGS_CONV + 8 * 32 * FT_REGS_EPI <= 65536, "register file");
+static_assert(4 * 32 * FT_REGS_CTRL + 4 * 32 * FT_REGS_CONV + 16 * 32 * FT_REGS_EPI <= FT_THREADS * 80, "register pool of the launch (80 registers per thread)");
 
 // Pipeline trace of CTA 0 (experiments: MRL_FVP_TC_TRACE=1, tools/micro/fvp_trace.py): per role, (clock64, code) pairs
 #define FT_TRN 4096
+#ifndef FT_TRACE
+#define FT_TR(role, code) do { (void)trn; } while (0)
+#else
 #define FT_TR(role, code)                                                                        \
   do {                                                                                           \
     if (a.trace && blockIdx.x == 0 && trn < FT_TRN) {                                            \
@@ -112,6 +140,7 @@ static_assert(4 * 32 * FT_REGS_CTRL + 4 * 32 * FT_REGS_CONV + 8 * 32 * FT_REGS_E
       ++trn;                                                                                     \
     }                                                                                            \
   } while (0)
+#endif
 
 struct FtArgs {
   const float* WC;      // chain weight images of theta
@@ -136,23 +165,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
   uint64_t* rw_empty = rw_full + FT_RSTAGES;      // [FT_RSTAGES]
   uint64_t* dw_full = rw_empty + FT_RSTAGES;      // [FT_DSTAGES]
   uint64_t* dw_empty = dw_full + FT_DSTAGES;      // [FT_DSTAGES]
-  uint64_t* ra_full = dw_empty + FT_DSTAGES;      // [2] R ring slot written (4 warps)
+  uint64_t* ra_full = dw_empty + FT_DSTAGES;      // [2] R ring slot written (the 4 warps of its group)
   uint64_t* ra_empty = ra_full + 2;               // [2]
   uint64_t* da_full = ra_empty + 2;               // [2] delta ring slot
   uint64_t* da_empty = da_full + 2;               // [2]
   uint64_t* racc_full = da_empty + 2;             // [FT_MAX_R] accumulator of R stage complete (the last one = Rz_L)
   uint64_t* dacc_full = racc_full + FT_MAX_R;     // [FT_MAX_D]
-  uint64_t* rz_free = dacc_full + FT_MAX_D;       // [1] the head has read Rz_L (4 warps)
+  uint64_t* rz_free = dacc_full + FT_MAX_D;       // [1] the head has read Rz_L (8 warps)
   uint64_t* kconv = rz_free + 1;                  // [FT_KSLOTS]
   uint64_t* kempty = kconv + FT_KSLOTS;           // [FT_KSLOTS]
-  uint64_t* d_full = kempty + FT_KSLOTS;          // [FT_MAX_PASS] delta blocks of a (k) pass in shared memory (4 warps)
+  uint64_t* d_full = kempty + FT_KSLOTS;          // [FT_MAX_PASS] delta blocks of a (k) pass in shared memory (8 warps)
   uint64_t* d_free = d_full + FT_MAX_PASS;        // [FT_MAX_PASS]
   uint64_t* gacc_full = d_free + FT_MAX_PASS;     // [1]
   uint64_t* gacc_empty = gacc_full + 1;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gacc_empty + 1);
   float* vb_s = reinterpret_cast<float*>(smem_raw + 512);       // tangent biases [vboff[l] + j], 512 floats
   float* ivar_s = vb_s + 512;                                   // 64 floats
-  float* gb1s = ivar_s + 64;                                    // [4 delta-phase warps][128] layer-1 bias partials
+  float* gb1s = ivar_s + 64;                                    // [8 delta-phase warps][128] layer-1 bias partials
   float* rring = reinterpret_cast<float*>(smem_raw + 8192);     // [FT_RSTAGES][rstage_floats]
   float* dring = rring + (size_t)FT_RSTAGES * P.rstage_floats;  // [FT_DSTAGES][dstage_floats]
   float* kbuf = dring + (size_t)FT_DSTAGES * P.dstage_floats;   // (k) B operands: per pass [hi | lo][ngroup][32 k-chunks][8][4]
@@ -168,16 +197,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
     }
     for (int i = 0; i < FT_MAX_R; ++i) mbar_init(&racc_full[i], 1);
     for (int i = 0; i < FT_MAX_D; ++i) mbar_init(&dacc_full[i], 1);
-    mbar_init(rz_free, 4);
+    mbar_init(rz_free, 8);
     for (int i = 0; i < FT_KSLOTS; ++i) { mbar_init(&kconv[i], 4); mbar_init(&kempty[i], 1); }
-    for (int i = 0; i < FT_MAX_PASS; ++i) { mbar_init(&d_full[i], 4); mbar_init(&d_free[i], 1); }
+    for (int i = 0; i < FT_MAX_PASS; ++i) { mbar_init(&d_full[i], 8); mbar_init(&d_free[i], 1); }
     mbar_init(gacc_full, 1);
     mbar_init(gacc_empty, 4);
     fence_barrier_init();
   }
   // tangent biases, 1/sigma^2, zeroed bias partials and (k) operand buffers (their padding columns stay zero)
   for (int i = threadIdx.x; i < 512; i += FT_THREADS) vb_s[i] = 0.f;
-  for (int i = threadIdx.x; i < 4 * 128; i += FT_THREADS) gb1s[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * 128; i += FT_THREADS) gb1s[i] = 0.f;
   for (int i = threadIdx.x; i < P.kbuf_floats; i += FT_THREADS) kbuf[i] = 0.f;
   __syncthreads();
   for (int l = 1; l <= L; ++l)
@@ -213,29 +242,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       long long total_tiles = 0;
       for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x)
         total_tiles += min(slab * a.slab_mt + a.slab_mt, a.n_mtiles) - slab * a.slab_mt;
-      int r_per = 0, d_per = 0;                      // ring stages per tile
-      for (int r = 0; r < nR; ++r) r_per += P.rs[r].kgs;
-      for (int k = 0; k < nD; ++k) d_per += P.ds[k].kgs;
+      int r_per = 0, d_per = 0;                      // ring stages (pairs of k-groups) per tile
+      for (int r = 0; r < nR; ++r) r_per += (P.rs[r].kgs + 1) >> 1;
+      for (int k = 0; k < nD; ++k) d_per += (P.ds[k].kgs + 1) >> 1;
       long long r_left = total_tiles * r_per, d_left = total_tiles * d_per;
       uint32_t rc = 0, dc = 0;                       // stages issued so far
       int rst = 0, rkg = 0, dst_ = 0, dkg = 0;       // position inside the tile
-      // L2 prefetch of the activations, one tile ahead of the R phase
+      // optional L2 prefetch of the next tile's activations and x.V_1 (off: it competes with the demand loads, see FT_PF)
       int pf_slab = blockIdx.x, pf_mt = blockIdx.x * a.slab_mt;
-      long long r_tiles_done = 0;
+      auto prefetch_piece = [&](const float* p, size_t bytes) {
+        for (size_t o = 0; o < bytes; o += 16384) {
+          const uint32_t nb = (uint32_t)(bytes - o < 16384 ? bytes - o : 16384);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(p) + o), "r"(nb) : "memory");
+        }
+      };
       auto prefetch_next = [&]() {
-        // advance to the tile after the one the R ring is about to work on
         int mt = pf_mt + 1, slab = pf_slab;
         if (mt >= min(slab * a.slab_mt + a.slab_mt, a.n_mtiles)) { slab += gridDim.x; mt = slab * a.slab_mt; }
         pf_slab = slab; pf_mt = mt;
         if (slab >= a.n_slabs) return;
         const int t0 = 2 * mt, nt = min(2, a.n_tiles - t0);
         if (nt <= 0) return;
+#ifndef FT_PF
+#define FT_PF 0       // measured at 1 M Humanoid timesteps: no L2 prefetch 1.04 ms, one bulk prefetch per tile 1.07, 16 KB pieces 1.22
+#endif
+#if FT_PF == 2
+        prefetch_piece(a.cache + (size_t)t0 * tile_c, (size_t)nt * tile_c * 4);
+        prefetch_piece(a.Zt + (size_t)t0 * tile_z, (size_t)nt * tile_z * 4);
+#elif FT_PF == 1
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.cache + (size_t)t0 * tile_c),
                      "r"((uint32_t)(nt * tile_c * 4)) : "memory");
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Zt + (size_t)t0 * tile_z),
                      "r"((uint32_t)(nt * tile_z * 4)) : "memory");
+#endif
+        (void)prefetch_piece;
       };
-      (void)r_tiles_done;
       while (r_left > 0 || d_left > 0) {
         bool progressed = false;
         if (r_left > 0) {
@@ -243,13 +284,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           if (mbar_probe(&rw_empty[ws], ((rc / FT_RSTAGES) & 1) ^ 1)) {
             const FtRStage st = P.rs[rst];
             const int kgf = 2 * st.N * 8;                       // floats per k-group of one image (hi | lo)
+            const int nk = min(2, st.kgs - rkg);
             float* dst = rring + (size_t)ws * P.rstage_floats;
-            mbar_expect_tx(&rw_full[ws], 2u * kgf * 4u);
-            bulk_g2s(dst, a.WC + st.w_off + (size_t)rkg * kgf, kgf * 4u, &rw_full[ws]);
-            bulk_g2s(dst + kgf, a.VC + st.v_off + (size_t)rkg * kgf, kgf * 4u, &rw_full[ws]);
+            mbar_expect_tx(&rw_full[ws], 2u * nk * kgf * 4u);
+            bulk_g2s(dst, a.WC + st.w_off + (size_t)rkg * kgf, nk * kgf * 4u, &rw_full[ws]);
+            bulk_g2s(dst + 2 * kgf, a.VC + st.v_off + (size_t)rkg * kgf, nk * kgf * 4u, &rw_full[ws]);
             if (rst == 0 && rkg == 0) prefetch_next();
             ++rc; --r_left; progressed = true;
-            if (++rkg == st.kgs) { rkg = 0; if (++rst == nR) rst = 0; }
+            rkg += 2;
+            if (rkg >= st.kgs) { rkg = 0; if (++rst == nR) rst = 0; }
           }
         }
         if (d_left > 0) {
@@ -257,13 +300,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           if (mbar_probe(&dw_empty[ws], ((dc / FT_DSTAGES) & 1) ^ 1)) {
             const FtDStage st = P.ds[dst_];
             const int kgf = 2 * st.N * 8;
-            mbar_expect_tx(&dw_full[ws], kgf * 4u);
-            bulk_g2s(dring + (size_t)ws * P.dstage_floats, a.WC + st.w_off + (size_t)dkg * kgf, kgf * 4u, &dw_full[ws]);
+            const int nk = min(2, st.kgs - dkg);
+            mbar_expect_tx(&dw_full[ws], nk * kgf * 4u);
+            bulk_g2s(dring + (size_t)ws * P.dstage_floats, a.WC + st.w_off + (size_t)dkg * kgf, nk * kgf * 4u, &dw_full[ws]);
             ++dc; --d_left; progressed = true;
-            if (++dkg == st.kgs) { dkg = 0; if (++dst_ == nD) dst_ = 0; }
+            dkg += 2;
+            if (dkg >= st.kgs) { dkg = 0; if (++dst_ == nD) dst_ = 0; }
           }
         }
-        if (!progressed) __nanosleep(100);
+        if (!progressed) __nanosleep(200);
       }
     }
   } else if (warp == 1) {
@@ -272,7 +317,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
     const uint32_t ring_u32 = smem_u32(rring);
     uint32_t wc = 0, u = 0, tcount = 0;
     int trn = 0;
-    FT_FOR_TILES(
+    for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
+      const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
+      for (int mt = mt0; mt < mt1; ++mt) {
       for (int r = 0; r < nR; ++r) {
         const FtRStage st = P.rs[r];
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(st.N >> 3) << 17) | ((128u >> 4) << 24);
@@ -283,67 +330,78 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           mbar_wait_sleep(rz_free, (tcount & 1) ^ 1);
           tc_fence_after();
         }
-        for (int kg = 0; kg < st.kgs; ++kg, ++wc, ++u) {
-          const int ws = wc % FT_RSTAGES, e = u & 1;
+        for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc) {
+          const int ws = wc % FT_RSTAGES, nk = min(2, st.kgs - kg0);
           mbar_wait_sleep(&rw_full[ws], (wc / FT_RSTAGES) & 1);
-          if (lane == 0) FT_TR(0, (1 << 24) | (r << 8) | kg);
-          mbar_wait_sleep(&ra_full[e], (u >> 1) & 1);
-          tc_fence_after();
-          if (lane == 0) FT_TR(0, (2 << 24) | (r << 8) | kg);
-          if (elect_one()) {
-            const uint32_t bW = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.rstage_floats * 4u, lbo);
-            const uint32_t bV = bW + (kgb >> 4);
-            const uint32_t tr = tmem_base + P.rring_col + 32 * e, th = tr + 16;   // [Rh hi 8 | Rh lo 8 | h hi 8 | h lo 8]
-            umma_tf32_ts(d_tmem, tr + 8, bW, desc_hi, idesc, kg ? 1u : 0u);        // Rh_lo . W_hi
-            umma_tf32_ts(d_tmem, tr, bW + (kgb >> 5), desc_hi, idesc, 1u);         // Rh_hi . W_lo
-            umma_tf32_ts(d_tmem, tr, bW, desc_hi, idesc, 1u);                      // Rh_hi . W_hi
-            umma_tf32_ts(d_tmem, th + 8, bV, desc_hi, idesc, 1u);                  // h_lo . V_hi
-            umma_tf32_ts(d_tmem, th, bV + (kgb >> 5), desc_hi, idesc, 1u);         // h_hi . V_lo
-            umma_tf32_ts(d_tmem, th, bV, desc_hi, idesc, 1u);                      // h_hi . V_hi
-            tc_commit(&ra_empty[e]);
-            tc_commit(&rw_empty[ws]);
-            if (kg + 1 == st.kgs) tc_commit(&racc_full[r]);
+          const uint32_t bw = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.rstage_floats * 4u, lbo);
+          for (int c = 0; c < nk; ++c, ++u) {
+            const int e = u & 1;
+            if (lane == 0) FT_TR(0, (1 << 24) | (r << 8) | (kg0 + c));
+            mbar_wait_sleep(&ra_full[e], (u >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) FT_TR(0, (2 << 24) | (r << 8) | (kg0 + c));
+            if (elect_one()) {
+              const uint32_t bW = bw + ((c * kgb) >> 4), bV = bw + ((2 * kgb + c * kgb) >> 4);
+              const uint32_t tr = tmem_base + P.rring_col + 32 * e, th = tr + 16;   // [Rh hi 8 | Rh lo 8 | h hi 8 | h lo 8]
+              umma_tf32_ts(d_tmem, tr + 8, bW, desc_hi, idesc, (kg0 + c) ? 1u : 0u);   // Rh_lo . W_hi
+              umma_tf32_ts(d_tmem, tr, bW + (kgb >> 5), desc_hi, idesc, 1u);           // Rh_hi . W_lo
+              umma_tf32_ts(d_tmem, tr, bW, desc_hi, idesc, 1u);                        // Rh_hi . W_hi
+              umma_tf32_ts(d_tmem, th + 8, bV, desc_hi, idesc, 1u);                    // h_lo . V_hi
+              umma_tf32_ts(d_tmem, th, bV + (kgb >> 5), desc_hi, idesc, 1u);           // h_hi . V_lo
+              umma_tf32_ts(d_tmem, th, bV, desc_hi, idesc, 1u);                        // h_hi . V_hi
+              tc_commit(&ra_empty[e]);
+              if (c + 1 == nk) tc_commit(&rw_empty[ws]);
+              if (kg0 + c + 1 == st.kgs) tc_commit(&racc_full[r]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       ++tcount;
-    )
+    }
+    }
   } else if (warp == 2) {
     // ================================================================ delta-phase MMA issuer
     const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
     const uint32_t ring_u32 = smem_u32(dring);
     uint32_t wc = 0, u = 0;
     int trn = 0;
-    FT_FOR_TILES(
+    for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
+      const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
+      for (int mt = mt0; mt < mt1; ++mt) {
       for (int k = 0; k < nD; ++k) {
         const FtDStage st = P.ds[k];
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(st.N >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t lbo = (uint32_t)st.N * 16u;
         const uint32_t kgb = (uint32_t)st.N * 64u;
         const uint32_t d_tmem = tmem_base + st.acc_col;
-        for (int kg = 0; kg < st.kgs; ++kg, ++wc, ++u) {
-          const int ws = wc % FT_DSTAGES, e = u & 1;
+        for (int kg0 = 0; kg0 < st.kgs; kg0 += 2, ++wc) {
+          const int ws = wc % FT_DSTAGES, nk = min(2, st.kgs - kg0);
           mbar_wait_sleep(&dw_full[ws], (wc / FT_DSTAGES) & 1);
-          if (lane == 0) FT_TR(1, (1 << 24) | (k << 8) | kg);
-          mbar_wait_sleep(&da_full[e], (u >> 1) & 1);
-          tc_fence_after();
-          if (lane == 0) FT_TR(1, (2 << 24) | (k << 8) | kg);
-          if (elect_one()) {
-            const uint32_t bW = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.dstage_floats * 4u, lbo);
-            const uint32_t td = tmem_base + P.dring_col + 16 * e;                  // [delta hi 8 | delta lo 8]
-            umma_tf32_ts(d_tmem, td + 8, bW, desc_hi, idesc, kg ? 1u : 0u);
-            umma_tf32_ts(d_tmem, td, bW + (kgb >> 5), desc_hi, idesc, 1u);
-            umma_tf32_ts(d_tmem, td, bW, desc_hi, idesc, 1u);
-            tc_commit(&da_empty[e]);
-            tc_commit(&dw_empty[ws]);
-            if (kg + 1 == st.kgs) tc_commit(&dacc_full[k]);
+          const uint32_t bw = umma_desc_lo(ring_u32 + (uint32_t)ws * (uint32_t)P.dstage_floats * 4u, lbo);
+          for (int c = 0; c < nk; ++c, ++u) {
+            const int e = u & 1;
+            if (lane == 0) FT_TR(1, (1 << 24) | (k << 8) | (kg0 + c));
+            mbar_wait_sleep(&da_full[e], (u >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) FT_TR(1, (2 << 24) | (k << 8) | (kg0 + c));
+            if (elect_one()) {
+              const uint32_t bW = bw + ((c * kgb) >> 4);
+              const uint32_t td = tmem_base + P.dring_col + 16 * e;                  // [delta hi 8 | delta lo 8]
+              umma_tf32_ts(d_tmem, td + 8, bW, desc_hi, idesc, (kg0 + c) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, td, bW + (kgb >> 5), desc_hi, idesc, 1u);
+              umma_tf32_ts(d_tmem, td, bW, desc_hi, idesc, 1u);
+              tc_commit(&da_empty[e]);
+              if (c + 1 == nk) tc_commit(&dw_empty[ws]);
+              if (kg0 + c + 1 == st.kgs) tc_commit(&dacc_full[k]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
-    )
-  } else {
+    }
+    }
+  } else if (warp == 3) {
     // ================================================================ (k) MMA issuer: G tiles += h^T delta over the slab
     const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 4096) >> 32);   // SBO = 32 k-chunks x 128 B between n-groups
     const uint32_t kbuf_u32 = smem_u32(kbuf);
@@ -384,7 +442,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       }
     }
   }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ================================================================ converters: h^T -> tensor memory, slab flush
     ft_reg_dec<FT_REGS_CONV>();
     const int q = warp & 3, m = q * 32 + lane;
@@ -396,14 +454,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       for (int mt = mt0; mt < mt1; ++mt) {
         for (int p = 0; p < P.n_pass; ++p) {
           const int crow = P.row_cache[p][m];
-          if (warp == 12 && lane == 0) FT_TR(5, (1 << 24) | (p << 8));
-          // the 16 k-steps (8 timesteps each) of the tile in groups of four; group g + 1 is requested before group g is
-          // converted, so the L2 latency is covered by the conversion of four k-steps
-          float4 xa[4][2], xb[4][2];
-          auto request = [&](int g4, float4 (&x)[4][2]) {
+          if (warp == 20 && lane == 0) FT_TR(5, (1 << 24) | (p << 8));
+          // the 16 k-steps (8 timesteps each) of the tile in groups of two; group g + 1 is requested before group g is
+          // converted, so the L2 latency is covered by the conversion of two k-steps
+          float4 xa[2][2], xb[2][2];
+          auto request = [&](int g2, float4 (&x)[2][2]) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ks = 4 * g4 + i, t64 = 2 * mt + (ks >> 3);
+            for (int i = 0; i < 2; ++i) {
+              const int ks = 2 * g2 + i, t64 = 2 * mt + (ks >> 3);
               if (crow >= 0 && t64 < a.n_tiles) {
                 const float4* src = reinterpret_cast<const float4*>(a.cache + (size_t)t64 * tile_c + (size_t)crow * MRL_LDT + (ks & 7) * 8);
                 x[i][0] = __ldg(src);
@@ -415,15 +473,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
               }
             }
           };
-          auto convert = [&](const float4 (&xx)[4][2]) {
+          auto convert = [&](const float4 (&xx)[2][2]) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i, ++kc) {
+            for (int i = 0; i < 2; ++i, ++kc) {
               const int sl = kc % FT_KSLOTS;
+              const uint32_t freeq = mbar_try(&kempty[sl], ((kc / FT_KSLOTS) & 1) ^ 1);
               const float x[8] = {xx[i][0].x, xx[i][0].y, xx[i][0].z, xx[i][0].w, xx[i][1].x, xx[i][1].y, xx[i][1].z, xx[i][1].w};
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) ft_split(x[k], hi[k], lo[k]);
-              mbar_wait_sleep(&kempty[sl], ((kc / FT_KSLOTS) & 1) ^ 1);
+              if (!freeq) mbar_wait_ns<200>(&kempty[sl], ((kc / FT_KSLOTS) & 1) ^ 1);
               tc_fence_after();
               const uint32_t ta = tlane + P.kslot_col + 16 * sl;
               tmem_st8(ta, hi);
@@ -435,32 +494,32 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             }
           };
           request(0, xa);
-          request(1, xb);
-          convert(xa);
-          request(2, xa);
-          convert(xb);
-          request(3, xb);
-          convert(xa);
-          convert(xb);
-          if (warp == 12 && lane == 0) FT_TR(5, (2 << 24) | (p << 8));
+#pragma unroll 1
+          for (int g2 = 0; g2 < 8; g2 += 2) {
+            request(g2 + 1, xb);
+            convert(xa);
+            if (g2 + 2 < 8) request(g2 + 2, xa);
+            convert(xb);
+          }
+          if (warp == 20 && lane == 0) FT_TR(5, (2 << 24) | (p << 8));
         }
       }
       // ---- slab flush: accumulator rows -> fp32 slab partial (weights of layers >= 2, their biases from the ones row)
-      mbar_wait_sleep(gacc_full, scount & 1);
+      mbar_wait_ns<500>(gacc_full, scount & 1);
       tc_fence_after();
       float* part = a.partm + (size_t)slab * g.pmid;
       for (int p = 0; p < P.n_pass; ++p) {
         const int crow = P.row_cache[p][m], rl = P.row_lay[p][m], rf = P.row_f[p][m];
-        for (int c0 = 0; c0 < P.pass_N[p]; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tlane + P.pass_acc[p] + c0, v);
+        for (int c0 = 0; c0 < P.pass_N[p]; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(tlane + P.pass_acc[p] + c0, v);
           if (crow == -1) continue;
           for (int l = P.pass_last_l[p]; l <= P.pass_first_l[p]; ++l) {
             if (crow >= 0 && l != rl) continue;
             const int col0 = P.lay_col[l];
             float* dst = crow >= 0 ? part + g.off_W[l] + (size_t)rf * g.ldw[l] : part + g.off_b[l];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const int n = c0 + j - col0;
               if (n >= 0 && n < g.d[l]) dst[n] = __uint_as_float(v[j]);
             }
@@ -475,15 +534,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
     ft_reg_inc<FT_REGS_EPI>();
     const int q = warp & 3, m = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (warp < 8) {
+    if (warp < 12) {
       // ============================================================== R-phase epilogue: one thread = one timestep
-      // Produces the A operand [Rh_ul | h_ul] of R stage r, one k-group (8 features) per ring slot.  The cached
-      // activations (and x.V_1 for layer 1) of the NEXT k-group are requested before the current one is processed,
-      // those of the first k-group before the wait for the previous stage's accumulator.
-      uint32_t u = 0, tcount = 0;
+      // Two groups of four warps (one warp per TMEM lane quarter) take alternate k-groups: group e owns ring slot e.  A
+      // slot is the A operand [Rh_ul | h_ul] of one k-group (8 features).  The cached activations (and x.V_1 for layer
+      // 1) of a group's NEXT k-group are requested before its current one is processed, those of the first before the
+      // wait for the previous stage's accumulator; the probe of the slot's empty barrier is issued before the arithmetic.
+      const int e = (warp - 4) >> 2;
+      const uint32_t ring = tlane + P.rring_col + 32 * e;
+      uint32_t u = 0, ue = 0, tcount = 0;
       int trn = 0;
       const bool tr_on = warp == 4 && lane == 0;
-      FT_FOR_TILES(
+      for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
+      const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
+      for (int mt = mt0; mt < mt1; ++mt) {
         const int t64c = min(2 * mt + (m >> 6), a.n_tiles - 1);      // a tile beyond the batch reads the last one (masked at the head)
         const float* cb = a.cache + (size_t)t64c * tile_c + (m & 63);
         const float* zb = a.Zt + (size_t)t64c * tile_z + (m & 63);
@@ -502,7 +566,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
               for (int i = 0; i < 8; ++i) zz[i] = __ldg(pz + i * MRL_LDT);
             }
           };
-          request(0, hc, zc);
+          int kg = (e - (int)(u & 1)) & 1;            // this group's first k-group of the stage
+          u += kgs;
+          if (kg < kgs) request(kg, hc, zc);
           uint32_t src_acc = 0;
           if (tr_on) FT_TR(3, (1 << 24) | (r << 8));
           if (r > 0) {
@@ -511,8 +577,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             src_acc = tlane + P.rs[r - 1].acc_col;
           }
           if (tr_on) FT_TR(3, (2 << 24) | (r << 8));
-          for (int kg = 0; kg < kgs; ++kg, ++u) {
-            if (kg + 1 < kgs) request(kg + 1, hn, zn);
+          for (; kg < kgs; kg += 2, ++ue) {
+            const uint32_t freeq = mbar_try(&ra_empty[e], (ue & 1) ^ 1);
+            if (kg + 2 < kgs) request(kg + 2, hn, zn);
             float val[8];
             if (r == 0) {
 #pragma unroll
@@ -527,19 +594,19 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
 #pragma unroll
               for (int i = 0; i < 8; ++i) a.dbg[((size_t)r * 128 + m) * 128 + 8 * kg + i] = val[i];
             }
-            uint32_t hi[8], lo[8], h2[8], l2[8];
+            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ft_split(val[i], hi[i], lo[i]); ft_split(hc[i], h2[i], l2[i]); }
-            const int e = u & 1;
+            for (int i = 0; i < 8; ++i) ft_split(val[i], hi[i], lo[i]);
             if (tr_on) FT_TR(3, (3 << 24) | (r << 8) | kg);
-            mbar_wait_sleep(&ra_empty[e], ((u >> 1) & 1) ^ 1);
+            if (!freeq) mbar_wait_sleep(&ra_empty[e], (ue & 1) ^ 1);
             tc_fence_after();
             if (tr_on) FT_TR(3, (4 << 24) | (r << 8) | kg);
-            const uint32_t ring = tlane + P.rring_col + 32 * e;
             tmem_st8(ring, hi);
             tmem_st8(ring + 8, lo);
-            tmem_st8(ring + 16, h2);
-            tmem_st8(ring + 24, l2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ft_split(hc[i], hi[i], lo[i]);
+            tmem_st8(ring + 16, hi);
+            tmem_st8(ring + 24, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -550,20 +617,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           }
         }
         ++tcount;
-      )
+      }
+      }
     } else {
       // ============================================================== delta-phase epilogue: one thread = one timestep
       // head metric -> delta_L, delta_l = d_l' * act'(h_l) (l = L-1 .. 2), delta_1 -> DG + layer-1 bias partial sums.
-      // delta_l (l >= 2) goes to the delta ring (A operand of the next GEMM) and, as the K-major B operand of the (k)
-      // GEMM, to shared memory.  When the last GEMM is split into column chunks, delta_2 is produced once per chunk.
-      const int dw = warp - 8;
-      float* gb1w = gb1s + dw * 128;
+      // Two groups of four warps take alternate k-groups (group e owns delta ring slot e) and alternate 8-column chunks
+      // of delta_1.  delta_l (l >= 2) goes to the delta ring (A operand of the next GEMM) and, as the K-major B operand
+      // of the (k) GEMM, to shared memory.  When the last GEMM is split into column chunks, delta_2 is produced once per chunk.
+      const int e = (warp - 12) >> 2;
+      const uint32_t ring = tlane + P.dring_col + 16 * e;
+      float* gb1w = gb1s + (warp - 12) * 128;
       const int rot = (m >> 2) & 7;
       const bool cat = g.head == MRL_HEAD_CAT;
       const int nu = a.nu;
-      uint32_t u = 0, tcount = 0;
+      uint32_t u = 0, ue = 0, tcount = 0;
       int trn = 0;
-      const bool tr_on = warp == 8 && lane == 0;
+      const bool tr_on = warp == 12 && lane == 0;
       for (int slab = blockIdx.x; slab < a.n_slabs; slab += gridDim.x) {
         const int mt0 = slab * a.slab_mt, mt1 = min(mt0 + a.slab_mt, a.n_mtiles);
         for (int mt = mt0; mt < mt1; ++mt, ++tcount) {
@@ -595,7 +665,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
                   for (int i = 0; i < 8; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
                 }
               };
-              request(0, hc);
+              int kg = (e - (int)(u & 1)) & 1;        // this group's first k-group
+              u += kgs;
+              if (kg < kgs) request(kg, hc);
               uint32_t src_acc;
               if (tr_on) FT_TR(4, (1 << 24) | (l << 8) | c);
               if (c == 0) {
@@ -614,19 +686,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
               if (tr_on) FT_TR(4, (2 << 24) | (l << 8) | c);
               float sdot = 0.f;     // Categorical: p . Rz over the whole row
               if (is_head && cat) {
-                for (int c0 = 0; c0 < P.Np[L]; c0 += 16) {
-                  uint32_t v[16];
-                  tmem_ld16(src_acc + c0, v);
+                for (int c0 = 0; c0 < P.Np[L]; c0 += 8) {
+                  uint32_t v[8];
+                  tmem_ld8(src_acc + c0, v);
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
+                  for (int i = 0; i < 8; ++i) {
                     const int f = c0 + i;
                     const float p = f < du ? __ldg(hrow + (size_t)f * MRL_LDT) : 0.f;
                     sdot += p * (__uint_as_float(v[i]) + vbl[f]);
                   }
                 }
               }
-              for (int kg = 0; kg < kgs; ++kg, ++u) {
-                if (kg + 1 < kgs) request(kg + 1, hn);
+              for (; kg < kgs; kg += 2, ++ue) {
+                const uint32_t freeq = mbar_try(&da_empty[e], (ue & 1) ^ 1);
+                if (kg + 2 < kgs) request(kg + 2, hn);
                 uint32_t v[8];
                 tmem_ld8(src_acc + 8 * kg, v);
                 float val[8];
@@ -649,12 +722,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ft_split(val[i], hi[i], lo[i]);
-                const int e = u & 1;
                 if (tr_on) FT_TR(4, (3 << 24) | (l << 8) | kg);
-                mbar_wait_sleep(&da_empty[e], ((u >> 1) & 1) ^ 1);
+                if (!freeq) mbar_wait_sleep(&da_empty[e], (ue & 1) ^ 1);
                 tc_fence_after();
                 if (tr_on) FT_TR(4, (4 << 24) | (l << 8) | kg);
-                const uint32_t ring = tlane + P.dring_col + 16 * e;
                 tmem_st8(ring, hi);
                 tmem_st8(ring + 8, lo);
                 if (c == 0) {
@@ -691,78 +762,77 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
                 }
               }
               if (l == 2) {
-                // ---- final, chunk c: delta_1 = d_1' * act'(h_1) -> DG (MN-major B operand of the layer-1 gradient GEMM:
-                // four features of one timestep = one 16-byte store, a warp writes 4 x 128 contiguous bytes) + bias sums
+                // ---- final, chunk c: delta_1 = d_1' * act'(h_1) -> DG (K-major tcgen05 B operand of the layer-1 gradient
+                // GEMM: [t/8][hi|lo][khalf][n/8][8 n][4 t]) + bias partial sums.  The two groups take alternate 8-column
+                // blocks; a 4 x 4 transpose inside each lane quad turns (4 features of my timestep) into (my feature at
+                // the quad's 4 timesteps) = one 16-byte store.
                 const FtDStage st = P.ds[k];
                 const float* h1row = cb + (size_t)g.off_act[1] * MRL_LDT;
-                float h1c[16], h1n[16];
-                auto request1 = [&](int c0, float (&hb)[16]) {
+                float h1c[8], h1n[8];
+                auto request1 = [&](int c0, float (&hb)[8]) {
                   const float* ph = h1row + (size_t)c0 * MRL_LDT;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
+                  for (int i = 0; i < 8; ++i) hb[i] = __ldg(ph + i * MRL_LDT);
                 };
-                request1(st.col0, h1c);
+                int j0 = 8 * e;
+                if (j0 < st.N) request1(st.col0 + j0, h1c);
                 if (tr_on) FT_TR(4, (6 << 24) | c);
                 mbar_wait_sleep(&dacc_full[k], tcount & 1);
                 tc_fence_after();
                 if (tr_on) FT_TR(4, (7 << 24) | c);
                 const uint32_t facc = tlane + st.acc_col;
-                float* dgp = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + (T & 7) * 4;
-                for (int j0 = 0; j0 < st.N; j0 += 16) {
+                // quad base: timesteps 4 (T / 4) .. + 3 of feature n: + (n / 8) * 32 + (n % 8) * 4
+                float* dgq = a.DG + (size_t)(T >> 3) * (2 * nu * 8) + ((T >> 2) & 1) * (nu * 4);
+                for (; j0 < st.N; j0 += 16) {
                   const int c0 = st.col0 + j0;
                   if (j0 + 16 < st.N) request1(c0 + 16, h1n);
-                  uint32_t v[16];
-                  tmem_ld16(facc + j0, v);
-                  float val[16];
+                  uint32_t v[8];
+                  tmem_ld8(facc + j0, v);
+                  float val[8];
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) val[i] = __uint_as_float(v[i]) * dact_from_h<ACT>(h1c[i]);   // padding columns are zero
-                  if (ok) {
+                  for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) * dact_from_h<ACT>(h1c[i]);   // padding columns are zero
+                  if (a.dbg && mt == 0) {
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                      uint32_t hi[4], lo[4];
+                    for (int i = 0; i < 8; ++i) a.dbg[((size_t)(nR + L - 1) * 128 + m) * 128 + c0 + i] = val[i];
+                  }
 #pragma unroll
-                      for (int i = 0; i < 4; ++i) ft_split(val[4 * qd + i], hi[i], lo[i]);
-                      float* p = dgp + (size_t)((c0 >> 2) + qd) * 32;
+                  for (int hq = 0; hq < 2; ++hq) {
+                    float tq[4] = {val[4 * hq], val[4 * hq + 1], val[4 * hq + 2], val[4 * hq + 3]};
+                    ft_quad_transpose(tq, lane);
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ft_split(tq[i], hi[i], lo[i]);
+                    if (ok) {
+                      const int n = c0 + 4 * hq + (lane & 3);
+                      float* p = dgq + (n >> 3) * 32 + (n & 7) * 4;
                       *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                       *reinterpret_cast<uint4*>(p + nu * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                   }
-                  if (a.dbg && mt == 0) {
+                  // column sums over the warp's 32 timesteps: 8 -> 4 -> 2 -> 1 values per lane, then the quad
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) a.dbg[((size_t)(nR + L - 1) * 128 + m) * 128 + c0 + i] = val[i];
-                  }
-                  // column sums over the warp's 32 timesteps: 16 -> 8 -> 4 -> 2 -> 1 values per lane, then the pair
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float send = (lane & 16) ? val[i] : val[i + 8];
-                    const float keep = (lane & 16) ? val[i + 8] : val[i];
+                  for (int i = 0; i < 4; ++i) {
+                    const float send = (lane & 16) ? val[i] : val[i + 4];
+                    const float keep = (lane & 16) ? val[i + 4] : val[i];
                     val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                   }
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float send = (lane & 8) ? val[i] : val[i + 4];
-                    const float keep = (lane & 8) ? val[i + 4] : val[i];
+                  for (int i = 0; i < 2; ++i) {
+                    const float send = (lane & 8) ? val[i] : val[i + 2];
+                    const float keep = (lane & 8) ? val[i + 2] : val[i];
                     val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                   }
-#pragma unroll
-                  for (int i = 0; i < 2; ++i) {
-                    const float send = (lane & 4) ? val[i] : val[i + 2];
-                    const float keep = (lane & 4) ? val[i + 2] : val[i];
-                    val[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                  }
                   {
-                    const float send = (lane & 2) ? val[0] : val[1];
-                    const float keep = (lane & 2) ? val[1] : val[0];
-                    val[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    const float send = (lane & 4) ? val[0] : val[1];
+                    const float keep = (lane & 4) ? val[1] : val[0];
+                    val[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                   }
+                  val[0] += __shfl_xor_sync(0xffffffffu, val[0], 2);
                   val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
-                  // lane holds column c0 + 8 b4 + 4 b3 + 2 b2 + b1 (b4 = bit 4 of the lane, ...)
-                  if ((lane & 1) == 0) {
-                    const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    gb1w[col] += val[0];
-                  }
+                  // lane holds column c0 + 4 b4 + 2 b3 + b2 (b4 = bit 4 of the lane, ...)
+                  if ((lane & 3) == 0) gb1w[c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] += val[0];
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) h1c[i] = h1n[i];
+                  for (int i = 0; i < 8; ++i) h1c[i] = h1n[i];
                 }
                 tc_fence_before();
                 if (tr_on) FT_TR(4, (8 << 24) | c);
@@ -770,14 +840,19 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             }
           }
         }
-        // ---- slab end: layer-1 bias partial (fixed order over the 4 delta-phase warps), logstd block = 0 (set by the reduce)
+        // ---- slab end: layer-1 bias partial (fixed order over the 8 delta-phase warps), logstd block = 0 (set by the reduce)
         ft_dbar();
         float* part = a.partm + (size_t)slab * g.pmid;
-        const int et = threadIdx.x - 256;              // 0..127 over the delta-phase warps
-        for (int f = et; f < g.d[1]; f += 128) part[g.off_b[1] + f] = (gb1s[f] + gb1s[128 + f]) + (gb1s[256 + f] + gb1s[384 + f]);
-        for (int j = et; j < g.d[L]; j += 128) part[g.off_pm_logstd + j] = 0.f;
+        const int et = threadIdx.x - 384;              // 0..255 over the delta-phase warps
+        for (int f = et; f < g.d[1]; f += 256) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += gb1s[w * 128 + f];
+          part[g.off_b[1] + f] = sum;
+        }
+        for (int j = et; j < g.d[L]; j += 256) part[g.off_pm_logstd + j] = 0.f;
         ft_dbar();
-        for (int f = et; f < 4 * 128; f += 128) gb1s[f] = 0.f;
+        for (int f = et; f < 8 * 128; f += 256) gb1s[f] = 0.f;
         ft_dbar();
       }
     }
@@ -847,7 +922,7 @@ static bool ft_build_plan(const NetGeom& g, FtPlan* P) {
     st.w_off = wc; st.v_off = vc;
     wc += st.kgs * 2 * st.N * 8;
     vc += st.kgs * 2 * st.N * 8;
-    if (2 * 2 * st.N * 8 > P->rstage_floats) P->rstage_floats = 2 * 2 * st.N * 8;     // (W, V) x (hi, lo) of one k-group
+    if (2 * 2 * 2 * st.N * 8 > P->rstage_floats) P->rstage_floats = 2 * 2 * 2 * st.N * 8;     // two k-groups x (W, V) x (hi, lo)
   }
   int nD = 0;
   for (int l = L; l >= 2; --l) {
@@ -860,7 +935,7 @@ static bool ft_build_plan(const NetGeom& g, FtPlan* P) {
       st.l = l; st.kgs = P->Kg[l]; st.N = Nout - col0 < 64 ? Nout - col0 : 64; st.col0 = col0;
       st.w_off = wc;
       wc += st.kgs * 2 * st.N * 8;
-      if (2 * st.N * 8 > P->dstage_floats) P->dstage_floats = 2 * st.N * 8;
+      if (2 * 2 * st.N * 8 > P->dstage_floats) P->dstage_floats = 2 * 2 * st.N * 8;
     }
   }
   P->nD = nD;
