@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="humanoid")
+    ap.add_argument("--workload", default="humanoid",
+                    help="humanoid (configs[2], default) | hopper (configs[1]) | walker_ppo (configs[3]) | cat_vf (configs[4]) | any synth.WORKLOADS name")
     ap.add_argument("--timesteps", type=int, default=0, help="total timesteps (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="timesteps of the CPU baseline sample (b200 arm)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget of the K+W sampled steps")
@@ -209,6 +210,27 @@ def chain_mma_flops_per_timestep(dims):
     return 3 * (3 * pairs) * 2048 / 16 + blocks * 3 * 2048 / 8
 
 
+def tc_chain_issued_flops_per_timestep(dims):
+    """TF32 tensor-core flops the tcgen05 Fisher-vector chain (mlp_fvp_tc.cu) ISSUES per timestep: 3 MMAs per product
+    (split precision), K padded to 8, N to 16, the (k) weight-gradient tiles always M = 128 rows."""
+    L = len(dims) - 1
+    r8 = lambda d: -(-d // 8) * 8
+    r16 = lambda d: -(-d // 16) * 16
+    macs = 0
+    for l in range(2, L + 1):
+        macs += 2 * r8(dims[l - 1]) * r16(dims[l])        # Rh.W and h.V
+        macs += r8(dims[l]) * r16(dims[l - 1])            # delta.W^T
+    l = L                                                   # (k) passes: consecutive layers share a 128-row tile
+    while l >= 2:
+        rows = cols = 0
+        k = l
+        while k >= 2 and rows + dims[k - 1] + 1 <= 128 and cols + r16(dims[k]) <= 128:
+            rows += dims[k - 1]; cols += r16(dims[k]); k -= 1
+        macs += 128 * cols
+        l = k
+    return 3 * 2 * macs
+
+
 def algorithmic_flops_per_timestep(dims):
     d0d1 = dims[0] * dims[1]
     S = sum(dims[l - 1] * dims[l] for l in range(2, len(dims)))
@@ -298,10 +320,242 @@ def run_parity(args, wl, n_total, rank, world, dist, dev, net, vf, batch, comm, 
     out["pass"] = bool(ok)
     return out
 
+# ----------------------------------------------------------------------------- configs[3] and configs[4]
+def kernel_table(lib, steps):
+    nk = lib.mrl_profile_kinds()
+    pms, pcnt = (C.c_double * nk)(), (C.c_longlong * nk)()
+    from modular_rl_b200 import _lib as L
+    L.check(lib.mrl_profile_read(pms, pcnt))
+    lib.mrl_profile_enable(0)
+    out = {}
+    for k in range(nk):
+        if pcnt[k]:
+            out[lib.mrl_profile_kind_name(k).decode()] = {"launches_per_step": pcnt[k] / steps, "ms_per_step": pms[k] / steps,
+                                                          "avg_ms": pms[k] / pcnt[k]}
+    return out
+
+
+def run_extra(args):
+    """`--workload walker_ppo`: PpoLbfgsUpdater penalised-KL update on the 200 k-timestep Walker2d batch (configs[3]);
+    `--workload cat_vf`: VF predict + GAE + standardise + NnVf fit on the 4 M-timestep ragged Categorical batch
+    (configs[4]).  One GPU.  scipy's L-BFGS-B runs on the host as in the reference (ppo.py:85, core.py:687), every
+    loss / gradient evaluation is a device pass over the resident batch."""
+    import scipy.optimize
+    import torch
+    from modular_rl_b200 import _lib as L, synth
+    from modular_rl_b200.device import DeviceBatch, DeviceNet
+    from oracle import advantage as oadv, policy_math as pm, ppo_penalty, valuefn as vfo
+    torch.cuda.set_device(0)
+    lib = L.lib()
+    ppo = args.workload == "walker_ppo"
+    wl = synth.WORKLOADS["walker2d" if ppo else "cat128"]
+    N = args.timesteps or wl.N
+    rng = np.random.default_rng(wl.seed)
+    theta0 = synth.init_params(wl.dims, wl.head, rng)
+    ob = synth.make_obs(N, wl.dims[0], rng)
+    off, term = synth.make_paths(N, wl.t_max, rng)
+    reward = rng.standard_normal(N)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    ob_h, reward_h = pin(ob), pin(reward)
+    batch = DeviceBatch(wl.dims[0], True)
+    batch.set_obs(ob).set_paths(off, term, float(wl.t_max))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sampler = ClockSampler(0)
+    maxiter = 25
+    if ppo:
+        net = DeviceNet(wl.dims, wl.head)
+        net.set_params(theta0)
+        out = net.forward(batch)
+        d = wl.dims[-1]
+        oldprob = np.concatenate([out, np.broadcast_to(np.exp(theta0[-d:])[None], out.shape)], 1).astype(np.float32)
+        act = synth.sample_actions(wl.head, oldprob, rng)
+        adv = rng.standard_normal(N)
+        adv = ((adv - adv.mean()) / adv.std()).astype(np.float32)
+        act_h, adv_h, oldprob_h = pin(act), pin(adv), pin(oldprob)
+        batch.set_policy_inputs(wl.head, d, act, adv, oldprob)
+        theta = synth.perturb(theta0, 0.01, wl.seed + 7)
+        kl_coeff, kl_target = 1.0, 0.01
+        evals = [0]
+
+        def update(b):
+            def lossandgrad(th):
+                evals[0] += 1
+                net.set_params(th)
+                pen, g, _ = net.ppo_lossgrad(b, kl_coeff, 2 * kl_target)
+                return pen, g
+            net.set_params(theta)
+            before = net.ppo_lossgrad(b, kl_coeff, 2 * kl_target, want_grad=False)[2]
+            th, _, _ = scipy.optimize.fmin_l_bfgs_b(lossandgrad, theta.astype(np.float64), maxiter=maxiter)
+            net.set_params(th)
+            after = net.ppo_lossgrad(b, kl_coeff, 2 * kl_target, want_grad=False)[2]
+            return before, after
+
+        step_resident = lambda: update(batch)
+        batch2 = DeviceBatch(wl.dims[0], True)
+
+        def step_e2e():
+            batch2.set_obs(ob_h.numpy()).set_paths(off, term, float(wl.t_max))
+            batch2.set_policy_inputs(wl.head, d, act_h.numpy(), adv_h.numpy(), oldprob_h.numpy())
+            return update(batch2)
+        h2d = ob_h.numel() * 4 + act_h.numel() * 4 + adv_h.numel() * 4 + oldprob_h.numel() * 4 + off.nbytes + term.nbytes
+        d2h = 0
+        metric, what = "ppo_lbfgs_update_timesteps_per_sec", "PpoLbfgsUpdater update (penalised KL, L-BFGS-B maxiter 25 on the host, ppo.py:59-112)"
+    else:
+        vdims = (wl.dims[0] + 1, 64, 64, 1)
+        vf = DeviceNet(vdims, synth.VALUE)
+        vtheta = synth.init_params(vdims, synth.VALUE, np.random.default_rng(wl.seed + 1), last_scale=1.0)
+        vf.set_params(vtheta)
+        reward_d = reward_h.cuda()
+        evals = [0]
+        ret_h = torch.empty(N, dtype=torch.float64).pin_memory()
+        adv_h = torch.empty(N, dtype=torch.float64).pin_memory()
+
+        def fit(b):
+            def lossandgrad(th):
+                evals[0] += 1
+                vf.set_params(th)
+                ls, g = vf.vf_lossgrad(b, 1e-3)
+                return ls[0], g
+            b.mix_vf_target(0.1)                                # core.py:622-624, mixfrac = 0.1 (agentzoo.py:60)
+            th, _, _ = scipy.optimize.fmin_l_bfgs_b(lossandgrad, vtheta.astype(np.float64), maxiter=maxiter)
+            vf.set_params(th)
+            return vf.vf_lossgrad(b, 1e-3, want_grad=False)[0]
+
+        def step_resident():
+            vf.set_params(vtheta)
+            vf.predict_into_baseline(batch)
+            batch.gae(reward_d, None, CFG["gamma"], CFG["lam"], True, None, want_outputs=False)
+            return fit(batch)
+        batch2 = DeviceBatch(wl.dims[0], True)
+
+        def step_e2e():
+            batch2.set_obs(ob_h.numpy()).set_paths(off, term, float(wl.t_max))
+            vf.set_params(vtheta)
+            vf.predict_into_baseline(batch2)
+            batch2.gae(reward_h.numpy(), None, CFG["gamma"], CFG["lam"], True, None, out=(ret_h.numpy(), adv_h.numpy()))
+            return fit(batch2)
+        h2d = ob_h.numel() * 4 + reward_h.numel() * 8 + off.nbytes + term.nbytes
+        d2h = 2 * N * 8
+        metric, what = "gae_vf_fit_timesteps_per_sec", "VF predict + GAE + standardise + NnVf.fit (L-BFGS-B maxiter 25 on the host, core.py:63-105,619-697)"
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if profile:
+            lib.mrl_profile_enable(1)
+        l0 = lib.mrl_launch_count()
+        evals[0] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), int(lib.mrl_launch_count() - l0), res, evals[0] / steps
+    sampler.start()
+    ms, launches, res, n_eval = timed(step_resident, args.steps, max(args.warmup, 3))
+    pms, _, _, _ = timed(step_resident, args.steps, 1, profile=True)
+    clocks = sampler.stop()
+    kernels = kernel_table(lib, args.steps)
+    ems, _, _, _ = timed(step_e2e, args.steps, 3)
+    fp32, tc32 = C.c_double(), C.c_double()
+    L.check(lib.mrl_measure_fp32_tflops(0, C.byref(fp32)))
+    L.check(lib.mrl_measure_tcgen05_tf32_tflops(0, C.byref(tc32)))
+    dims = wl.dims if ppo else vdims
+    flops = algorithmic_flops_per_timestep((dims[0],) + tuple(dims[1:]))
+    for k, v in kernels.items():
+        if k in flops:
+            v["algo_tflops"] = flops[k] * N / (v["avg_ms"] * 1e-3) / 1e12
+    top = max((k for k in kernels if k in flops), key=lambda k: kernels[k]["ms_per_step"])
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    roof = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["algo_tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": kernels[top]["algo_tflops"] / peak_tf, "traffic": None,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"),
+            "flops_counted": "algorithmic FP32 flops; each costs 3 TF32 MMAs", "tcgen05_tf32_peak_tflops": tc32.value,
+            "fp32_fma_peak_tflops": fp32.value, "share_of_step": kernels[top]["ms_per_step"] / (pms / args.steps),
+            "device_ms_per_step_all_kernels": sum(v["ms_per_step"] for v in kernels.values()),
+            "host_ms_per_step": ms / args.steps - sum(v["ms_per_step"] for v in kernels.values())}
+    extra_roof = None
+    if not ppo and "gae" in kernels:
+        gbs = 24.0 * N / (kernels["gae"]["avg_ms"] * 1e-3) / 1e9
+        hbm = peaks.get("hbm_gbs") or 6650.0
+        extra_roof = {"kernel": "gae", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                      "algorithmic_bytes_per_timestep": 24, "real_bytes_per_timestep": 40,
+                      "note": "24 B = float32 reward/baseline in, return/advantage out + standardise; the kernel moves float64 reward, baseline, return, advantage"}
+    # ---- parity at full size (outside the timed region) and the CPU port on a bounded sample
+    if args.verify == "none":
+        print(json.dumps({"metric": metric, "value": N * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                          "kernels": kernels, "note": "--verify none: timing only"}), flush=True)
+        return
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    n_cpu = min(N, 100_000 if ppo else 400_000)
+    k = int(np.searchsorted(off, n_cpu, side="right"))
+    offc = np.concatenate([off[:k], [n_cpu]]) if off[k - 1] != n_cpu else off[:k]
+    termc = term[:len(offc) - 1]
+    if ppo:
+        spec = pm.NetSpec(wl.dims, pm.GAUSS)
+        net.set_params(theta)
+        pen, g, ls = net.ppo_lossgrad(batch, kl_coeff, 2 * kl_target)
+        open_, og = pm.ppo_lossgrad(theta, spec, ob, act, adv, oldprob, kl_coeff, 2 * kl_target)
+        parity = {"timesteps": N, "pensurr_abs": float(abs(pen - open_)), "grad_rel_l2": rel(g, og), "tolerance": 1e-5,
+                  "pass": bool(rel(g, og) < 2e-5)}
+        t0 = time.perf_counter()
+        ppo_penalty.ppo_lbfgs_update(theta, spec, ob[:n_cpu], act[:n_cpu], adv[:n_cpu], oldprob[:n_cpu], kl_coeff, kl_target,
+                                     maxiter=maxiter, dtype=np.float32)
+        sec = time.perf_counter() - t0
+    else:
+        spec = pm.NetSpec(vdims, pm.VALUE)
+        vf.set_params(vtheta)
+        base = vf.forward(batch)[:, 0]
+        vf.predict_into_baseline(batch)
+        ret, advd = batch.gae(reward, None, CFG["gamma"], CFG["lam"], True)
+        oret, oad = oadv.gae_flat(reward, base.astype(np.float64), off, term, CFG["gamma"], CFG["lam"])
+        tidx, _ = oadv.time_index(off)
+        x = np.empty((N, vdims[0]), np.float64)
+        x[:, :-1] = ob
+        x[:, -1] = tidx / float(wl.t_max)
+        batch.set_vf_target(ret)
+        lsd, gd = vf.vf_lossgrad(batch, 1e-3)
+        _, og = vfo.vf_lossgrad(vtheta, spec, x, oret.reshape(-1, 1), l2coeff=1e-3)
+        parity = {"timesteps": N, "returns_rel_l2": rel(ret, oret), "advantages_max_abs": float(np.max(np.abs(advd - oadv.standardize(oad)))),
+                  "vf_grad_rel_l2": rel(gd, og), "time_index_exact": bool(np.array_equal(batch.time_index(), tidx.astype(np.int32))),
+                  "tolerance": 1e-5, "pass": bool(rel(gd, og) < 1e-5 and rel(ret, oret) < 1e-12)}
+        t0 = time.perf_counter()
+        b32 = base[:n_cpu]
+        r_, a_ = oadv.gae_flat(reward[:n_cpu], b32, offc, termc, CFG["gamma"], CFG["lam"])
+        oadv.standardize(a_)
+        vfo.regression_fit(vtheta, spec, x[:n_cpu].astype(np.float32), r_.reshape(-1, 1), mixfrac=0.1, maxiter=maxiter, dtype=np.float32)
+        sec = time.perf_counter() - t0
+    threads = blas_threads()
+    cpu = {"value": n_cpu / sec, "unit": UNIT, "cores": threads or HOST_CORES, "kind": "port",
+           "sample": f"one step on {n_cpu} of {N} timesteps ({sec:.1f} s), oracle port in float32 (numpy + scipy L-BFGS-B / lfilter), {threads} BLAS threads"}
+    line = {"metric": metric, "value": N * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: obs {wl.dims[0]}, {N} timesteps, {len(term)} trajectories; step = {what}",
+                       "timesteps": N, "lossgrad_evals_per_step": n_eval, "maxiter": maxiter,
+                       "l2": "inputs larger than L2" if N * wl.dims[0] * 4 > 126e6 else "L2 flushed by the step's own traffic (> 126 MB per step)",
+                       **CFG},
+            "roofline": roof, "roofline_gae": extra_roof, "cpu_baseline": cpu,
+            "e2e": {"value": N * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ems / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "kernels": kernels, "parity": parity,
+            "result": [float(v) for v in np.ravel(res[1] if ppo else res)]}
+    print(json.dumps(line), flush=True)
+
 
 def main():
     args = parse()
     from modular_rl_b200 import synth
+    if args.workload in ("walker_ppo", "cat_vf"):
+        if args.impl == "reference" or int(os.environ.get("WORLD_SIZE", 1)) > 1:
+            raise SystemExit("--workload walker_ppo / cat_vf: one GPU, b200 arm only")
+        return run_extra(args)
     wl = synth.WORKLOADS[args.workload]
     n_total = args.timesteps or wl.N
     rank = int(os.environ.get("RANK", 0))
@@ -455,9 +709,11 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        fp32, mma32 = C.c_double(), C.c_double()
+        fp32, mma32, tc32 = C.c_double(), C.c_double(), C.c_double()
         L.check(lib.mrl_measure_fp32_tflops(local_rank, C.byref(fp32)))
         L.check(lib.mrl_measure_mma_tf32_tflops(local_rank, C.byref(mma32)))
+        L.check(lib.mrl_measure_tcgen05_tf32_tflops(local_rank, C.byref(tc32)))
+        fvp_on_tc = os.environ.get("MRL_FVP_TC", "1") != "0" and wl.name in ("humanoid", "hopper", "walker2d", "cat128", "cartpole")
         flops = algorithmic_flops_per_timestep(wl.dims)
         kernels = {}
         for k in range(nk):
@@ -481,7 +737,10 @@ def main():
                 traffic = tr["kernels"][top]["read"] + tr["kernels"][top]["write"]
         except Exception:
             pass
-        pipes = {"mid_backward_fvp": "per-warp register chain, mma.sync TF32 x3 split precision (FP32-class accuracy) + FP32 epilogues",
+        pipes = {"mid_backward_fvp": ("tcgen05.mma kind::tf32 x3 split precision in TS mode (activations written to TMEM by the epilogue warps, "
+                                      "weights streamed through a shared-memory ring), R-forward and delta phases of consecutive tiles overlapped"
+                                      if fvp_on_tc else
+                                      "per-warp register chain, mma.sync TF32 x3 split precision (FP32-class accuracy) + FP32 epilogues"),
                  "mid_backward_grad": "per-warp register chain, mma.sync TF32 x3 split precision + FP32 heads",
                  "mid_forward": "per-warp register chain, mma.sync TF32 x3 split precision + FP32 heads",
                  "l1_forward": "tcgen05.mma kind::tf32 x3 split precision, TMEM accumulators, raw-fp32 operand split in shared memory",
@@ -491,15 +750,21 @@ def main():
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else
                                 "fallback 1.4 PFLOP/s sustained (of fallback)"),
                 "pipe": pipes.get(top, ""), "flops_counted": "algorithmic FP32 flops; each costs 3 TF32 MMAs",
-                "tf32_mma_tflops_issued": (chain_mma_flops_per_timestep(wl.dims) * n_local / (kernels[top]["avg_ms"] * 1e-3) / 1e12
+                "tf32_mma_tflops_issued": (((tc_chain_issued_flops_per_timestep if fvp_on_tc else chain_mma_flops_per_timestep)(wl.dims)
+                                            * n_local / (kernels[top]["avg_ms"] * 1e-3) / 1e12)
                                            if top == "mid_backward_fvp" else 3.0 * kernels[top]["algo_tflops"]),
                 "mma_sync_tf32_peak_tflops": mma32.value,
+                "tcgen05_tf32_peak_tflops": tc32.value,
                 "fp32_fma_peak_tflops": fp32.value,
                 "frac_of_fp32_fma_peak": kernels[top]["algo_tflops"] / fp32.value,
                 "share_of_step": kernels[top]["ms_per_step"] / (pms_total / args.steps),
                 "kernel_events": "second pass of the same %d steps with per-kernel CUDA events (%.3f ms per step; "
                                  "the timed region itself has none)" % (args.steps, pms_total / args.steps)}
-        roof["frac_of_mma_sync_tf32_peak"] = roof["tf32_mma_tflops_issued"] / mma32.value if mma32.value else None
+        on_tc = top in ("l1_forward", "l1_grad") or (top == "mid_backward_fvp" and fvp_on_tc)
+        if on_tc:
+            roof["frac_of_tcgen05_tf32_peak"] = roof["tf32_mma_tflops_issued"] / tc32.value if tc32.value else None
+        else:
+            roof["frac_of_mma_sync_tf32_peak"] = roof["tf32_mma_tflops_issued"] / mma32.value if mma32.value else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))

@@ -56,6 +56,9 @@ int mrl_profile_read(double* ms_out, long long* count_out);
 int mrl_measure_fp32_tflops(int device, double* tflops_out);
 /* measured mma.sync m16n8k8 TF32 throughput (dense TFLOP/s): the pipe of the register-chain kernels */
 int mrl_measure_mma_tf32_tflops(int device, double* tflops_out);
+/* measured tcgen05.mma kind::tf32 throughput (dense TFLOP/s, TS mode, M = 128, N = 128): the pipe of the layer-1 GEMMs
+ * and of the Fisher-vector chain (mlp_l1_tc.cu, mlp_fvp_tc.cu); every algorithmic product costs three of these */
+int mrl_measure_tcgen05_tf32_tflops(int device, double* tflops_out);
 
 /* ---------------------------------------------------------------- batch (paths, flattened)
  * Replaces the `concat([path[k] for path in paths])` host copies of trpo.py:74-77,

@@ -41,6 +41,7 @@ _SIGS = {
     "mrl_profile_read": (_I, [_P, _P]),
     "mrl_measure_fp32_tflops": (_I, [_I, _P]),
     "mrl_measure_mma_tf32_tflops": (_I, [_I, _P]),
+    "mrl_measure_tcgen05_tf32_tflops": (_I, [_I, _P]),
     "mrl_batch_refresh_advantages": (_I, [_P, _P]),
     "mrl_batch_create": (_I, [C.POINTER(_P), _I, _I, _I]),
     "mrl_batch_destroy": (_I, [_P]),
