@@ -199,6 +199,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def nvlink_kib(gpu_index):
+    """(tx KiB, rx KiB) summed over the NVLink links of one GPU (nvidia-smi nvlink -gt d), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        for ln in out.splitlines():
+            f = ln.split()
+            if "Tx:" in f:
+                tx += int(f[f.index("Tx:") + 1])
+            if "Rx:" in f:
+                rx += int(f[f.index("Rx:") + 1])
+        return (tx, rx) if (tx or rx) else None
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def chain_mma_flops_per_timestep(dims):
     """TF32 tensor-core flops the backward chain kernel ISSUES per timestep for an Fvp (3xTF32, widths padded to 8,
@@ -682,7 +698,16 @@ def main():
     # of a step opens ~4 us of launch gap each (0.43 ms per step, measured; 1 % at 1M timesteps on one
     # GPU but 7 % of the 8-GPU step).  The per-kernel table and the roofline come from a second pass of the
     # same K steps, in this process, with the library's CUDA events on the launching stream.
+    nv0 = nvlink_kib(local_rank) if (rank == 0 and world > 1) else None
     ms, launches, (stats, info) = timed(step_resident, args.steps, max(args.warmup, 3))
+    nv1 = nvlink_kib(local_rank) if (rank == 0 and world > 1) else None
+    nvlink = None
+    if nv0 and nv1:
+        nsteps = args.steps + max(args.warmup, 3)
+        nvlink = {"tx_kib_per_step": (nv1[0] - nv0[0]) / nsteps, "rx_kib_per_step": (nv1[1] - nv0[1]) / nsteps,
+                  "how": "nvidia-smi nvlink -gt d on rank 0's GPU around the warm-up + timed steps",
+                  "expected_kib_per_step": 13 * net.P * 8 * (world - 1) / 1024.0,
+                  "what": "each of the 13 sums over ranks per update (1 gradient, 11 Fvp, loss triples apart) pushes P doubles to every peer"}
     pms_total, _, _ = timed(step_resident, args.steps, 1, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     nk = lib.mrl_profile_kinds()
@@ -783,7 +808,7 @@ def main():
                            "l2": "inputs larger than L2 (observations %.2f GB per GPU)" % (n_local * wl.dims[0] * 4 / 1e9),
                            **CFG},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "kernels": kernels, "parity": parity,
+                "kernels": kernels, "parity": parity, "nvlink": nvlink,
                 "update": {"stats": [float(s) for s in stats], "info": info}}
         print(json.dumps(line), flush=True)
     if world > 1:

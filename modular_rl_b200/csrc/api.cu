@@ -852,7 +852,8 @@ static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
 
 // reverse sweep + layer-1 gradient + slab reduce -> out32 (float[P], device) and out64 (double[P]).
 static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
-                         const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
+                         const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st,
+                         P2pGather* defer = nullptr) {
   const NetGeom& g = n->g;
   const bool tc = mode == MRL_MODE_FVP && n->tc_fvp;
   const Plan pl = plan_for(b, tc);
@@ -863,7 +864,9 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.imgv = nullptr;
   a.Zt = nullptr;
   if (mode == MRL_MODE_FVP) {
-    CKP(PK_PACK, launch_pack_params(g, v_dev, n->imgv.as<float>(), n->WBv.as<float>(), st), 1);
+    // tangent -> operand images: one launch packs the layer-1 operand and (tcgen05 chain) the chain images
+    if (tc) CKP(PK_PACK, launch_fvp_tc_pack(g, v_dev, n->VC.as<float>(), 1, st, n->WBv.as<float>()), 1);
+    else CKP(PK_PACK, launch_pack_params(g, v_dev, n->imgv.as<float>(), n->WBv.as<float>(), st), 1);
     CKP(PK_L1F, launch_l1_forward_tc(g, b->XA.as<float>(), b->d0p / 8, n->WBv.as<float>(), n->Z1.as<float>(), b->n_tiles, st), 1);
     a.imgv = n->imgv.as<float>();
     a.Zt = n->Z1.as<float>();
@@ -880,7 +883,6 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   a.mode = mode;
   a.reverse_kl = reverse_kl;
   if (tc) {
-    CKP(PK_PACK, launch_fvp_tc_pack(g, v_dev, n->VC.as<float>(), 1, st), 1);
     FvpTcArgs x;
     x.WC = n->WC.as<float>(); x.VC = n->VC.as<float>(); x.vflat = v_dev; x.img = n->img.as<float>();
     x.Zt = n->Z1.as<float>(); x.cache = n->cache.as<float>(); x.DG = n->DG.as<float>(); x.partm = n->partm.as<float>();
@@ -902,7 +904,10 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
                              mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32,
                              p2p ? nullptr : out64, p2p ? &push : nullptr, st), 1);
-  if (p2p) {          // fused: the reduce kernel pushed this rank's vector to every peer; wait + sum in rank order
+  if (defer) defer->world = 0;
+  if (p2p && defer) {   // the caller's next kernel (the CG iteration) is the receiving side of the sum
+    RET(mrl_comm_p2p_pending(n->comm, defer));
+  } else if (p2p) {     // fused: the reduce kernel pushed this rank's vector to every peer; wait + sum in rank order
     RET(mrl_comm_p2p_finish(n->comm, g.P, out64, out32, st));
     g_launches += 1;
   } else if (world > 1) {
@@ -1073,12 +1078,15 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   CK(cudaMemcpyAsync(n->h_scal, n->scal.p, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(n->h_cg, n->cgstate.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
   // CG does not depend on the host check below, so it is enqueued before the sync
+  const bool fuse_rx = cg_step_fuses_gather(P);
   for (int it = 0; it < cfg->cg_iters; ++it) {
+    P2pGather ga;
+    ga.world = 0;
     RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
-                      n->out64.as<double>(), st));
+                      n->out64.as<double>(), st, fuse_rx ? &ga : nullptr));
     CKP(PK_CG, launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
                        n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(),
-                       n->cgscratch.as<double>(), st), 1);
+                       n->cgscratch.as<double>(), st, ga.world ? &ga : nullptr), 1);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
   RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),

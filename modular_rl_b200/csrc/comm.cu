@@ -208,40 +208,34 @@ int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push) {
 // Wait until every rank's flag of this parity shows `seq`, then out[i] = sum_r slot[r][i] in rank order.
 // Double buffering by parity is enough: rank r can only start operation seq+2 after it has seen every
 // rank's flag for seq+1, which a rank raises after it finished reading the slots of seq.
-__global__ void p2p_gather_kernel(const unsigned long long* __restrict__ flags, const double* __restrict__ slots,
-                                  long long cap, int world, unsigned long long seq, long long n,
-                                  double* __restrict__ out64, float* __restrict__ out32,
-                                  unsigned long long timeout_ns, int* __restrict__ err) {
-  if (threadIdx.x < world) {
-    const unsigned long long* f = flags + threadIdx.x;
-    unsigned long long t0 = 0;
-    unsigned int spins = 0;
-    while (ld_acquire_sys(f) < seq) {
-      // a peer may legitimately be late by seconds (its host is busy); the bound is wall-clock time, and a
-      // lost peer becomes an error word the host checks - never a trap, never a hung GPU
-      if ((++spins & 1023u) == 0) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > timeout_ns) { *err = 1; break; }
-      }
-    }
-  }
-  __syncthreads();
+__global__ void p2p_gather_kernel(P2pGather ga, long long n, double* __restrict__ out64, float* __restrict__ out32) {
+  p2p_wait_flags(ga);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int r = 0; r < world; ++r) s += __ldcg(slots + (size_t)r * cap + i);
+    for (int r = 0; r < ga.world; ++r) s += __ldcg(ga.slots + (size_t)r * ga.cap + i);
     if (out64) out64[i] = s;
     if (out32) out32[i] = (float)s;
   }
 }
-int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st) {
+int mrl_comm_p2p_pending(mrl_comm* c, P2pGather* out) {
+  if (!c || !c->p2p.on) return mrl_set_error("mrl_comm_p2p_pending: transport not ready");
   P2pState& p = c->p2p;
   const int parity = (int)(p.seq & 1);
+  out->flags = p2p_flags(p.local, parity);
+  out->slots = p2p_slot(p.local, p.cap, c->world, parity, 0);
+  out->cap = p.cap;
+  out->seq = p.seq;
+  out->timeout_ns = p.timeout_ns;
+  out->err = p.d_err;
+  out->world = c->world;
+  return 0;
+}
+int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st) {
+  P2pGather ga;
+  if (mrl_comm_p2p_pending(c, &ga)) return 1;
   int blocks = (int)((n + 255) / 256);
-  if (blocks > 64) blocks = 64;     // all CTAs are resident: they spin on the flags
-  p2p_gather_kernel<<<blocks, 256, 0, st>>>(p2p_flags(p.local, parity), p2p_slot(p.local, p.cap, c->world, parity, 0), p.cap,
-                                            c->world, p.seq, n, out64, out32, p.timeout_ns, p.d_err);
+  if (blocks > 64) blocks = 64;     // all CTAs are resident: they poll the flags
+  p2p_gather_kernel<<<blocks, 256, 0, st>>>(ga, n, out64, out32);
   if (cudaGetLastError() != cudaSuccess) return mrl_set_error("p2p_gather_kernel launch failed");
   return 0;
 }

@@ -21,7 +21,20 @@ struct P2pPush {
   unsigned long long seq;
   int world;                    // 0: no push
 };
+// The receiving side of one peer-memory sum, for a kernel that folds the wait + rank-order sum into its own work
+// (cg_step_cluster_kernel): where this rank's receive slots and flags of the pending operation are.
+struct P2pGather {
+  const unsigned long long* flags;   // [world] sequence flags of the operation's parity
+  const double* slots;               // [world][cap]
+  long long cap;
+  unsigned long long seq, timeout_ns;
+  int* err;                          // mapped host word, set on timeout
+  int world;                         // 0: no gather (single rank or NCCL path)
+};
 bool mrl_comm_p2p_ready(const mrl_comm* c, long long n);
+// Arguments of the operation begun last with mrl_comm_p2p_begin.  The caller's kernel then takes the place of
+// mrl_comm_p2p_finish: it MUST call p2p_wait_flags (even if it has nothing to do with the sum) and read the slots.
+int mrl_comm_p2p_pending(mrl_comm* c, P2pGather* out);
 // Begin one all-reduce of n doubles: fills `push` for the producing kernel.  Every begin must be followed by
 // mrl_comm_p2p_finish on the same stream.
 int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push);
@@ -39,6 +52,25 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+// Wait until every rank's flag shows the operation's sequence number (threads 0..world-1 of the CTA poll, then the CTA
+// synchronises).  A peer may legitimately be late by seconds; the bound is wall-clock time and a lost peer becomes an
+// error word the host checks - never a trap, never a hung GPU.
+__device__ __forceinline__ void p2p_wait_flags(const P2pGather& ga) {
+  if (threadIdx.x < ga.world) {
+    const unsigned long long* f = ga.flags + threadIdx.x;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (ld_acquire_sys(f) < ga.seq) {
+      if ((++spins & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > ga.timeout_ns) { *ga.err = 1; break; }
+      }
+    }
+  }
+  __syncthreads();
 }
 __device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) {
 #pragma unroll

@@ -96,7 +96,8 @@ struct FvpTcArgs {
 };
 bool fvp_tc_supported(const NetGeom& g);
 size_t fvp_tc_image_floats(const NetGeom& g, int tangent);
-cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* dst, int tangent, cudaStream_t st);
+// WB1 != nullptr: also the layer-1 tensor-core operand of the same vector (one launch per tangent instead of two)
+cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* dst, int tangent, cudaStream_t st, float* WB1 = nullptr);
 cudaError_t launch_fvp_tc(const NetGeom& g, const FvpTcArgs& a, cudaStream_t st);
 
 // ---- vec_kernels.cu  (CG / line-search vector algebra on device-resident fp64 vectors)
@@ -108,9 +109,12 @@ cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* 
                            CgState* s, cudaStream_t st);
 #define CG_CTAS 32                              // co-resident CTAs of the CG iteration kernel
 #define CG_SCRATCH_DOUBLES (2 * CG_CTAS + 40)   // two partial-sum rows + the grid barrier words
+// ga != nullptr (data-parallel, peer-memory transport): the kernel is also the receiving side of the pending sum
+// over ranks and takes z from the receive slots instead of z32 (only where cg_step_fuses_gather(P))
+bool cg_step_fuses_gather(int P);
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
                            float* p32, CgState* s, double* scratch /* CG_SCRATCH_DOUBLES, zeroed once */,
-                           cudaStream_t st);
+                           cudaStream_t st, const struct P2pGather* ga = nullptr);
 cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st);
 cudaError_t launch_cg_finish(int P, const float* z32, double damping, double max_kl, const float* g,
                              const double* x, double* fullstep, CgState* s, cudaStream_t st);

@@ -873,9 +873,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
 // B[n = in - col0][k = out].
 struct FtPackJob { int off, N, kgs, l, transposed, col0, end; };
 struct FtPackJobs { FtPackJob j[FT_MAX_R + FT_MAX_D]; int n; };
-__global__ void ft_pack_kernel(NetGeom g, FtPackJobs jobs, const float* __restrict__ src, float* __restrict__ dst, int total) {
+__global__ void ft_pack_kernel(NetGeom g, FtPackJobs jobs, const float* __restrict__ src, float* __restrict__ dst, int total,
+                               float* __restrict__ WB1, int nu) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  if (i >= total) {
+    // the layer-1 operand of the same vector (WB of mlp_l1_tc.cu: [kg][hi|lo][khalf][ngroup][8][4]) in the same launch
+    const int j = i - total;
+    if (WB1 == nullptr || j >= g.d0p * nu) return;
+    const int k = j / nu, n = j % nu;
+    const float x = (k < g.d[0] && n < g.d[1]) ? src[g.off_flat_W[1] + k * g.d[1] + n] : 0.f;
+    const float h = tf32_rna(x);
+    float* base = WB1 + (size_t)(k >> 3) * (2 * nu * 8) + ((k & 7) >> 2) * (nu * 4) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);
+    base[0] = h;
+    base[nu * 8] = tf32_rna(x - h);
+    return;
+  }
   int q = 0, base = 0;
   while (q < jobs.n - 1 && i >= jobs.j[q].end) { base = jobs.j[q].end; ++q; }
   const FtPackJob jb = jobs.j[q];
@@ -1012,7 +1024,7 @@ size_t fvp_tc_image_floats(const NetGeom& g, int tangent) {
   if (!ft_build_plan(g, &P)) return 0;
   return tangent ? P.vc_floats : P.wc_floats;
 }
-cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* dst, int tangent, cudaStream_t st) {
+cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* dst, int tangent, cudaStream_t st, float* WB1) {
   FtPlan P;
   if (!ft_build_plan(g, &P)) return cudaErrorInvalidConfiguration;
   FtPackJobs jobs;
@@ -1034,7 +1046,9 @@ cudaError_t launch_fvp_tc_pack(const NetGeom& g, const float* src_flat, float* d
     total += sg.N * sg.kgs * 8;
     jb.end = total;
   }
-  ft_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, jobs, src_flat, dst, total);
+  const int nu = l1tc_nu(g);
+  const int n_all = total + (WB1 ? g.d0p * nu : 0);
+  ft_pack_kernel<<<(n_all + 255) / 256, 256, 0, st>>>(g, jobs, src_flat, dst, total, WB1, nu);
   return cudaGetLastError();
 }
 
