@@ -169,6 +169,14 @@ int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char handle_out[64])
 int mrl_comm_p2p_connect(mrl_comm* c, const char* handles /* [world][64] */);
 int mrl_comm_p2p_enable(mrl_comm* c, int on);   /* after every rank connected successfully */
 
+/* ---------------------------------------------------------------- population forward (cross-entropy method)
+ * cem.py:43-44 scores every candidate theta of an iteration by one rollout, one candidate at a time; this entry point
+ * evaluates the net of ALL candidates at once: member m has its own flat theta (Dense kernels and biases in the
+ * reference's order, no logstd; row stride ld_theta) and its own observation; out[m] is the raw output of the linear
+ * last layer (agentzoo.py:63-81).  thetas / obs / out live where `loc` says. */
+int mrl_population_forward(int device, int n_layers, const int* dims, int activation, const float* thetas,
+                           long long ld_theta, const float* obs, int n_members, float* out, int loc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,7 @@ _SIGS = {
     "mrl_net_vf_lossgrad": (_I, [_P, _P, _D, _P, _P, _P]),
     "mrl_net_trpo_step": (_I, [_P, _P, C.POINTER(TrpoCfg), _P, _P, _P]),
     "mrl_net_get_trpo_vectors": (_I, [_P, _P, _P, _P]),
+    "mrl_population_forward": (_I, [_I, _I, C.POINTER(_I), _I, _P, _LL, _P, _I, _P, _I, _P]),
     "mrl_comm_unique_id": (_I, [_P]),
     "mrl_comm_create": (_I, [C.POINTER(_P), _P, _I, _I, _I]),
     "mrl_comm_destroy": (_I, [_P]),

@@ -8,7 +8,7 @@ from __future__ import print_function
 
 import numpy as np
 
-from .core import rollout
+from .core import _filter_block, rollout
 from .misc_utils import update_default_config
 
 try:
@@ -16,6 +16,41 @@ try:
 except ImportError:  # pragma: no cover
     def tabulate(rows):
         return "\n".join(" ".join("%10.4g" % v for v in r) for r in rows)
+
+
+def evaluate_population(env, agent, ths, timestep_limit):
+    """Total reward of one rollout per candidate theta, all candidates in lockstep: per step ONE launch evaluates every
+    live member's net on its own observation (`mrl_population_forward`) - the population-batched forward of SURVEY
+    section 8f rank 4; the reference scores the candidates one rollout after another (cem.py:43-44,88-91).  The
+    environments are copies of `env`; the agent's filters see the observations of a step as one block."""
+    import copy
+    from .core import Categorical
+    from .device import population_forward
+    pol = agent.policy
+    ths = np.asarray(ths, np.float32)
+    M = ths.shape[0]
+    envs = [copy.deepcopy(env) for _ in range(M)]
+    obs = [e.reset() for e in envs]
+    total = np.zeros(M)
+    live = list(range(M))
+    discrete = isinstance(pol.probtype, Categorical)
+    for _ in range(timestep_limit):
+        if not live:
+            break
+        block = _filter_block(agent.obfilter, np.stack([np.asarray(obs[i], np.float64) for i in live]))
+        out = population_forward(pol.dims, pol.activation, ths[live], block)
+        acts = out.argmax(axis=1) if discrete else out          # maxprob of the deterministic policy (core.py:364-365,437-438)
+        rews, still = [], []
+        for j, i in enumerate(live):
+            ob, rew, done, _ = envs[i].step(acts[j])
+            obs[i] = ob
+            total[i] += rew
+            rews.append(rew)
+            if not done:
+                still.append(i)
+        _filter_block(agent.rewfilter, np.asarray(rews, np.float64))
+        live = still
+    return total
 
 
 def cem(f, th_mean, batch_size, n_iter, elite_frac, initial_std=1.0, extra_std=0.0, std_decay_time=1.0, pool=None):
@@ -31,7 +66,10 @@ def cem(f, th_mean, batch_size, n_iter, elite_frac, initial_std=1.0, extra_std=0
         print("extra var", extra_var_multiplier)
         sample_std = np.sqrt(th_std + np.square(extra_std) * extra_var_multiplier)
         ths = th_mean[None, :] + sample_std[None, :] * np.random.randn(batch_size, th_mean.size)
-        ys = np.array(list(map(f, ths)) if pool is None else pool.map(f, ths))
+        if getattr(f, "population", None) is not None:
+            ys = np.asarray(f.population(ths))                  # all candidates in one lockstep evaluation
+        else:
+            ys = np.array(list(map(f, ths)) if pool is None else pool.map(f, ths))
         assert ys.ndim == 1
         elite_inds = ys.argsort()[-n_elite:]
         elite_ths = ths[elite_inds]
@@ -53,9 +91,10 @@ CEM_OPTIONS = [
 
 
 def run_cem_algorithm(env, agent, usercfg=None, callback=None):
-    """cem.py:63-98.  `parallel` is accepted and ignored: the reference forks a process pool around a CPU
-    Theano function; a forked child cannot share this process's CUDA context, and one GPU serves the
-    population sequentially faster than the hosts' cores run the environment."""
+    """cem.py:63-98.  `parallel=1`: the reference forks a process pool around a CPU Theano function (every worker with
+    its own copy of the agent and its filters); a forked child cannot share this process's CUDA context, so here
+    parallel=1 scores the whole population in lockstep with one population-batched device forward per environment step
+    (`evaluate_population`).  parallel=0 scores one candidate after another as cem.py:43 does."""
     cfg = update_default_config(CEM_OPTIONS, usercfg)
     if cfg["std_decay_time"] < 0:
         cfg["std_decay_time"] = cfg["n_iter"] / 2
@@ -63,13 +102,15 @@ def run_cem_algorithm(env, agent, usercfg=None, callback=None):
         cfg.update(usercfg)
     print("cem config", {k: cfg[k] for (k, _, _, _) in CEM_OPTIONS})
     if cfg["parallel"]:
-        print("parallel=1: evaluating the population sequentially on the device")
+        print("parallel=1: population-batched evaluation (one device forward per step for all candidates)")
     timestep_limit = cfg["timestep_limit"]
 
     def objective(th):
         agent.set_from_flat(th)
         path = rollout(env, agent, timestep_limit)
         return path["reward"].sum()
+    if cfg["parallel"]:
+        objective.population = lambda ths: evaluate_population(env, agent, ths, timestep_limit)
 
     th_mean = agent.get_flat()
     for info in cem(objective, th_mean, cfg["batch_size"], cfg["n_iter"], cfg["elite_frac"],

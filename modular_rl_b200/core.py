@@ -16,6 +16,8 @@ import time
 from collections import OrderedDict, defaultdict
 from importlib import import_module
 
+import os
+
 import numpy as np
 import scipy.optimize
 
@@ -178,10 +180,84 @@ def run_policy_gradient_algorithm(env, agent, usercfg=None, callback=None):
             callback(stats)
 
 
+# Environments stepped in lockstep per rollout round (one batched device forward + one ZFilter block scan per step).
+# 0 / 1 = the reference's serial rollouts.  Not an agent option - the reference's option tables stay unchanged -
+# but a process setting: MRL_VEC_ENVS in the environment or run_pg.py --vec_envs.
+VEC_ENVS = int(os.environ.get("MRL_VEC_ENVS", "0") or 0)
+
+
 def get_paths(env, agent, cfg, seed_iter):
     if cfg["parallel"]:
         raise NotImplementedError
+    if VEC_ENVS > 1:
+        return do_rollouts_vectorized(env, agent, cfg["timestep_limit"], cfg["timesteps_per_batch"], seed_iter, VEC_ENVS)
     return do_rollouts_serial(env, agent, cfg["timestep_limit"], cfg["timesteps_per_batch"], seed_iter)
+
+
+def _filter_block(filt, X):
+    """N consecutive filt(x) calls on a block (ZFilter: one Welford scan on the device; anything else: per row)."""
+    return filt.filter_batch(X) if hasattr(filt, "filter_batch") else np.stack([filt(x) for x in X])
+
+
+def rollouts_vectorized(envs, agent, timestep_limit):
+    """len(envs) rollouts in lockstep: per step ONE ZFilter block scan and ONE device
+    forward for all live environments (`ZFilter.filter_batch`, `StochPolicy.act_batch`) instead of a batch-1 `act`
+    per environment step (core.py:193).  Returns one path dict per environment with the keys of `rollout`.  With one
+    environment the result is identical to `rollout` (same filter updates, same numpy draws); with several the running
+    filter statistics see the observations in lockstep order instead of episode after episode."""
+    K = len(envs)
+    obs = [env.reset() for env in envs]
+    data = [defaultdict(list) for _ in range(K)]
+    terminated = [False] * K
+    live = list(range(K))
+    stochastic = getattr(agent, "stochastic", True)
+    for _ in range(timestep_limit):
+        if not live:
+            break
+        block = _filter_block(agent.obfilter, np.stack([np.asarray(obs[i], np.float64) for i in live]))
+        actions, info = agent.policy.act_batch(block, stochastic=stochastic)
+        rews = []
+        still = []
+        for j, i in enumerate(live):
+            data[i]["observation"].append(block[j])
+            data[i]["action"].append(actions[j])
+            for (k, v) in info.items():
+                data[i][k].append(v[j])
+            ob, rew, done, envinfo = envs[i].step(actions[j])
+            obs[i] = ob
+            data[i]["reward"].append(rew)
+            rews.append(rew)
+            for (k, v) in envinfo.items():
+                data[i][k].append(v)
+            if done:
+                terminated[i] = True
+            else:
+                still.append(i)
+        _filter_block(agent.rewfilter, np.asarray(rews, np.float64))     # only advances its statistics (SURVEY A.5)
+        live = still
+    paths = []
+    for i in range(K):
+        d = {k: np.array(v) for (k, v) in data[i].items()}
+        d["terminated"] = terminated[i]
+        paths.append(d)
+    return paths
+
+
+def do_rollouts_vectorized(env, agent, timestep_limit, n_timesteps, seed_iter, n_envs):
+    """Rounds of n_envs lockstep rollouts until more than n_timesteps are collected (the strict test of
+    core.py:219); numpy is reseeded once per round from the same counter `do_rollouts_serial` draws from."""
+    import copy
+    envs = [env] + [copy.deepcopy(env) for _ in range(n_envs - 1)]
+    paths = []
+    timesteps_sofar = 0
+    while True:
+        np.random.seed(next(seed_iter))
+        for path in rollouts_vectorized(envs, agent, timestep_limit):
+            paths.append(path)
+            timesteps_sofar += pathlength(path)
+        if timesteps_sofar > n_timesteps:
+            break
+    return paths
 
 
 def rollout(env, agent, timestep_limit):

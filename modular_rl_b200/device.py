@@ -285,6 +285,21 @@ class DeviceNet:
         return sd, fs, dict(shs=sc[0], lm=sc[1], expected_improve_rate=sc[2], cg_rdotr=sc[3])
 
 
+def population_forward(dims: Sequence[int], activation: str, thetas, obs, device: int = 0) -> np.ndarray:
+    """mrl_population_forward: out[m] = MLP_{thetas[m]}(obs[m]) for all members in one launch (linear last layer).
+    thetas [M, P] holds Dense kernels and biases in the reference's flat order (no logstd block)."""
+    th = np.ascontiguousarray(thetas, np.float32)
+    ob = np.ascontiguousarray(obs, np.float32)
+    dims = [int(d) for d in dims]
+    M = th.shape[0]
+    assert ob.shape == (M, dims[0]), (ob.shape, M, dims[0])
+    out = np.empty((M, dims[-1]), np.float32)
+    arr = (C.c_int * len(dims))(*dims)
+    L.check(L.lib().mrl_population_forward(device, len(dims) - 1, arr, L.ACTIVATIONS[activation], L.ptr(th), th.shape[1],
+                                           L.ptr(ob), M, L.ptr(out), L.HOST, None))
+    return out
+
+
 def gae_flat(reward, baseline, offsets, terminated, gamma, lam):
     """mrl_gae on host arrays -> (returns, advantages) float64."""
     r = L.as_c(reward, _F)

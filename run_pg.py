@@ -29,6 +29,9 @@ def main():
     parser.add_argument("--env", default="CartPole-v0")
     parser.add_argument("--agent", default="modular_rl.agentzoo.TrpoAgent")
     parser.add_argument("--plot", action="store_true")
+    parser.add_argument("--vec_envs", type=int, default=0,
+                        help="environments stepped in lockstep with one batched device forward per step "
+                             "(0: serial rollouts as the reference); not an agent option")
     args, _ = parser.parse_known_args([arg for arg in sys.argv[1:] if arg not in ('-h', '--help')])
     env = make(args.env)
     env_spec = env.spec
@@ -44,6 +47,9 @@ def main():
     if args.timestep_limit == 0:
         args.timestep_limit = env_spec.max_episode_steps
     cfg = args.__dict__
+    if args.vec_envs > 1:
+        from modular_rl_b200 import core as _core
+        _core.VEC_ENVS = args.vec_envs
     np.random.seed(args.seed)
     if args.load_snapshot:
         # the reference declares the flag (misc_utils.py:102) without reading it; here it resumes from a

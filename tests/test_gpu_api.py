@@ -358,3 +358,91 @@ def test_ppo_sgd_updater_matches_oracle(kind):
     # Adam normalises the gradient, so float32 noise in near-zero components moves a parameter by O(stepsize)
     th = agent.policy.get_flat()
     assert np.abs(th - oth).max() < 5e-3 and relerr(th, oth) < 2e-3
+
+
+# ----------------------------------------------------------------------------- SURVEY 8f rank 1 / rank 4 (round 2)
+@pytest.mark.parametrize("act", ["tanh", "relu", "sigmoid"])
+def test_population_forward_matches_oracle(act):
+    """mrl_population_forward: every member's own theta on its own observation, one launch, against the oracle's
+    float64 forward member by member."""
+    from modular_rl_b200 import device
+    from oracle import policy_math as pm
+    rng = np.random.default_rng(3)
+    dims = (9, 33, 20, 4)
+    spec = pm.NetSpec(dims, pm.VALUE, act)
+    P = pm.num_params(spec)
+    M = 37
+    ths = (0.4 * rng.standard_normal((M, P))).astype(np.float32)
+    obs = rng.standard_normal((M, dims[0])).astype(np.float32)
+    out = device.population_forward(dims, act, ths, obs)
+    want = np.stack([pm.forward(ths[m], spec, obs[m:m + 1])[1][0] for m in range(M)])
+    assert out.shape == (M, dims[-1])
+    assert np.linalg.norm(out - want) / np.linalg.norm(want) < 1e-5
+    # row stride larger than P (a population matrix with padding) and a single member
+    pad = np.concatenate([ths, np.zeros((M, 5), np.float32)], axis=1)
+    assert np.array_equal(device.population_forward(dims, act, pad, obs), out)
+    assert np.array_equal(device.population_forward(dims, act, ths[:1], obs[:1]), out[:1])
+
+
+@pytest.mark.parametrize("kind", ["box", "discrete"])
+def test_rollouts_vectorized(kind):
+    """Lockstep rollouts through act_batch / filter_batch: with one environment identical to the serial `rollout`
+    (same observations after filtering, actions, probabilities and filter state); with several, every path is a valid
+    rollout and the filters have seen every step once."""
+    import copy
+    from modular_rl_b200 import agentzoo, core, envs
+    env = envs.CartPoleEnv() if kind == "discrete" else envs.PendulumEnv()
+    cfg = dict(hid_sizes=[16, 8], timestep_limit=40)
+    np.random.seed(0)
+    a1 = agentzoo.TrpoAgent(env.observation_space, env.action_space, cfg)
+    a2 = copy.deepcopy(a1)
+    np.random.seed(11)
+    p_serial = core.rollout(copy.deepcopy(env), a1, 40)
+    np.random.seed(11)
+    (p_vec,) = core.rollouts_vectorized([copy.deepcopy(env)], a2, 40)
+    assert p_serial["terminated"] == p_vec["terminated"]
+    for k in ("observation", "action", "reward", "prob"):
+        assert np.allclose(p_serial[k], p_vec[k], rtol=1e-6, atol=1e-7), k
+    assert a1.obfilter.rs.n == a2.obfilter.rs.n and np.allclose(a1.obfilter.rs.mean, a2.obfilter.rs.mean, rtol=1e-12)
+    n0 = a2.obfilter.rs.n
+    paths = core.rollouts_vectorized([copy.deepcopy(env) for _ in range(5)], a2, 40)
+    assert len(paths) == 5
+    steps = sum(core.pathlength(p) for p in paths)
+    assert a2.obfilter.rs.n == n0 + steps
+    for p in paths:
+        T = core.pathlength(p)
+        assert p["observation"].shape[0] == T == len(p["reward"]) == p["prob"].shape[0] and 1 <= T <= 40
+    # the policy-gradient loop takes the lockstep rollouts when core.VEC_ENVS > 1 (run_pg.py --vec_envs): same dict keys downstream
+    from itertools import count
+    got = core.do_rollouts_vectorized(copy.deepcopy(env), a2, 40, 150, count(), 4)
+    assert sum(core.pathlength(p) for p in got) > 150 and len(got) % 4 == 0
+    core.compute_advantage(a2.baseline, got, 0.99, 0.97)
+    assert all("advantage" in p for p in got)
+
+
+def test_cem_population_evaluation_matches_sequential():
+    """parallel=1 in run_cem_algorithm: one population-batched forward per environment step for all candidates; with
+    the filters off the scores equal those of one rollout per candidate (cem.py:88-91)."""
+    import copy
+    from modular_rl_b200 import agentzoo, cem, core, envs
+    env = envs.CartPoleEnv()
+    np.random.seed(0)
+    agent = agentzoo.DeterministicAgent(env.observation_space, env.action_space, dict(hid_sizes=[8], filter=0))
+    th0 = agent.get_flat()
+    rng = np.random.default_rng(4)
+    ths = th0[None, :] + 0.5 * rng.standard_normal((12, th0.size))
+    np.random.seed(21)
+    seq = []
+    for th in ths:
+        agent.set_from_flat(th)
+        seq.append(core.rollout(copy.deepcopy(env), agent, 60)["reward"].sum())
+    np.random.seed(21)
+    pop = cem.evaluate_population(env, agent, ths, 60)
+    # the environments draw their start states from numpy's global generator: sequentially one reset per rollout,
+    # in lockstep all resets first - the same draws in the same order because CartPole's dynamics draw nothing
+    assert np.array_equal(np.asarray(seq), pop)
+    def f(th):
+        raise AssertionError("cem must use f.population when it is given")
+    f.population = lambda t: cem.evaluate_population(env, agent, t, 30)
+    infos = list(cem.cem(f, th0, 8, 2, 0.25))
+    assert len(infos) == 2 and infos[0]["ys"].shape == (8,)
