@@ -169,6 +169,18 @@ int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char handle_out[64])
 int mrl_comm_p2p_connect(mrl_comm* c, const char* handles /* [world][64] */);
 int mrl_comm_p2p_enable(mrl_comm* c, int on);   /* after every rank connected successfully */
 
+/* ---------------------------------------------------------------- PpoSgdUpdater (ppo.py:115-258), minibatches on the device
+ * mrl_batch_gather: dst <- rows idx[0..n) of src (observations + policy side inputs), a device gather from the
+ *   resident batch (the reference slices numpy arrays per minibatch, ppo.py:194-199); idx lives where `loc` says.
+ * mrl_net_ppo_sgd_step: one `train` call (ppo.py:162-167): penalised-surrogate loss + gradient on the minibatch and
+ *   the Adam update of adam_updates (ppo.py:231-258), no host synchronisation; the losses evaluated before the step
+ *   are added to a running sum that mrl_net_ppo_sgd_read returns as a mean (and resets). */
+int mrl_batch_gather(mrl_batch* dst, const mrl_batch* src, const int* idx, int n, int loc, void* stream);
+int mrl_net_ppo_sgd_step(mrl_net* net, mrl_batch* minibatch, double kl_coeff, double kl_cutoff, int reverse_kl,
+                         double stepsize, double beta1, double beta2, double epsilon, void* stream);
+int mrl_net_ppo_sgd_read(mrl_net* net, double losses[3], long long* count, void* stream);
+int mrl_net_adam_reset(mrl_net* net, void* stream);
+
 /* ---------------------------------------------------------------- population forward (cross-entropy method)
  * cem.py:43-44 scores every candidate theta of an iteration by one rollout, one candidate at a time; this entry point
  * evaluates the net of ALL candidates at once: member m has its own flat theta (Dense kernels and biases in the

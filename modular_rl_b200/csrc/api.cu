@@ -275,6 +275,40 @@ extern "C" int mrl_batch_set_policy_inputs(mrl_batch* b, int head, int dout, con
   return 0;
 }
 
+// dst <- rows idx[0..n) of src (observations in both tensor-core layouts + the policy side inputs), on the device
+extern "C" int mrl_batch_gather(mrl_batch* dst, const mrl_batch* src, const int* idx, int n, int loc, void* stream) {
+  if (!dst || !src || !idx || n <= 0) return fail("mrl_batch_gather: bad arguments");
+  if (dst == src) return fail("mrl_batch_gather: dst and src must differ");
+  if (src->N <= 0 || src->pol_head < 0) return fail("mrl_batch_gather: bind observations and policy inputs of the source first");
+  if (dst->device != src->device || dst->ob_dim != src->ob_dim || dst->with_time != src->with_time)
+    return fail("mrl_batch_gather: batches differ in device / shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(dst->device));
+  const int* idx_dev = idx;
+  if (loc == MRL_HOST) {
+    CK(dst->stage2.reserve((size_t)n * 4));
+    CK(cudaMemcpyAsync(dst->stage2.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    idx_dev = dst->stage2.as<int>();
+  }
+  dst->N = n;
+  dst->Nglobal = n;
+  dst->n_tiles = (n + MRL_TILE - 1) / MRL_TILE;
+  dst->version = g_batch_version.fetch_add(1);
+  dst->has_baseline = dst->has_adv32 = dst->has_ret = false;
+  dst->n_paths = 0;
+  dst->pol_head = src->pol_head;
+  dst->pol_dout = src->pol_dout;
+  dst->naux_pol = src->naux_pol;
+  const long long n_mtiles = (dst->n_tiles + 1) / 2;
+  const int xg_ftiles = (dst->xdim + 127) / 128;
+  CK(dst->XA.reserve(l1tc_xa_floats(dst->d0p / 8, n_mtiles) * 4));
+  CK(dst->XG.reserve(l1tc_xg_floats(xg_ftiles, dst->n_tiles) * 4));
+  CK(dst->aux_pol.reserve((size_t)dst->n_tiles * src->naux_pol * MRL_LDT * 4));
+  CKL(launch_gather_rows(idx_dev, n, src->N, src->XA.as<float>(), dst->XA.as<float>(), dst->d0p / 8, src->XG.as<float>(),
+                         dst->XG.as<float>(), xg_ftiles, src->aux_pol.as<float>(), dst->aux_pol.as<float>(), src->naux_pol, st), 1);
+  return 0;
+}
+
 // advantage row of the policy side inputs <- the float32 advantages mrl_batch_gae left on the device
 extern "C" int mrl_batch_refresh_advantages(mrl_batch* b, void* stream) {
   if (!b || !b->has_adv32 || b->pol_head < 0) return fail("mrl_batch_refresh_advantages: needs mrl_batch_gae and bound policy inputs");
@@ -598,6 +632,8 @@ struct mrl_net {
   int device = 0;
   NetGeom g;
   DevBuf trace;
+  DevBuf adam_m, adam_v, sgd_acc;   // PpoSgd: Adam moments (float32) and the running sum of the minibatch losses
+  long long adam_t = 0;
   DevBuf WC, VC, dbg;      // tcgen05 Fisher-vector chain: weight images of theta / of the tangent, debug dump
   bool tc_fvp = false;
   DevBuf DG, WBt, WBv, theta, theta_prev, theta_trial, img, imgv, vflat, Z1, cache, part1, partm, loss_part, out32,
@@ -673,7 +709,7 @@ extern "C" int mrl_net_create(mrl_net** out, int device, int n_layers, const int
 extern "C" int mrl_net_destroy(mrl_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
-  DevBuf* bufs[] = {&n->trace, &n->WC, &n->VC, &n->dbg, &n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
+  DevBuf* bufs[] = {&n->adam_m, &n->adam_v, &n->sgd_acc, &n->trace, &n->WC, &n->VC, &n->dbg, &n->DG, &n->WBt, &n->WBv, &n->theta, &n->theta_prev, &n->theta_trial, &n->img, &n->imgv, &n->vflat,
                     &n->Z1, &n->cache, &n->part1, &n->partm, &n->loss_part, &n->out32, &n->out64, &n->g32,
                     &n->cg_b, &n->cg_x, &n->cg_r, &n->cg_p, &n->p32, &n->x32, &n->fullstep, &n->cgstate, &n->cgscratch, &n->scal,
                     &n->headout, &n->stage};
@@ -1052,6 +1088,69 @@ extern "C" int mrl_net_vf_lossgrad(mrl_net* n, mrl_batch* b, double l2coeff, dou
   const double mse = n->h_scal[0], l2 = n->h_scal[4];
   if (losses) { losses[0] = mse + l2; losses[1] = mse; losses[2] = l2; }
   if (gout) RET(d2h_sync(gout, n->out64.p, (size_t)n->g.P * 8, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------ PpoSgd minibatch step
+// One `train` call of PpoSgdUpdater (ppo.py:162-167,199): penalised-surrogate loss and gradient on the minibatch, then
+// the Adam update of adam_updates (ppo.py:231-258), everything on the device and without a host synchronisation; the
+// losses (evaluated BEFORE the step, as Theano evaluates outputs before applying updates) are added to a running sum.
+extern "C" int mrl_net_ppo_sgd_step(mrl_net* n, mrl_batch* b, double kl_coeff, double kl_cutoff, int reverse_kl,
+                                    double stepsize, double beta1, double beta2, double epsilon, void* stream) {
+  RET(check_pair(n, b, true));
+  if (n->g.head == MRL_VALUE) return fail("mrl_net_ppo_sgd_step: value net");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  const size_t P = n->g.P;
+  if (!n->adam_m.p) {
+    CK(n->adam_m.reserve(P * 4));
+    CK(n->adam_v.reserve(P * 4));
+    CK(n->sgd_acc.reserve(4 * 8));
+    CK(cudaMemsetAsync(n->adam_m.p, 0, P * 4, st));
+    CK(cudaMemsetAsync(n->adam_v.p, 0, P * 4, st));
+    CK(cudaMemsetAsync(n->sgd_acc.p, 0, 4 * 8, st));
+    n->adam_t = 0;
+  }
+  RET(pass_forward(n, b, true, true, nullptr, st, reverse_kl));
+  double* scal = n->scal.as<double>();
+  negate_first<<<1, 1, 0, st>>>(scal);
+  CKL(cudaGetLastError(), 1);
+  CKL(launch_ppo_coef(scal, kl_coeff, kl_cutoff, scal + 8, scal + 10, st), 1);
+  CKL(launch_accum_losses(scal, n->sgd_acc.as<double>(), st), 1);
+  RET(pass_backward(n, b, MRL_MODE_GRAD, scal + 8, reverse_kl, nullptr, 0.0, nullptr, n->out64.as<double>(), st));
+  n->adam_t += 1;
+  const float f1 = (float)beta1, f2 = (float)beta2;
+  // a_t in float32, operation by operation as the numpy float32 expression of the host version
+  const float a_t = (float)stepsize * sqrtf(1.f - powf(f2, (float)n->adam_t)) / (1.f - powf(f1, (float)n->adam_t));
+  CKL(launch_adam_step((int)P, n->out64.as<double>(), n->theta.as<float>(), n->adam_m.as<float>(), n->adam_v.as<float>(), a_t,
+                       f1, f2, (float)epsilon, st), 1);
+  return repack(n, st);
+}
+// mean of the minibatch losses accumulated since the last read (surr, kl, ent) and their count; resets the sum
+extern "C" int mrl_net_ppo_sgd_read(mrl_net* n, double losses[3], long long* count, void* stream) {
+  if (!n || !losses) return fail("mrl_net_ppo_sgd_read: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(n->device));
+  if (!n->sgd_acc.p) return fail("mrl_net_ppo_sgd_read: no minibatch step has run");
+  RET(d2h_sync(n->h_scal, n->sgd_acc.p, 32, st));
+  RET(comm_ok(n));
+  const double c = n->h_scal[3];
+  for (int i = 0; i < 3; ++i) losses[i] = c > 0 ? n->h_scal[i] / c : 0.0;
+  if (count) *count = (long long)c;
+  CK(cudaMemsetAsync(n->sgd_acc.p, 0, 32, st));
+  return 0;
+}
+// restart Adam (moments and step counter to zero)
+extern "C" int mrl_net_adam_reset(mrl_net* n, void* stream) {
+  if (!n) return fail("mrl_net_adam_reset: null net");
+  CK(cudaSetDevice(n->device));
+  n->adam_t = 0;
+  if (n->adam_m.p) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(n->adam_m.p, 0, (size_t)n->g.P * 4, st));
+    CK(cudaMemsetAsync(n->adam_v.p, 0, (size_t)n->g.P * 4, st));
+    CK(cudaMemsetAsync(n->sgd_acc.p, 0, 32, st));
+  }
   return 0;
 }
 

@@ -191,6 +191,90 @@ __global__ void time_feature_kernel(const long long* __restrict__ offsets, int n
   }
 }
 
+// ------------------------------------------------------------------------------------ minibatch gather
+// dst row i <- src row idx[i] for the three resident layouts of a batch (XA, XG, policy side inputs), on the device:
+// a PpoSgd minibatch (ppo.py:194-199) is 128 rows of the batch that is already resident - no host round trip.
+// Rows i >= n of the last destination tiles are written as zeros.
+__global__ void gather_rows_kernel(const int* __restrict__ idx, int n, long long n_src,
+                                   const float* __restrict__ sXA, float* __restrict__ dXA, int xa_kg, int rows_a,
+                                   const float* __restrict__ sXG, float* __restrict__ dXG, int xg_ft, int rows_g,
+                                   const float* __restrict__ sAux, float* __restrict__ dAux, int naux) {
+  const int quads = xa_kg * 2, fpad = xg_ft * 128;
+  const long long nA = (long long)rows_a * quads, nG = (long long)rows_g * fpad, nX = (long long)rows_g * naux;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nA) {                       // XA [mtile][kg][khalf][mgroup 16][8][4]: one float4 = 4 features of one timestep
+    const int t = (int)(i / quads), q = (int)(i % quads);
+    const int kg = q >> 1, kh = q & 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < n) {
+      const long long ts = idx[t];
+      if (ts >= 0 && ts < n_src)
+        v = *reinterpret_cast<const float4*>(sXA + ((size_t)(ts / 128) * xa_kg + kg) * 1024 + kh * 512 + ((ts % 128) >> 3) * 32 + (ts & 7) * 4);
+    }
+    *reinterpret_cast<float4*>(dXA + ((size_t)(t / 128) * xa_kg + kg) * 1024 + kh * 512 + ((t % 128) >> 3) * 32 + (t & 7) * 4) = v;
+    return;
+  }
+  long long j = i - nA;
+  if (j < nG) {                       // XG [t/8][ftile][khalf][fgroup 16][8 features][4 timesteps]
+    const int t = (int)(j / fpad), f = (int)(j % fpad);
+    float v = 0.f;
+    if (t < n) {
+      const long long ts = idx[t];
+      if (ts >= 0 && ts < n_src)
+        v = sXG[((size_t)(ts >> 3) * xg_ft + f / 128) * 1024 + ((ts >> 2) & 1) * 512 + ((f % 128) >> 3) * 32 + (f & 7) * 4 + (ts & 3)];
+    }
+    dXG[((size_t)(t >> 3) * xg_ft + f / 128) * 1024 + ((t >> 2) & 1) * 512 + ((f % 128) >> 3) * 32 + (f & 7) * 4 + (t & 3)] = v;
+    return;
+  }
+  j -= nG;
+  if (j < nX && naux > 0) {           // side inputs, tile-major [tile][row][LDT]
+    const int t = (int)(j / naux), r = (int)(j % naux);
+    float v = 0.f;
+    if (t < n) {
+      const long long ts = idx[t];
+      if (ts >= 0 && ts < n_src) v = sAux[((size_t)(ts / MRL_TILE) * naux + r) * MRL_LDT + ts % MRL_TILE];
+    }
+    dAux[((size_t)(t / MRL_TILE) * naux + r) * MRL_LDT + t % MRL_TILE] = v;
+  }
+}
+cudaError_t launch_gather_rows(const int* idx, int n, long long n_src, const float* sXA, float* dXA, int xa_kg,
+                               const float* sXG, float* dXG, int xg_ft, const float* sAux, float* dAux, int naux,
+                               cudaStream_t st) {
+  const int n_tiles = (n + MRL_TILE - 1) / MRL_TILE;
+  const int rows_a = ((n_tiles + 1) / 2) * 128, rows_g = n_tiles * MRL_TILE;
+  const long long total = (long long)rows_a * xa_kg * 2 + (long long)rows_g * xg_ft * 128 + (long long)rows_g * naux;
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(idx, n, n_src, sXA, dXA, xa_kg, rows_a, sXG, dXG, xg_ft,
+                                                                     rows_g, sAux, dAux, naux);
+  return cudaGetLastError();
+}
+
+// adam_updates (ppo.py:231-258) on the device, float32 like the host version it replaces: m, v, theta in place;
+// a_t = lr sqrt(1 - b2^t) / (1 - b1^t) comes from the host (one float), epsilon is not bias-corrected.
+__global__ void adam_step_kernel(int P, const double* __restrict__ g64, float* __restrict__ theta, float* __restrict__ m,
+                                 float* __restrict__ v, float a_t, float b1, float b2, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float g = (float)g64[i];
+  const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.f - b1, g));
+  const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(__fmul_rn(1.f - b2, g), g));
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] = __fsub_rn(theta[i], __fdiv_rn(__fmul_rn(a_t, mi), __fadd_rn(__fsqrt_rn(vi), eps)));
+}
+cudaError_t launch_adam_step(int P, const double* g64, float* theta, float* m, float* v, float a_t, float b1, float b2,
+                             float eps, cudaStream_t st) {
+  adam_step_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, g64, theta, m, v, a_t, b1, b2, eps);
+  return cudaGetLastError();
+}
+__global__ void accum_losses_kernel(const double* __restrict__ scal, double* __restrict__ acc) {
+  if (threadIdx.x < 3) acc[threadIdx.x] += scal[threadIdx.x];
+  if (threadIdx.x == 3) acc[3] += 1.0;
+}
+cudaError_t launch_accum_losses(const double* scal, double* acc, cudaStream_t st) {
+  accum_losses_kernel<<<1, 32, 0, st>>>(scal, acc);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------ launchers
 cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img, float* WB, cudaStream_t st) {
   const int nu = l1tc_nu(g);

@@ -13,6 +13,13 @@ cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncol
 cudaError_t launch_time_feature(const long long* offsets, int n_paths, long long N, double limit, int col, int* tindex,
                                 float* XA, int xa_kgroups, float* XG, int xg_ftiles, cudaStream_t st);
 
+cudaError_t launch_gather_rows(const int* idx, int n, long long n_src, const float* sXA, float* dXA, int xa_kg,
+                               const float* sXG, float* dXG, int xg_ft, const float* sAux, float* dAux, int naux,
+                               cudaStream_t st);
+cudaError_t launch_adam_step(int P, const double* g64, float* theta, float* m, float* v, float a_t, float b1, float b2,
+                             float eps, cudaStream_t st);
+cudaError_t launch_accum_losses(const double* scal, double* acc, cudaStream_t st);
+
 // ---- mlp_l1_tc.cu  (tcgen05 / TMEM layer-1 GEMMs, 3xTF32)
 int l1tc_nu(const NetGeom& g);
 size_t l1tc_wb_floats(const NetGeom& g);

@@ -175,6 +175,20 @@ class DeviceBatch:
                                       comm._h if comm else None, pret, padv, lr, stream))
         return ret, adv
 
+    def gather_from(self, src: "DeviceBatch", idx, stream=None):
+        """This batch <- rows idx of `src` (observations + policy side inputs), gathered on the device."""
+        if _is_torch_cuda(idx):
+            import torch
+            assert idx.dtype == torch.int32
+            idx = idx.contiguous()
+            n, p, loc, keep = int(idx.numel()), C.c_void_p(idx.data_ptr()), L.DEVICE, idx
+        else:
+            keep = np.ascontiguousarray(idx, np.int32)
+            n, p, loc = int(keep.size), L.ptr(keep), L.HOST
+        L.check(L.lib().mrl_batch_gather(self._h, src._h, p, n, loc, stream))
+        self.N = n
+        return self
+
     def refresh_advantages(self, stream=None):
         L.check(L.lib().mrl_batch_refresh_advantages(self._h, stream))
         return self
@@ -262,6 +276,23 @@ class DeviceNet:
         L.check(L.lib().mrl_net_ppo_lossgrad(self._h, batch._h, float(kl_coeff), float(kl_cutoff),
                                              int(bool(reverse_kl)), C.byref(pen), L.ptr(g), L.ptr(ls), stream))
         return pen.value, g, ls
+
+    def ppo_sgd_step(self, minibatch: DeviceBatch, kl_coeff, kl_cutoff, stepsize, reverse_kl=False, beta1=0.9,
+                     beta2=0.999, epsilon=1e-8, stream=None):
+        """One PpoSgd `train` call on the device: loss + gradient on the minibatch, Adam step, no host sync."""
+        self.theta_version += 1
+        L.check(L.lib().mrl_net_ppo_sgd_step(self._h, minibatch._h, float(kl_coeff), float(kl_cutoff), int(bool(reverse_kl)),
+                                             float(stepsize), float(beta1), float(beta2), float(epsilon), stream))
+
+    def ppo_sgd_read(self, stream=None):
+        """-> (mean [surr, kl, ent] of the minibatch losses since the last read, number of minibatches)"""
+        ls = np.zeros(3, np.float64)
+        cnt = C.c_longlong()
+        L.check(L.lib().mrl_net_ppo_sgd_read(self._h, L.ptr(ls), C.byref(cnt), stream))
+        return ls, int(cnt.value)
+
+    def adam_reset(self, stream=None):
+        L.check(L.lib().mrl_net_adam_reset(self._h, stream))
 
     def vf_lossgrad(self, batch: DeviceBatch, l2coeff=1e-3, want_grad=True, stream=None):
         ls = np.zeros(3, np.float64)

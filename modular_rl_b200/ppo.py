@@ -134,26 +134,14 @@ class PpoSgdUpdater(EzFlat, EzPickle):
         self.loss_names = ["surr", "kl", "ent"]
         self._full = DeviceBatch(stochpol.dims[0], with_time_feature=True)
         self._mb = DeviceBatch(stochpol.dims[0], with_time_feature=True)
-        P = stochpol.net.P
-        self._t = 0                                   # adam_updates' shared step counter
-        self._m = np.zeros(P, np.float32)
-        self._v = np.zeros(P, np.float32)
-
-    def _bind(self, batch, ob, act, adv, prob):
-        batch.set_obs(np.asarray(ob).reshape(len(ob), -1))
-        batch.set_policy_inputs(self.stochpol.probtype.head, self.stochpol.dims[-1], act, adv, prob)
-        return batch
-
-    def _adam(self, theta, g, beta1=0.9, beta2=0.999, epsilon=1e-8):
-        f = np.float32
-        self._t += 1
-        a_t = f(self.cfg["stepsize"]) * np.sqrt(f(1) - f(beta2) ** self._t) / (f(1) - f(beta1) ** self._t)
-        g = g.astype(f)
-        self._m = f(beta1) * self._m + f(1 - beta1) * g
-        self._v = f(beta2) * self._v + f(1 - beta2) * g * g
-        return (theta - a_t * self._m / (np.sqrt(self._v) + f(epsilon))).astype(f)
+        self._sl = DeviceBatch(stochpol.dims[0], with_time_feature=True)
+        stochpol.net.adam_reset()                     # adam_updates' moments and shared step counter live on the device
 
     def __call__(self, paths):
+        """ppo.py:170-228.  The whole batch is bound ONCE; every minibatch of 128 is an index gather from the resident
+        batch (mrl_batch_gather), its loss / gradient / Adam step one call without a host synchronisation
+        (mrl_net_ppo_sgd_step); the host only draws the permutations (numpy's global generator, as the reference) and
+        reads the mean losses once per epoch."""
         cfg = self.cfg
         net = self.stochpol.net
         ob_no = concat([path["observation"] for path in paths])
@@ -163,37 +151,35 @@ class PpoSgdUpdater(EzFlat, EzPickle):
         N = ob_no.shape[0]
         bs = self.batchsize
         kl_cutoff = cfg["kl_target"] * 2.0
+        head, dout = self.stochpol.probtype.head, self.stochpol.dims[-1]
 
         # update_old_net (ppo.py:174): the old policy is the current one; one forward pass gives its rows
         self._full.set_obs(ob_no)
         oldprob_np = self.stochpol.output_from_head(net.forward(self._full))
+        self._full.set_policy_inputs(head, dout, action_na, advantage_n, oldprob_np)
 
-        def losses_of(sl):
-            b = self._bind(self._full, ob_no[sl], action_na[sl], advantage_n[sl], oldprob_np[sl])
+        def losses_of(lo, hi):
+            b = self._full if (lo == 0 and hi == N) else self._sl.gather_from(self._full, np.arange(lo, hi, dtype=np.int32))
             return net.ppo_lossgrad(b, 0.0, 1e300, False, want_grad=False)[2]
 
         if cfg["do_split"]:
             train_stop = (int(.75 * N) // bs) * bs
-            test_losses_before = losses_of(slice(train_stop, None))
+            test_losses_before = losses_of(train_stop, N)
         else:
             train_stop = N
-        train_losses_before = losses_of(slice(0, train_stop))
+        train_losses_before = losses_of(0, train_stop)
 
-        theta = self.get_params_flat().astype(np.float32)
         train_losses = train_losses_before
+        net.ppo_sgd_read() if getattr(self, "_ran", False) else None      # drop a stale running sum
+        self._ran = True
         for _ in range(cfg["epochs"]):
-            sortinds = np.random.permutation(train_stop)
-            losses = []
+            sortinds = np.random.permutation(train_stop).astype(np.int32)
             for istart in range(0, train_stop, bs):
-                idx = sortinds[istart:istart + bs]
-                mb = self._bind(self._mb, ob_no[idx], action_na[idx], advantage_n[idx], oldprob_np[idx])
-                _, g, ls = net.ppo_lossgrad(mb, self.kl_coeff, kl_cutoff, False)
-                losses.append(ls)
-                theta = self._adam(theta, g)
-                self.set_params_flat(theta)
-            train_losses = np.mean(losses, axis=0)
+                mb = self._mb.gather_from(self._full, sortinds[istart:istart + bs])
+                net.ppo_sgd_step(mb, self.kl_coeff, kl_cutoff, cfg["stepsize"])
+            train_losses, _ = net.ppo_sgd_read()
             if cfg["do_split"]:
-                test_losses = losses_of(slice(train_stop, None))
+                test_losses = losses_of(train_stop, N)
 
         klafter = train_losses[self.loss_names.index("kl")]
         if klafter > 1.3 * cfg["kl_target"]:

@@ -446,3 +446,37 @@ def test_cem_population_evaluation_matches_sequential():
     f.population = lambda t: cem.evaluate_population(env, agent, t, 30)
     infos = list(cem.cem(f, th0, 8, 2, 0.25))
     assert len(infos) == 2 and infos[0]["ys"].shape == (8,)
+
+
+@pytest.mark.parametrize("head", [0, 1])
+def test_batch_gather_matches_oracle_on_the_subset(head):
+    """mrl_batch_gather: a minibatch gathered on the device from the resident batch gives the oracle's loss and
+    gradient on ob[idx] (ppo.py:194-199 slices numpy arrays); 1e-5 as everywhere."""
+    from modular_rl_b200 import device, synth
+    from oracle import policy_math as pm
+    dims = (13, 32, 16, 3) if head == 0 else (13, 32, 16, 5)
+    wl = synth.Workload("g", dims, head, 1000, 100, 5)
+    spec = pm.NetSpec(dims, pm.GAUSS if head == 0 else pm.CAT)
+
+    def fwd(th, ob):
+        _, z = pm.forward(th, spec, ob)
+        return z if head == 0 else pm.softmax(z)
+    d = synth.policy_batch(wl, fwd)
+    theta = synth.perturb(d["theta"], 0.03, 2)
+    net = device.DeviceNet(dims, head)
+    full = device.DeviceBatch(dims[0], True)
+    full.set_obs(d["ob"]).set_policy_inputs(head, dims[-1], d["act"], d["adv"], d["oldprob"])
+    net.set_params(theta)
+    rng = np.random.default_rng(1)
+    for n in (128, 77, 1, 300):
+        idx = rng.permutation(1000)[:n].astype(np.int32)
+        mb = device.DeviceBatch(dims[0], True).gather_from(full, idx)
+        pen, g, ls = net.ppo_lossgrad(mb, 0.5, 1e-4, False)
+        open_, og = pm.ppo_lossgrad(theta, spec, d["ob"][idx], d["act"][idx], d["adv"][idx], d["oldprob"][idx], 0.5, 1e-4)
+        assert np.linalg.norm(g - og) / np.linalg.norm(og) < 2e-5, n
+        ols, _, _ = pm.surr_kl_grads(theta, spec, d["ob"][idx], d["act"][idx], d["adv"][idx], d["oldprob"][idx], ratio="lik")
+        assert np.allclose(ls, ols, rtol=1e-5, atol=2e-7), (n, ls, ols)
+    # the source batch is untouched
+    _, g_full, _ = net.ppo_lossgrad(full, 0.5, 1e-4, False)
+    _, og_full = pm.ppo_lossgrad(theta, spec, d["ob"], d["act"], d["adv"], d["oldprob"], 0.5, 1e-4)
+    assert np.linalg.norm(g_full - og_full) / np.linalg.norm(og_full) < 2e-5
