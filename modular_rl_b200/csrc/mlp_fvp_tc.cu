@@ -581,14 +581,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             const uint32_t freeq = mbar_try(&ra_empty[e], (ue & 1) ^ 1);
             if (kg + 2 < kgs) request(kg + 2, hn, zn);
             float val[8];
+            const float4 vb0 = *reinterpret_cast<const float4*>(vbl + 8 * kg), vb1 = *reinterpret_cast<const float4*>(vbl + 8 * kg + 4);
+            const float vbk[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
             if (r == 0) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (zc[i] + vbl[8 * kg + i]);
+              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (zc[i] + vbk[i]);
             } else {
               uint32_t v[8];
               tmem_ld8(src_acc + 8 * kg, v);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (__uint_as_float(v[i]) + vbl[8 * kg + i]);
+              for (int i = 0; i < 8; ++i) val[i] = dact_from_h<ACT>(hc[i]) * (__uint_as_float(v[i]) + vbk[i]);
             }
             if (a.dbg && mt == 0) {
 #pragma unroll

@@ -36,7 +36,10 @@ __device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();   // a protocol bug becomes an error, never a hung GPU
   }
 }
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_ns<40>(bar, parity); }
+#ifndef MRL_WAIT_NS
+#define MRL_WAIT_NS 40
+#endif
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait_ns<MRL_WAIT_NS>(bar, parity); }
 // warp-converged election of one lane (the pattern the tcgen05 issue path is compiled best for: inside an
 // `if (lane == 0)` region ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes)
 __device__ __forceinline__ bool elect_one() {
