@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
         if (slab >= a.n_slabs) return;
         const int t0 = 2 * mt, nt = min(2, a.n_tiles - t0);
         if (nt <= 0) return;
+#ifndef FT_AHEAD2
+#define FT_AHEAD2 0
+#endif
 #ifndef FT_PF
 #define FT_PF 0       // measured at 1 M Humanoid timesteps: no L2 prefetch 1.04 ms, one bulk prefetch per tile 1.07, 16 KB pieces 1.22
 #endif
@@ -555,7 +558,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           const int ul = r + 1, kgs = P.rs[r].kgs;
           const float* hrow = cb + (size_t)g.off_act[ul] * MRL_LDT;
           const float* vbl = vb_s + P.vboff[ul];
+#if FT_AHEAD2
+          float hc[8], zc[8], hn[8], zn[8], hf[8], zf[8];     // current, next and next-but-one k-group of this group
+#else
           float hc[8], zc[8], hn[8], zn[8];
+#endif
           auto request = [&](int kg, float (&hb)[8], float (&zz)[8]) {
             const float* ph = hrow + (size_t)(8 * kg) * MRL_LDT;
 #pragma unroll
@@ -569,6 +576,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           int kg = (e - (int)(u & 1)) & 1;            // this group's first k-group of the stage
           u += kgs;
           if (kg < kgs) request(kg, hc, zc);
+#if FT_AHEAD2
+          if (kg + 2 < kgs) request(kg + 2, hn, zn);
+#endif
           uint32_t src_acc = 0;
           if (tr_on) FT_TR(3, (1 << 24) | (r << 8));
           if (r > 0) {
@@ -579,7 +589,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
           if (tr_on) FT_TR(3, (2 << 24) | (r << 8));
           for (; kg < kgs; kg += 2, ++ue) {
             const uint32_t freeq = mbar_try(&ra_empty[e], (ue & 1) ^ 1);
+#if FT_AHEAD2
+            if (kg + 4 < kgs) request(kg + 4, hf, zf);
+#else
             if (kg + 2 < kgs) request(kg + 2, hn, zn);
+#endif
             float val[8];
             const float4 vb0 = *reinterpret_cast<const float4*>(vbl + 8 * kg), vb1 = *reinterpret_cast<const float4*>(vbl + 8 * kg + 4);
             const float vbk[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
@@ -614,8 +628,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
             __syncwarp();
             if (lane == 0) mbar_arrive(&ra_full[e]);
             if (tr_on) FT_TR(3, (5 << 24) | (r << 8) | kg);
+#if FT_AHEAD2
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; zc[i] = zn[i]; hn[i] = hf[i]; zn[i] = zf[i]; }
+#else
 #pragma unroll
             for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; zc[i] = zn[i]; }
+#endif
           }
         }
         ++tcount;
