@@ -53,29 +53,52 @@ def evaluate_population(env, agent, ths, timestep_limit):
     return total
 
 
+class _GaussianSearch(object):
+    """Diagonal-Gaussian search distribution of the noisy cross-entropy method (cem.py:10-50).  `var` is the elite
+    VARIANCE (the reference's `th_std`, which starts as ones * initial_std); a generation is drawn with deviation
+    sqrt(var + extra_std^2 * max(1 - generation / std_decay_time, 0)).  One `np.random.randn(batch, dim)` call per
+    generation keeps the reference's random stream (pinned bit-exactly by tests/golden/cem_vectors.npz)."""
+
+    def __init__(self, mean, initial_std, extra_std, std_decay_time):
+        self.mean = np.asarray(mean, np.float64)
+        self.var = np.full(self.mean.size, 1.0) * initial_std
+        self.extra_var = np.square(extra_std)
+        self.decay = float(std_decay_time)
+        self.generation = 0
+
+    def noise_left(self):
+        return max(1.0 - self.generation / self.decay, 0)
+
+    def draw(self, count):
+        self.dev = np.sqrt(self.var + self.extra_var * self.noise_left())
+        return self.mean[None, :] + self.dev[None, :] * np.random.randn(count, self.mean.size)
+
+    def refit(self, candidates, scores, keep):
+        best = candidates[scores.argsort()[-keep:]]
+        self.mean, self.var = best.mean(axis=0), best.var(axis=0)
+        self.generation += 1
+
+
+def _score(f, ths, pool):
+    population = getattr(f, "population", None)
+    if population is not None:
+        return np.asarray(population(ths))                      # all candidates in one lockstep evaluation
+    return np.array([f(th) for th in ths] if pool is None else pool.map(f, ths))
+
+
 def cem(f, th_mean, batch_size, n_iter, elite_frac, initial_std=1.0, extra_std=0.0, std_decay_time=1.0, pool=None):
-    """Generator of one info dict per iteration (cem.py:10-50): theta ~ Normal(th_mean, sample_std), keep the
-    round(batch_size*elite_frac) best, refit.  As in the reference the running `th_std` holds the elite
-    VARIANCE (and starts as ones*initial_std), and the sampling deviation is
-    sqrt(th_std + extra_std^2 * max(1 - iteration/std_decay_time, 0))."""
-    n_elite = int(np.round(batch_size * elite_frac))
-    th_mean = np.asarray(th_mean, np.float64)
-    th_std = np.ones(th_mean.size) * initial_std
-    for iteration in range(n_iter):
-        extra_var_multiplier = max(1.0 - iteration / float(std_decay_time), 0)
-        print("extra var", extra_var_multiplier)
-        sample_std = np.sqrt(th_std + np.square(extra_std) * extra_var_multiplier)
-        ths = th_mean[None, :] + sample_std[None, :] * np.random.randn(batch_size, th_mean.size)
-        if getattr(f, "population", None) is not None:
-            ys = np.asarray(f.population(ths))                  # all candidates in one lockstep evaluation
-        else:
-            ys = np.array(list(map(f, ths)) if pool is None else pool.map(f, ths))
+    """Generator of one info dict per iteration - the reference's `cem` signature and info keys (cem.py:10-50):
+    keep the round(batch_size * elite_frac) best of each generation and refit the search distribution to them.  An
+    objective that has a `population` attribute is scored with one call for the whole generation."""
+    search = _GaussianSearch(th_mean, initial_std, extra_std, std_decay_time)
+    keep = int(np.round(batch_size * elite_frac))
+    for _ in range(n_iter):
+        print("extra var", search.noise_left())
+        ths = search.draw(batch_size)
+        ys = _score(f, ths, pool)
         assert ys.ndim == 1
-        elite_inds = ys.argsort()[-n_elite:]
-        elite_ths = ths[elite_inds]
-        th_mean = elite_ths.mean(axis=0)
-        th_std = elite_ths.var(axis=0)
-        yield {"ys": ys, "th": th_mean, "ymean": ys.mean(), "std": sample_std}
+        search.refit(ths, ys, keep)
+        yield {"ys": ys, "th": search.mean, "ymean": ys.mean(), "std": search.dev}
 
 
 CEM_OPTIONS = [

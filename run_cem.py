@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""This script runs the cross-entropy method - same flags as the reference's run_cem.py (GENERAL_OPTIONS +
---env --agent --plot + the agent's options + CEM_OPTIONS, run_cem.py:13-30), with every population member
-evaluated through the device-resident deterministic policy.
+"""Cross-entropy-method driver with the reference's run_cem.py command line (GENERAL_OPTIONS, --env, --agent, --plot,
+the agent's own options, CEM_OPTIONS - run_cem.py:13-30).  Candidates are scored through the device-resident
+deterministic policy; with --parallel 1 the whole population is scored in lockstep by one population-batched forward
+per environment step.
 
   python run_cem.py --env CartPole-v0 --agent modular_rl.agentzoo.DeterministicAgent --n_iter 10 --batch_size 40
 """
@@ -13,65 +14,78 @@ import sys
 
 import numpy as np
 
-from modular_rl import *  # noqa: F401,F403
+import modular_rl as mrl
 from modular_rl_b200.envs import make
 
-try:
-    from tabulate import tabulate
-except ImportError:  # pragma: no cover
-    def tabulate(rows):
-        return "\n".join("%-24s %s" % (k, v) for k, v in rows)
+
+def _table(pairs):
+    try:
+        from tabulate import tabulate
+        return tabulate(pairs)
+    except ImportError:  # pragma: no cover
+        return "\n".join("%-24s %s" % kv for kv in pairs)
 
 
-def main():
-    parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    update_argument_parser(parser, GENERAL_OPTIONS)
-    parser.add_argument("--env", required=True)
-    parser.add_argument("--agent", required=True)
-    parser.add_argument("--plot", action="store_true")
-    args, _ = parser.parse_known_args([arg for arg in sys.argv[1:] if arg not in ('-h', '--help')])
-    env = make(args.env)
-    env_spec = env.spec
-    # read the snapshot before the results directory of a previous run (which may hold it) is cleared
-    snapshot_agent = load_agent_snapshot(args.load_snapshot) if args.load_snapshot else None
-    mondir = args.outfile + ".dir"
-    if os.path.exists(mondir):
-        shutil.rmtree(mondir)
-    os.makedirs(mondir)
-    agent_ctor = get_agent_cls(args.agent)
-    update_argument_parser(parser, agent_ctor.options)
-    update_argument_parser(parser, CEM_OPTIONS)
-    args = parser.parse_args()
-    if args.timestep_limit == 0:
-        args.timestep_limit = env_spec.max_episode_steps
-    cfg = args.__dict__
-    np.random.seed(args.seed)
-    agent = snapshot_agent if args.load_snapshot else agent_ctor(env.observation_space, env.action_space, cfg)
-    if args.use_hdf:
-        hdf, diagnostics = prepare_h5_file(args)
+def parse_cli(argv):
+    """Two-stage parse as in the reference: the agent class named by --agent contributes its own options."""
+    ap = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    mrl.update_argument_parser(ap, mrl.GENERAL_OPTIONS)
+    ap.add_argument("--env", required=True)
+    ap.add_argument("--agent", required=True)
+    ap.add_argument("--plot", action="store_true")
+    first, _ = ap.parse_known_args([a for a in argv if a not in ("-h", "--help")])
+    agent_cls = mrl.get_agent_cls(first.agent)
+    mrl.update_argument_parser(ap, agent_cls.options)
+    mrl.update_argument_parser(ap, mrl.CEM_OPTIONS)
+    return ap.parse_args(argv), agent_cls
 
-    counter = [0]
 
-    def callback(stats):
-        if args.use_hdf:
-            for (stat, val) in stats.items():
-                diagnostics[stat].append(val)
-        if args.plot:
-            animate_rollout(env, agent, min(500, args.timestep_limit))
-        print("*********** Iteration %i ****************" % counter[0])
-        print(tabulate([(k, v) for k, v in stats.items() if np.asarray(v).size == 1]))
-        counter[0] += 1
-        if args.snapshot_every and ((counter[0] % args.snapshot_every == 0) or (counter[0] == args.n_iter)):
-            agent.set_from_flat(stats["th"])
-            if args.use_hdf:
-                hdf['/agent_snapshots/%0.4i' % counter[0]] = np.array(pickle.dumps(agent, -1))
+class IterationLog(object):
+    """Per-iteration callback of run_cem_algorithm: diagnostics to hdf5, a table of the scalar stats, snapshots."""
+
+    def __init__(self, args, env, agent, results_dir, hdf=None, diagnostics=None):
+        self.args, self.env, self.agent, self.results_dir = args, env, agent, results_dir
+        self.hdf, self.diagnostics = hdf, diagnostics
+        self.done = 0
+
+    def snapshot_due(self):
+        every = self.args.snapshot_every
+        return bool(every) and (self.done % every == 0 or self.done == self.args.n_iter)
+
+    def __call__(self, stats):
+        if self.diagnostics is not None:
+            for key, val in stats.items():
+                self.diagnostics[key].append(val)
+        if self.args.plot:
+            mrl.animate_rollout(self.env, self.agent, min(500, self.args.timestep_limit))
+        print("*********** Iteration %i ****************" % self.done)
+        print(_table([(k, v) for k, v in stats.items() if np.asarray(v).size == 1]))
+        self.done += 1
+        if self.snapshot_due():
+            self.agent.set_from_flat(stats["th"])
+            if self.hdf is not None:
+                self.hdf["/agent_snapshots/%0.4i" % self.done] = np.array(pickle.dumps(self.agent, -1))
             else:
-                save_agent_snapshot(agent, mondir, counter[0], env_id=env_spec.id)
+                mrl.save_agent_snapshot(self.agent, self.results_dir, self.done, env_id=self.env.spec.id)
 
-    run_cem_algorithm(env, agent, callback=callback, usercfg=cfg)
 
-    if args.use_hdf:
-        hdf['env_id'] = env_spec.id
+def main(argv=None):
+    args, agent_cls = parse_cli(sys.argv[1:] if argv is None else argv)
+    env = make(args.env)
+    # a snapshot may live in the results directory of the previous run: read it before that directory is cleared
+    restored = mrl.load_agent_snapshot(args.load_snapshot) if args.load_snapshot else None
+    results_dir = args.outfile + ".dir"
+    shutil.rmtree(results_dir, ignore_errors=True)
+    os.makedirs(results_dir)
+    if args.timestep_limit == 0:
+        args.timestep_limit = env.spec.max_episode_steps
+    np.random.seed(args.seed)
+    cfg = vars(args)
+    agent = restored if restored is not None else agent_cls(env.observation_space, env.action_space, cfg)
+    hdf, diagnostics = mrl.prepare_h5_file(args) if args.use_hdf else (None, None)
+    mrl.run_cem_algorithm(env, agent, callback=IterationLog(args, env, agent, results_dir, hdf, diagnostics), usercfg=cfg)
+    if hdf is not None:
+        hdf["env_id"] = env.spec.id
     env.close()
 
 
