@@ -59,7 +59,7 @@ def parse():
                          "quick = losses, gradient, one Fvp, advantages; full = + the oracle's whole update (step direction, stats)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--nccl-only", action="store_true", help="sum over ranks with NCCL instead of the NVLink peer-memory push")
+    ap.add_argument("--nccl-only", action="store_true", help="sum over ranks with NCCL instead of the NVLink peer-memory exchange")
     return ap.parse_args()
 
 
@@ -587,6 +587,12 @@ def main():
     from modular_rl_b200.device import Comm, DeviceBatch, DeviceNet
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = 0
+    if world > 1 and os.environ.get("MRL_NUMA_BIND", "1") != "0":
+        from modular_rl_b200.parallel import bind_to_device_numa
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local_rank]) if visible and visible.replace(",", "").isdigit() else local_rank
+        numa_cores = bind_to_device_numa(phys)     # before any pinned allocation: first touch on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
@@ -803,8 +809,9 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_desc(wl, n_total), "timesteps": n_total,
                            "timesteps_per_gpu": n_local, "parallelism": f"dp{world}",
-                           "allreduce": ("none" if world == 1 else ("nvlink peer-memory push (fused into the slab reduce)"
-                                                                    if comm.p2p else "nccl")),
+                           "allreduce": ("none" if world == 1 else ("nvlink peer-memory exchange (publish fused into the slab reduce, "
+                                                                    "peer reads fused into the CG step)" if comm.p2p else "nccl")),
+                           "host_numa_cores_bound": numa_cores,
                            "l2": "inputs larger than L2 (observations %.2f GB per GPU)" % (n_local * wl.dims[0] * 4 / 1e9),
                            **CFG},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -775,7 +775,8 @@ static Plan plan_for(const mrl_batch* b, bool pairs = false) {
   const int sms = mrl_sm_count();   // callers have made b->device current
   Plan p;
   if (pairs) {
-    // tcgen05 Fisher-vector chain: 128-timestep MMA tiles = pairs of cache tiles, slabs of 1..8 of them
+    // kernels that walk two tiles per pass: the forward chain, and the tcgen05 Fisher-vector chain whose
+    // 128-timestep MMA tiles are pairs of cache tiles (slabs of 1..8 of them)
     if (b->n_tiles <= sms * 2) {
       p.slab_tiles = 2;
     } else {
@@ -853,7 +854,7 @@ static int reserve_ws(mrl_net* n, const mrl_batch* b, const Plan& pl) {
 static int pass_forward(mrl_net* n, mrl_batch* b, bool want_losses, bool want_cache, float* head_out,
                         cudaStream_t st, int reverse_kl = 0) {
   const NetGeom& g = n->g;
-  const Plan pl = plan_for(b);
+  const Plan pl = plan_for(b, true);
   RET(reserve_ws(n, b, pl));
   // the batch tile has b->d0p feature rows; the net consumes the first g.d0p of them
   NetGeom gl = g;

@@ -4,7 +4,6 @@
 // shared-memory image the fused chain loads ([biases | logstd | W2..WL | W2^T..WL^T]) and into the
 // split-precision tensor-core operand of layer 1 (see mlp_l1_tc.cu).  Side inputs of the batch
 // (advantages, actions, old probabilities, value targets) are repacked into the tile-major layout.
-#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "comm.h"
@@ -66,68 +65,64 @@ __global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, f
 // fp64 accumulation in a fixed slab order -> deterministic.
 #define RED_PX 32
 #define RED_SY 8
-// Grid-stride over 32-parameter chunks: all CTAs are resident at once (launch_reduce_partials sizes the grid), every
-// thread keeps four independent loads in flight, and a pushing CTA pays ONE system-scope fence after its last chunk
-// (the fence waits for the NVLink acknowledgements of all its peer stores - per chunk it was the whole kernel).
+#define RED_UN 8
 __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     NetGeom g, const float* __restrict__ part1, const float* __restrict__ partm, int n_slabs, double scale,
     const float* __restrict__ theta, double l2c2, const float* __restrict__ vlogstd_src, double vls,
     float* __restrict__ out32, double* __restrict__ out64, P2pPush push) {
   __shared__ double acc[RED_SY][RED_PX];
   const int px = threadIdx.x, sy = threadIdx.y;
-  const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int i = chunk * RED_PX + px;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (i < g.P) {
-      const float* src = nullptr;
-      size_t stride = 0;
-      if (i < g.off_flat_b[1]) {
-        const int k = i / g.d[1], n = i % g.d[1];
-        src = part1 + (size_t)k * g.n1p + n;
-        stride = (size_t)g.d[0] * g.n1p;
-      } else if (g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) {
-        src = partm + g.off_pm_logstd + (i - g.off_flat_logstd);
-        stride = g.pmid;
-      } else {
-        for (int l = g.L; l >= 1; --l) {
-          if (i >= g.off_flat_b[l]) {
-            src = partm + g.off_b[l] + (i - g.off_flat_b[l]);
-            break;
-          }
-          if (i >= g.off_flat_W[l]) {
-            const int q = i - g.off_flat_W[l];
-            src = partm + g.off_W[l] + (q / g.d[l]) * g.ldw[l] + (q % g.d[l]);
-            break;
-          }
+  const int i = blockIdx.x * RED_PX + px;
+  double s0 = 0.0, s1 = 0.0;   // even / odd batches of RED_UN slabs
+  if (i < g.P) {
+    const float* src = nullptr;
+    size_t stride = 0;
+    if (i < g.off_flat_b[1]) {
+      const int k = i / g.d[1], n = i % g.d[1];
+      src = part1 + (size_t)k * g.n1p + n;
+      stride = (size_t)g.d[0] * g.n1p;
+    } else if (g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) {
+      src = partm + g.off_pm_logstd + (i - g.off_flat_logstd);
+      stride = g.pmid;
+    } else {
+      for (int l = g.L; l >= 1; --l) {
+        if (i >= g.off_flat_b[l]) {
+          src = partm + g.off_b[l] + (i - g.off_flat_b[l]);
+          break;
         }
-        stride = g.pmid;
+        if (i >= g.off_flat_W[l]) {
+          const int q = i - g.off_flat_W[l];
+          src = partm + g.off_W[l] + (q / g.d[l]) * g.ldw[l] + (q % g.d[l]);
+          break;
+        }
       }
-      int sl = sy;   // this thread's slabs: sy, sy+8, ... in four chains for memory-level parallelism
-      for (; sl + 3 * RED_SY < n_slabs; sl += 4 * RED_SY) {
-        const float a0 = src[(size_t)sl * stride], a1 = src[(size_t)(sl + RED_SY) * stride];
-        const float a2 = src[(size_t)(sl + 2 * RED_SY) * stride], a3 = src[(size_t)(sl + 3 * RED_SY) * stride];
-        s0 += (double)a0; s1 += (double)a1; s2 += (double)a2; s3 += (double)a3;
-      }
-      if (sl < n_slabs) s0 += (double)src[(size_t)sl * stride];
-      if (sl + RED_SY < n_slabs) s1 += (double)src[(size_t)(sl + RED_SY) * stride];
-      if (sl + 2 * RED_SY < n_slabs) s2 += (double)src[(size_t)(sl + 2 * RED_SY) * stride];
+      stride = g.pmid;
     }
-    acc[sy][px] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (sy == 0 && i < g.P) {
-      double r = 0.0;
+    // this thread's slabs: sy, sy+8, ...; RED_UN loads are in flight at a time (the kernel is bound by the latency of
+    // these strided 128-byte-per-warp reads), summed in slab order
+    int sl = sy;
+    for (; sl + (RED_UN - 1) * RED_SY < n_slabs; sl += RED_UN * RED_SY) {
+      float a[RED_UN];
 #pragma unroll
-      for (int q = 0; q < RED_SY; ++q) r += acc[q][px];   // fixed order -> deterministic
-      r *= scale;
-      if (vlogstd_src != nullptr && g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) r = vls * (double)vlogstd_src[i];
-      if (theta != nullptr) r += l2c2 * (double)theta[i];
-      if (out32) out32[i] = (float)r;
-      if (out64) out64[i] = r;
-      // data-parallel: this rank's partial goes straight into every peer's receive buffer over NVLink
-      if (push.world) p2p_push_value(push, i, r);
+      for (int u = 0; u < RED_UN; ++u) a[u] = __ldcs(src + (size_t)(sl + u * RED_SY) * stride);
+#pragma unroll
+      for (int u = 0; u < RED_UN; u += 2) { s0 += (double)a[u]; s1 += (double)a[u + 1]; }
     }
-    __syncthreads();   // acc is reused by the next chunk
+    for (; sl < n_slabs; sl += RED_SY) s0 += (double)__ldcs(src + (size_t)sl * stride);
+  }
+  acc[sy][px] = s0 + s1;
+  __syncthreads();
+  if (sy == 0 && i < g.P) {
+    double r = 0.0;
+#pragma unroll
+    for (int q = 0; q < RED_SY; ++q) r += acc[q][px];   // fixed order -> deterministic
+    r *= scale;
+    if (vlogstd_src != nullptr && g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) r = vls * (double)vlogstd_src[i];
+    if (theta != nullptr) r += l2c2 * (double)theta[i];
+    if (out32) out32[i] = (float)r;
+    if (out64) out64[i] = r;
+    // data-parallel: into this rank's exported vector, which the peers read over NVLink (comm.h)
+    if (push.world) p2p_push_value(push, i, r);
   }
   if (push.world) p2p_push_done(push);
 }
@@ -294,25 +289,12 @@ cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img,
   return cudaGetLastError();
 }
 
-static int red_ctas_per_sm() {   // MRL_RED_CPS: experiment knob, 1..8 (8 x 256 threads fill an SM)
-  static const int v = [] {
-    const char* e = getenv("MRL_RED_CPS");
-    const int x = e ? atoi(e) : 6;
-    return x < 1 ? 1 : (x > 8 ? 8 : x);
-  }();
-  return v;
-}
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
                                    float* out32, double* out64, const P2pPush* push, cudaStream_t st) {
   P2pPush none;
   none.world = 0;
-  // one resident wave: at most RED_CTAS_PER_SM CTAs per SM, chunks dealt evenly (each CTA takes `rounds` of them)
-  const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
-  const int wave = mrl_sm_count() * red_ctas_per_sm();
-  const int rounds = (n_chunks + wave - 1) / wave;
-  const int grid = (n_chunks + rounds - 1) / rounds;
-  reduce_partials_kernel<<<grid, dim3(RED_PX, RED_SY), 0, st>>>(
+  reduce_partials_kernel<<<(g.P + RED_PX - 1) / RED_PX, dim3(RED_PX, RED_SY), 0, st>>>(
       g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32, out64, push ? *push : none);
   return cudaGetLastError();
 }

@@ -57,7 +57,7 @@ static int nccl_fail(const char* what, int rc) {
   return mrl_set_error(buf);
 }
 
-// receive buffer of one rank: [flags 2 x 8][data 2 (parity) x world x cap]
+// exported buffer of one rank: [flags 2 (parity) x 8, raised by the peers][this rank's vector, 2 (parity) x cap]
 struct P2pState {
   bool on = false;
   long long cap = 0;                                  // doubles per slot
@@ -73,8 +73,8 @@ struct P2pState {
 static inline unsigned long long* p2p_flags(unsigned char* base, int parity) {
   return reinterpret_cast<unsigned long long*>(base) + parity * MRL_P2P_MAX_WORLD;
 }
-static inline double* p2p_slot(unsigned char* base, long long cap, int world, int parity, int r) {
-  return reinterpret_cast<double*>(base + P2P_HEADER) + ((size_t)parity * world + r) * cap;
+static inline double* p2p_vector(unsigned char* base, long long cap, int parity) {
+  return reinterpret_cast<double*>(base + P2P_HEADER) + (size_t)parity * cap;
 }
 
 struct mrl_comm {
@@ -128,7 +128,7 @@ extern "C" int mrl_comm_destroy(mrl_comm* c) {
 }
 
 // ---------------------------------------------------------------------------------- peer-memory transport
-// Step 1 (every rank): allocate the receive buffer, return its CUDA IPC handle (64 bytes).
+// Step 1 (every rank): allocate the exported buffer, return its CUDA IPC handle (64 bytes).
 extern "C" int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char handle_out[64]) {
   if (!c || !handle_out || max_doubles <= 0) return mrl_set_error("mrl_comm_p2p_export: bad arguments");
   if (c->world > MRL_P2P_MAX_WORLD) return mrl_set_error("mrl_comm_p2p_export: world > 8");
@@ -136,7 +136,7 @@ extern "C" int mrl_comm_p2p_export(mrl_comm* c, long long max_doubles, char hand
   P2pState& p = c->p2p;
   if (p.local) return mrl_set_error("mrl_comm_p2p_export: already exported");
   p.cap = (max_doubles + 31) / 32 * 32;
-  const size_t bytes = P2P_HEADER + (size_t)2 * c->world * p.cap * 8;
+  const size_t bytes = P2P_HEADER + (size_t)2 * p.cap * 8;
   if (cudaMalloc(&p.local, bytes) != cudaSuccess || cudaMalloc(&p.counter, 4) != cudaSuccess)
     return mrl_set_error("mrl_comm_p2p_export: out of device memory");
   cudaMemset(p.local, 0, bytes);
@@ -194,25 +194,22 @@ int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push) {
   P2pState& p = c->p2p;
   p.seq += 1;
   const int parity = (int)(p.seq & 1);
-  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) { push->slot[q] = nullptr; push->flag[q] = nullptr; }
-  for (int q = 0; q < c->world; ++q) {
-    push->slot[q] = p2p_slot(p.peer[q], p.cap, c->world, parity, c->rank);
-    push->flag[q] = p2p_flags(p.peer[q], parity) + c->rank;
-  }
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) push->flag[q] = nullptr;
+  for (int q = 0; q < c->world; ++q) push->flag[q] = p2p_flags(p.peer[q], parity) + c->rank;
+  push->own = p2p_vector(p.local, p.cap, parity);
   push->counter = p.counter;
   push->seq = p.seq;
   push->world = c->world;
   return 0;
 }
 
-// Wait until every rank's flag of this parity shows `seq`, then out[i] = sum_r slot[r][i] in rank order.
-// Double buffering by parity is enough: rank r can only start operation seq+2 after it has seen every
-// rank's flag for seq+1, which a rank raises after it finished reading the slots of seq.
+// Wait until every rank's flag of this parity shows `seq`, then out[i] = sum_r vector_r[i] in rank order.
+// Double buffering by parity is enough: rank r can only overwrite its vector of operation seq (in seq+2) after it has
+// seen every rank's flag for seq+1, which a rank raises after it finished reading the vectors of seq.
 __global__ void p2p_gather_kernel(P2pGather ga, long long n, double* __restrict__ out64, float* __restrict__ out32) {
   p2p_wait_flags(ga);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < ga.world; ++r) s += __ldcg(ga.slots + (size_t)r * ga.cap + i);
+    const double s = p2p_gather_sum(ga, i);
     if (out64) out64[i] = s;
     if (out32) out32[i] = (float)s;
   }
@@ -222,8 +219,7 @@ int mrl_comm_p2p_pending(mrl_comm* c, P2pGather* out) {
   P2pState& p = c->p2p;
   const int parity = (int)(p.seq & 1);
   out->flags = p2p_flags(p.local, parity);
-  out->slots = p2p_slot(p.local, p.cap, c->world, parity, 0);
-  out->cap = p.cap;
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) out->src[q] = q < c->world ? p2p_vector(p.peer[q], p.cap, parity) : nullptr;
   out->seq = p.seq;
   out->timeout_ns = p.timeout_ns;
   out->err = p.d_err;

