@@ -889,8 +889,7 @@ static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
 
 // reverse sweep + layer-1 gradient + slab reduce -> out32 (float[P], device) and out64 (double[P]).
 static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
-                         const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st,
-                         P2pGather* defer = nullptr) {
+                         const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
   const NetGeom& g = n->g;
   const bool tc = mode == MRL_MODE_FVP && n->tc_fvp;
   const Plan pl = plan_for(b, tc);
@@ -935,19 +934,19 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   // terms that are not sums over timesteps are divided by `world` so that the sum over ranks restores them
   const double vls = (mode == MRL_MODE_FVP) ? 2.0 / world : 0.0;
   const bool p2p = world > 1 && mrl_comm_p2p_ready(n->comm, g.P);
+  // peer-memory transport: the reduce kernel publishes this rank's vector, waits for the peers' and writes the sum
+  // over ranks itself (comm.h); otherwise out64 holds this rank's share and NCCL sums it
   P2pPush push;
-  if (p2p) RET(mrl_comm_p2p_begin(n->comm, g.P, &push));
+  P2pGather gather;
+  if (p2p) {
+    RET(mrl_comm_p2p_begin(n->comm, g.P, &push));
+    RET(mrl_comm_p2p_pending(n->comm, &gather));
+  }
   CKP(PK_REDUCE, launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
-                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, world > 1 ? nullptr : out32,
-                             p2p ? nullptr : out64, p2p ? &push : nullptr, st), 1);
-  if (defer) defer->world = 0;
-  if (p2p && defer) {   // the caller's next kernel (the CG iteration) is the receiving side of the sum
-    RET(mrl_comm_p2p_pending(n->comm, defer));
-  } else if (p2p) {     // fused: the reduce kernel pushed this rank's vector to every peer; wait + sum in rank order
-    RET(mrl_comm_p2p_finish(n->comm, g.P, out64, out32, st));
-    g_launches += 1;
-  } else if (world > 1) {
+                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, (world > 1 && !p2p) ? nullptr : out32,
+                             out64, p2p ? &push : nullptr, p2p ? &gather : nullptr, st), 1);
+  if (world > 1 && !p2p) {
     RET(mrl_comm_allreduce_f64(n->comm, out64, g.P, st));
     if (out32) {
       cast_f64_f32(out64, out32, g.P, st);
@@ -1178,15 +1177,12 @@ extern "C" int mrl_net_trpo_step(mrl_net* n, mrl_batch* b, const mrl_trpo_cfg* c
   CK(cudaMemcpyAsync(n->h_scal, n->scal.p, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(n->h_cg, n->cgstate.p, sizeof(CgState), cudaMemcpyDeviceToHost, st));
   // CG does not depend on the host check below, so it is enqueued before the sync
-  const bool fuse_rx = cg_step_fuses_gather(P);
   for (int it = 0; it < cfg->cg_iters; ++it) {
-    P2pGather ga;
-    ga.world = 0;
     RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->p32.as<float>(), 0.0, n->out32.as<float>(),
-                      n->out64.as<double>(), st, fuse_rx ? &ga : nullptr));
+                      n->out64.as<double>(), st));
     CKP(PK_CG, launch_cg_step(P, n->out32.as<float>(), cfg->cg_damping, cfg->residual_tol, n->cg_x.as<double>(),
                        n->cg_r.as<double>(), n->cg_p.as<double>(), n->p32.as<float>(), n->cgstate.as<CgState>(),
-                       n->cgscratch.as<double>(), st, ga.world ? &ga : nullptr), 1);
+                       n->cgscratch.as<double>(), st), 1);
   }
   CKL(launch_cg_prepare_shs(P, n->cg_x.as<double>(), n->x32.as<float>(), st), 1);
   RET(pass_backward(n, b, MRL_MODE_FVP, nullptr, 0, n->x32.as<float>(), 0.0, n->out32.as<float>(),

@@ -4,6 +4,7 @@
 // shared-memory image the fused chain loads ([biases | logstd | W2..WL | W2^T..WL^T]) and into the
 // split-precision tensor-core operand of layer 1 (see mlp_l1_tc.cu).  Side inputs of the batch
 // (advantages, actions, old probabilities, value targets) are repacked into the tile-major layout.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "comm.h"
@@ -63,68 +64,97 @@ __global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, f
 // flat[i] = scale * sum_slabs(partials) (+ l2c2 * theta[i]); on the logstd block an Fvp is vls * v[i]
 // (fvp[logstd] = 2 v_logstd is data independent)
 // fp64 accumulation in a fixed slab order -> deterministic.
+// Data-parallel with the peer-memory transport (push.world > 0): phase 1 writes this rank's sums into its exported
+// vector and the last CTA raises this rank's flag on every peer; phase 2 waits for all ranks' flags, reads the peers'
+// vectors over NVLink - thread row sy reads rank sy, the whole GPU shares the round trips - and writes the sum over
+// ranks (rank order: identical bits everywhere).  CTAs spin in phase 2 while others still work in phase 1, so the
+// launcher sizes such a grid to be resident at once; chunks are dealt grid-stride.
 #define RED_PX 32
 #define RED_SY 8
 #define RED_UN 8
+static_assert(RED_SY >= MRL_P2P_MAX_WORLD, "one thread row per rank in the exchange phase");
 __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     NetGeom g, const float* __restrict__ part1, const float* __restrict__ partm, int n_slabs, double scale,
     const float* __restrict__ theta, double l2c2, const float* __restrict__ vlogstd_src, double vls,
-    float* __restrict__ out32, double* __restrict__ out64, P2pPush push) {
+    float* __restrict__ out32, double* __restrict__ out64, P2pPush push, P2pGather ga) {
   __shared__ double acc[RED_SY][RED_PX];
   const int px = threadIdx.x, sy = threadIdx.y;
-  const int i = blockIdx.x * RED_PX + px;
-  double s0 = 0.0, s1 = 0.0;   // even / odd batches of RED_UN slabs
-  if (i < g.P) {
-    const float* src = nullptr;
-    size_t stride = 0;
-    if (i < g.off_flat_b[1]) {
-      const int k = i / g.d[1], n = i % g.d[1];
-      src = part1 + (size_t)k * g.n1p + n;
-      stride = (size_t)g.d[0] * g.n1p;
-    } else if (g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) {
-      src = partm + g.off_pm_logstd + (i - g.off_flat_logstd);
-      stride = g.pmid;
-    } else {
-      for (int l = g.L; l >= 1; --l) {
-        if (i >= g.off_flat_b[l]) {
-          src = partm + g.off_b[l] + (i - g.off_flat_b[l]);
-          break;
+  const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int i = chunk * RED_PX + px;
+    double s0 = 0.0, s1 = 0.0;   // even / odd members of a batch of RED_UN slabs
+    if (i < g.P) {
+      const float* src = nullptr;
+      size_t stride = 0;
+      if (i < g.off_flat_b[1]) {
+        const int k = i / g.d[1], n = i % g.d[1];
+        src = part1 + (size_t)k * g.n1p + n;
+        stride = (size_t)g.d[0] * g.n1p;
+      } else if (g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) {
+        src = partm + g.off_pm_logstd + (i - g.off_flat_logstd);
+        stride = g.pmid;
+      } else {
+        for (int l = g.L; l >= 1; --l) {
+          if (i >= g.off_flat_b[l]) {
+            src = partm + g.off_b[l] + (i - g.off_flat_b[l]);
+            break;
+          }
+          if (i >= g.off_flat_W[l]) {
+            const int q = i - g.off_flat_W[l];
+            src = partm + g.off_W[l] + (q / g.d[l]) * g.ldw[l] + (q % g.d[l]);
+            break;
+          }
         }
-        if (i >= g.off_flat_W[l]) {
-          const int q = i - g.off_flat_W[l];
-          src = partm + g.off_W[l] + (q / g.d[l]) * g.ldw[l] + (q % g.d[l]);
-          break;
-        }
+        stride = g.pmid;
       }
-      stride = g.pmid;
+      // this thread's slabs: sy, sy+8, ...; RED_UN loads in flight at a time, summed in slab order
+      int sl = sy;
+      for (; sl + (RED_UN - 1) * RED_SY < n_slabs; sl += RED_UN * RED_SY) {
+        float a[RED_UN];
+#pragma unroll
+        for (int u = 0; u < RED_UN; ++u) a[u] = __ldcs(src + (size_t)(sl + u * RED_SY) * stride);
+#pragma unroll
+        for (int u = 0; u < RED_UN; u += 2) { s0 += (double)a[u]; s1 += (double)a[u + 1]; }
+      }
+      for (; sl < n_slabs; sl += RED_SY) s0 += (double)__ldcs(src + (size_t)sl * stride);
     }
-    // this thread's slabs: sy, sy+8, ...; RED_UN loads are in flight at a time (the kernel is bound by the latency of
-    // these strided 128-byte-per-warp reads), summed in slab order
-    int sl = sy;
-    for (; sl + (RED_UN - 1) * RED_SY < n_slabs; sl += RED_UN * RED_SY) {
-      float a[RED_UN];
+    acc[sy][px] = s0 + s1;
+    __syncthreads();
+    if (sy == 0 && i < g.P) {
+      double r = 0.0;
 #pragma unroll
-      for (int u = 0; u < RED_UN; ++u) a[u] = __ldcs(src + (size_t)(sl + u * RED_SY) * stride);
-#pragma unroll
-      for (int u = 0; u < RED_UN; u += 2) { s0 += (double)a[u]; s1 += (double)a[u + 1]; }
+      for (int q = 0; q < RED_SY; ++q) r += acc[q][px];   // fixed order -> deterministic
+      r *= scale;
+      if (vlogstd_src != nullptr && g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) r = vls * (double)vlogstd_src[i];
+      if (theta != nullptr) r += l2c2 * (double)theta[i];
+      if (push.world) {
+        p2p_push_value(push, i, r);     // this rank's share; the totals are written in phase 2
+      } else {
+        if (out32) out32[i] = (float)r;
+        if (out64) out64[i] = r;
+      }
     }
-    for (; sl < n_slabs; sl += RED_SY) s0 += (double)__ldcs(src + (size_t)sl * stride);
+    __syncthreads();                    // acc is reused
   }
-  acc[sy][px] = s0 + s1;
-  __syncthreads();
-  if (sy == 0 && i < g.P) {
-    double r = 0.0;
+  if (push.world == 0) return;
+  p2p_push_done(push);
+  p2p_wait_flags(ga, sy * RED_PX + px);
+  const double* peer = nullptr;          // rank sy's vector (selected without indexing the kernel parameter)
 #pragma unroll
-    for (int q = 0; q < RED_SY; ++q) r += acc[q][px];   // fixed order -> deterministic
-    r *= scale;
-    if (vlogstd_src != nullptr && g.off_flat_logstd >= 0 && i >= g.off_flat_logstd) r = vls * (double)vlogstd_src[i];
-    if (theta != nullptr) r += l2c2 * (double)theta[i];
-    if (out32) out32[i] = (float)r;
-    if (out64) out64[i] = r;
-    // data-parallel: into this rank's exported vector, which the peers read over NVLink (comm.h)
-    if (push.world) p2p_push_value(push, i, r);
+  for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q)
+    if (q == sy && q < ga.world) peer = ga.src[q];
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int i = chunk * RED_PX + px;
+    acc[sy][px] = (peer != nullptr && i < g.P) ? p2p_load(peer + i) : 0.0;
+    __syncthreads();
+    if (sy == 0 && i < g.P) {
+      double r = 0.0;
+      for (int q = 0; q < ga.world; ++q) r += acc[q][px];   // rank order
+      if (out32) out32[i] = (float)r;
+      if (out64) out64[i] = r;
+    }
+    __syncthreads();
   }
-  if (push.world) p2p_push_done(push);
 }
 
 // loss partials [n_slabs][4] doubles -> out[4] = scale * sums (single block)
@@ -291,11 +321,26 @@ cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img,
 
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
-                                   float* out32, double* out64, const P2pPush* push, cudaStream_t st) {
-  P2pPush none;
-  none.world = 0;
-  reduce_partials_kernel<<<(g.P + RED_PX - 1) / RED_PX, dim3(RED_PX, RED_SY), 0, st>>>(
-      g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32, out64, push ? *push : none);
+                                   float* out32, double* out64, const P2pPush* push, const P2pGather* gather,
+                                   cudaStream_t st) {
+  P2pPush no_push;
+  no_push.world = 0;
+  P2pGather no_gather;
+  no_gather.world = 0;
+  const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
+  int grid = n_chunks;
+  if (push) {
+    // the exchange phase spins on the peers' flags: every CTA of the grid must be resident
+    if (!gather || gather->world != push->world) return cudaErrorInvalidValue;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_partials_kernel, RED_PX * RED_SY, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const int wave = mrl_sm_count() * per_sm;
+    grid = n_chunks < wave ? n_chunks : wave;     // (equal chunk counts per CTA instead: same time, measured at 4 ranks)
+  }
+  reduce_partials_kernel<<<grid, dim3(RED_PX, RED_SY), 0, st>>>(g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32,
+                                                             out64, push ? *push : no_push, push ? *gather : no_gather);
   return cudaGetLastError();
 }
 

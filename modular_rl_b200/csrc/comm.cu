@@ -207,7 +207,7 @@ int mrl_comm_p2p_begin(mrl_comm* c, long long n, P2pPush* push) {
 // Double buffering by parity is enough: rank r can only overwrite its vector of operation seq (in seq+2) after it has
 // seen every rank's flag for seq+1, which a rank raises after it finished reading the vectors of seq.
 __global__ void p2p_gather_kernel(P2pGather ga, long long n, double* __restrict__ out64, float* __restrict__ out32) {
-  p2p_wait_flags(ga);
+  p2p_wait_flags(ga, threadIdx.x);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double s = p2p_gather_sum(ga, i);
     if (out64) out64[i] = s;

@@ -1,9 +1,11 @@
 // Data-parallel communicator.  Two transports for the sum over ranks of small fp64 vectors:
 //   * peer memory over NVLink / NVSwitch (CUDA IPC): every rank writes its vector into its OWN exported buffer
-//     straight from the kernel that produced it and raises a flag in every peer's buffer; each rank then READS the
-//     peers' vectors over NVLink and sums them in rank order - no collective launch, bit-identical sums on all
-//     ranks.  (Round 1 pushed the data instead: world x the stores and a system-scope fence per producing CTA that
-//     waited for every NVLink acknowledgement made the producing kernel 33-45 us against 13 us without the push.)
+//     straight from the kernel that produced it and raises a flag in every peer's buffer; the SAME kernel then waits
+//     for the peers' flags, READS their vectors over NVLink and sums them in rank order - no collective launch, one
+//     flag hop + one read round trip, bit-identical sums on all ranks.  (Round 1 pushed the data instead: world x
+//     the stores and a system-scope fence per producing CTA that waited for every NVLink acknowledgement made the
+//     producing kernel 33-45 us against 13 us alone; reading the peers from the 8-CTA CG cluster kernel cost it
+//     19 us at 8 ranks - too few SMs for that many NVLink round trips; the slab reduce has the whole GPU.)
 //   * NCCL (the copy torch already loaded, found with dlopen) as the fallback for vectors that do not fit the
 //     receive buffer or when peer access is unavailable.
 #pragma once
@@ -24,7 +26,8 @@ struct P2pPush {
   int world;                    // 0: no push
 };
 // The receiving side of one peer-memory sum, for a kernel that folds the wait + rank-order sum into its own work
-// (cg_step_cluster_kernel): this rank's flags of the pending operation and every rank's exported vector.
+// (reduce_partials_kernel, whose grid is sized to be resident at once when it exchanges): this rank's flags of the
+// pending operation and every rank's exported vector.
 struct P2pGather {
   const unsigned long long* flags;   // [world] sequence flags of the operation's parity (local memory)
   const double* src[MRL_P2P_MAX_WORLD];   // rank q's vector as mapped here (peer memory for q != this rank)
@@ -58,9 +61,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // Wait until every rank's flag shows the operation's sequence number (threads 0..world-1 of the CTA poll, then the CTA
 // synchronises).  A peer may legitimately be late by seconds; the bound is wall-clock time and a lost peer becomes an
 // error word the host checks - never a trap, never a hung GPU.
-__device__ __forceinline__ void p2p_wait_flags(const P2pGather& ga) {
-  if (threadIdx.x < ga.world) {
-    const unsigned long long* f = ga.flags + threadIdx.x;
+__device__ __forceinline__ void p2p_wait_flags(const P2pGather& ga, int tid) {   // tid: linear thread index in the CTA
+  if (tid < ga.world) {
+    const unsigned long long* f = ga.flags + tid;
     unsigned long long t0 = 0;
     unsigned int spins = 0;
     while (ld_acquire_sys(f) < ga.seq) {
@@ -74,6 +77,11 @@ __device__ __forceinline__ void p2p_wait_flags(const P2pGather& ga) {
   }
   __syncthreads();
 }
+__device__ __forceinline__ double p2p_load(const double* p) {   // relaxed system-scope load (after the flag acquire)
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 // element i of the rank-order sum: all ranks' loads are issued before the first add (peer loads cost an NVLink round
 // trip each); relaxed system-scope loads, ordered after the acquire of p2p_wait_flags
 __device__ __forceinline__ double p2p_gather_sum(const P2pGather& ga, long long i) {
@@ -81,7 +89,7 @@ __device__ __forceinline__ double p2p_gather_sum(const P2pGather& ga, long long 
 #pragma unroll
   for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q) {
     v[q] = 0.0;
-    if (q < ga.world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[q]) : "l"(ga.src[q] + i));
+    if (q < ga.world) v[q] = p2p_load(ga.src[q] + i);
   }
   double s = 0.0;
 #pragma unroll

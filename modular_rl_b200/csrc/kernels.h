@@ -6,7 +6,8 @@
 cudaError_t launch_pack_params(const NetGeom& g, const float* theta, float* img, float* WB, cudaStream_t st);
 cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const float* partm, int n_slabs,
                                    double scale, const float* theta, double l2c2, const float* vflat, double vls,
-                                   float* out32, double* out64, const struct P2pPush* push, cudaStream_t st);
+                                   float* out32, double* out64, const struct P2pPush* push, const struct P2pGather* gather,
+                                   cudaStream_t st);
 cudaError_t launch_reduce_losses(const double* parts, int n_slabs, double scale, double* out, cudaStream_t st);
 cudaError_t launch_pack_tiles(const void* src, int dtype, long long ld, int ncols, int ncols_out, long long N,
                               float* dst, int rows_per_tile, int row_off, int n_tiles, cudaStream_t st);
@@ -116,12 +117,9 @@ cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* 
                            CgState* s, cudaStream_t st);
 #define CG_CTAS 32                              // co-resident CTAs of the CG iteration kernel
 #define CG_SCRATCH_DOUBLES (2 * CG_CTAS + 40)   // two partial-sum rows + the grid barrier words
-// ga != nullptr (data-parallel, peer-memory transport): the kernel is also the receiving side of the pending sum
-// over ranks and takes z from the receive slots instead of z32 (only where cg_step_fuses_gather(P))
-bool cg_step_fuses_gather(int P);
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
                            float* p32, CgState* s, double* scratch /* CG_SCRATCH_DOUBLES, zeroed once */,
-                           cudaStream_t st, const struct P2pGather* ga = nullptr);
+                           cudaStream_t st);
 cudaError_t launch_cg_prepare_shs(int P, const double* x, float* x32, cudaStream_t st);
 cudaError_t launch_cg_finish(int P, const float* z32, double damping, double max_kl, const float* g,
                              const double* x, double* fullstep, CgState* s, cudaStream_t st);

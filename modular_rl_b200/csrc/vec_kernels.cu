@@ -164,14 +164,10 @@ __device__ __forceinline__ double cgc_cluster_sum(cgx::cluster_group& cl, double
 
 __global__ void __cluster_dims__(CGC_CTAS, 1, 1) __launch_bounds__(CGC_THREADS)
 cg_step_cluster_kernel(int P, const float* __restrict__ z32, double damping, double tol, double* __restrict__ x,
-                       double* __restrict__ r, double* __restrict__ p, float* __restrict__ p32, CgState* s, P2pGather ga) {
+                       double* __restrict__ r, double* __restrict__ p, float* __restrict__ p32, CgState* s) {
   cgx::cluster_group cl = cgx::this_cluster();
   __shared__ double wsum[32];
   __shared__ double slots[2], tots[2];
-  // data-parallel: this kernel is also the receiving side of the peer-memory sum of the Fisher-vector product (one
-  // launch less per CG iteration): wait for every rank's flag - even when CG is done, the double-buffering of the
-  // transport relies on it - then z = sum over ranks in rank order, rounded to float32 like the reference's fvp output
-  if (ga.world) p2p_wait_flags(ga);
   if (s->done) return;                 // uniform over the cluster
   const double rdotr = s->rdotr;
   const int t0 = (int)cl.block_rank() * CGC_THREADS + threadIdx.x;
@@ -182,8 +178,7 @@ cg_step_cluster_kernel(int P, const float* __restrict__ z32, double damping, dou
     const int i = t0 + k * (CGC_CTAS * CGC_THREADS);
     const bool in = i < P;
     pi[k] = in ? p[i] : 0.0;
-    if (ga.world) zf[k] = in ? (float)p2p_gather_sum(ga, i) : 0.f;
-    else zf[k] = in ? z32[i] : 0.f;
+    zf[k] = in ? z32[i] : 0.f;
     ri[k] = in ? r[i] : 0.0;
   }
   double pz = 0.0;
@@ -276,9 +271,8 @@ cudaError_t launch_cg_init(int P, const float* g, double* b, double* x, double* 
   cg_init_kernel<<<1, VEC_THREADS, 0, st>>>(P, g, b, x, r, p, p32, s);
   return cudaGetLastError();
 }
-bool cg_step_fuses_gather(int P) { return P <= CGC_CTAS * CGC_THREADS * CGC_K && !getenv("MRL_CG_GRID"); }
 cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, double* x, double* r, double* p,
-                           float* p32, CgState* s, double* scratch, cudaStream_t st, const P2pGather* ga) {
+                           float* p32, CgState* s, double* scratch, cudaStream_t st) {
   // scratch: [CG_CTAS] pz partials, [CG_CTAS] rr partials, then the barrier's arrive counter and generation
   // word (zero-initialised once by the caller; the barrier leaves arrive at 0)
   double* parts_pz = scratch;
@@ -286,12 +280,9 @@ cudaError_t launch_cg_step(int P, const float* z32, double damping, double tol, 
   unsigned int* bar = reinterpret_cast<unsigned int*>(scratch + 2 * CG_CTAS);   // arrive and generation on separate lines
   // MRL_CG_GRID=1 forces the grid-barrier kernel (the path of P > 49 152), so the tests can cover it on small nets
   if (P <= CGC_CTAS * CGC_THREADS * CGC_K && !getenv("MRL_CG_GRID")) {
-    P2pGather none;
-    none.world = 0;
-    cg_step_cluster_kernel<<<CGC_CTAS, CGC_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s, ga ? *ga : none);
+    cg_step_cluster_kernel<<<CGC_CTAS, CGC_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s);
     return cudaGetLastError();
   }
-  if (ga) return cudaErrorInvalidValue;   // the fused receive exists in the cluster kernel only (see cg_step_fuses_gather)
   cg_step_kernel<<<CG_CTAS, CG_THREADS, 0, st>>>(P, z32, damping, tol, x, r, p, p32, s, parts_pz, parts_rr, bar, bar + 32);
   return cudaGetLastError();
 }
