@@ -19,20 +19,23 @@
 // copies + converter another 23 KB: shared-memory bandwidth (128 B/cycle), not the tensor pipe, set the pace.
 //   stage (forward):  [A raw fp32: 3 k-groups x 4 KB][B: 3 x (hi | lo) x [khalf 2][ngroup NU/8][8][4]]
 //   stage (gradient): [A raw fp32: ftiles x 4 KB][B = delta_1 of 8 timesteps (hi | lo)]
-// Warp roles (384 threads): warp 0 = bulk-copy producer (one thread), warp 1 = TMEM allocator + MMA issuer (the
+// Warp roles (448 threads): warp 0 = bulk-copy producer (one thread), warp 1 = TMEM allocator + MMA issuer (the
 // whole warp walks the loop, one elected lane issues: inside an `if (lane == 0)` region ptxas wraps every
 // tcgen05.mma in an ELECT / BRA.U.ANY loop), warps 2..5 = epilogue (tcgen05.ld of their TMEM lane quarter ->
-// HBM), warps 6..9 = converters (one TMEM lane quarter each), warps 10..11 idle.  The forward kernel double-
+// HBM), warps 6..13 = converters (TC_CGROUPS groups of four, one TMEM lane quarter per warp; stage uses alternate between the groups).  The forward kernel double-
 // buffers its accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent grid.
 // The pipeline was tuned with a clock64 trace of every hand-over (-DMRL_TRACE, tools/micro/l1_trace.py).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
 
 #define TC_STAGES 12         // pipeline depth: ~4 KB of HBM data per stage must cover a ~4000-cycle round trip
-#define TC_CONV 6            // converter warps: warp c owns stages s = c (mod TC_CONV), visited in pipeline order
-                             // (a 1-bit phase parity must never be lapped)
-#define TC_THREADS (192 + 32 * TC_CONV)
+#define TC_CGROUPS 2         // converter groups of four warps (one per TMEM lane quarter).  With `cgroups` = 2 group c
+                             // converts the stage uses u = c (mod 2), so the tcgen05.st round trips of consecutive
+                             // stages overlap; the rings then have even lengths, every stage / slot (and its 1-bit
+                             // phase parity) belongs to ONE group, which visits it in pipeline order as before
+#define TC_THREADS (192 + 128 * TC_CGROUPS)
 #define TC_M 128
 
 #ifdef MRL_TRACE
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
                                                                       float* __restrict__ Zt, int kgroups,
                                                                       int xa_kgroups, int nu, int d1, int n_mtiles,
                                                                       int n_tiles, int acc_cols, int n_acc, int tmem_cols,
-                                                                      int nstages, int kps) {
+                                                                      int nstages, int kps, int cgroups) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [TC_STAGES]
   uint64_t* empty = full + TC_STAGES;                           // [TC_STAGES]
@@ -176,12 +179,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
         }
       }
     }
-  } else if (warp >= 6 && warp < 10) {   // ---------------- converters: raw A rows -> tensor memory (hi, lo)
+  } else if (warp >= 6) {   // ---------------- converters: raw A rows -> tensor memory (hi, lo)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;     // row of the 128-timestep tile
-    int s = 0, ph = 0, u = 0;
-    for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+    const int cgroup = (warp - 6) >> 2;
+    int s = cgroup, ph = 0, u = 0;
+    for (int mt = blockIdx.x; cgroup < cgroups && mt < n_mtiles; mt += gridDim.x) {
       for (int q = 0; q < spt; ++q, ++u) {
+        if ((u & (cgroups - 1)) != cgroup) continue;
         const int nk = min(kps, kgroups - q * kps);
         mbar_wait_guard(&full[s], ph);
         if (warp == 6 && lane == 0) TRACE(2, u);
@@ -206,7 +211,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_forward_tc_kernel(const floa
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
         if (warp == 6 && lane == 0) TRACE(3, u);
-        if (++s == nstages) { s = 0; ph ^= 1; }
+        s += cgroups;
+        if (s >= nstages) { s -= nstages; ph ^= 1; }
       }
     }
   } else if (warp >= 2 && warp < 6) {   // ---------------- epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
                                                                    int xg_ftiles, int nu, int d0, int n1p,
                                                                    int slab_tiles, int n_tiles, int n_slabs,
                                                                    int acc_stride, int tmem_cols, int nss, int nts,
-                                                                   int dg_mn) {
+                                                                   int dg_mn, int cgroups) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // two rings: nss shared-memory stages (raw A blocks + B) cover the HBM latency; nts tensor-memory slots hold
   // the converted A operand (hi, lo) of the stages the MMA thread is working on - tensor memory is mostly taken
@@ -346,13 +352,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
         if (++a == nts) { a = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 6 && warp < 10) {   // converters: raw A rows -> tensor memory (hi, lo)
+  } else if (warp >= 6) {   // converters: raw A rows -> tensor memory (hi, lo)
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    int s = 0, ph = 0, a = 0, aph = 0;
-    for (int slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+    const int cgroup = (warp - 6) >> 2;
+    int s = cgroup, ph = 0, a = cgroup, aph = 0, u = 0;
+    for (int slab = blockIdx.x; cgroup < cgroups && slab < n_slabs; slab += gridDim.x) {
       const int t0 = slab * slab_tiles, t1 = min(t0 + slab_tiles, n_tiles);
-      for (int tg = t0 * 8; tg < t1 * 8; ++tg) {
+      for (int tg = t0 * 8; tg < t1 * 8; ++tg, ++u) {
+        if ((u & (cgroups - 1)) != cgroup) continue;
         mbar_wait_guard(&full[s], ph);
         mbar_wait_guard(&aempty[a], aph ^ 1);
         tc_fence_after();
@@ -376,8 +384,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) l1_grad_tc_kernel(const float* 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[a]);
-        if (++s == nss) { s = 0; ph ^= 1; }
-        if (++a == nts) { a = 0; aph ^= 1; }
+        s += cgroups;
+        if (s >= nss) { s -= nss; ph ^= 1; }
+        a += cgroups;
+        if (a >= nts) { a -= nts; aph ^= 1; }
       }
     }
   } else if (warp >= 2 && warp < 6) {   // epilogue warps 2..5
@@ -472,16 +482,30 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   const int acc_cols = nu <= 32 ? 32 : (nu <= 64 ? 64 : (nu <= 128 ? 128 : 256));
   const int n_acc = acc_cols <= 128 ? 2 : 1;     // double-buffered accumulator when tensor memory has room
   // k-groups per stage: one stage hand-over (bulk copies, mbarrier round trips between the producer, converter
-  // and MMA threads) costs 500-1000 cycles whatever the copy size (tools/micro/bulk_rate*.cu), so a stage
-  // carries 3 k-groups.  Stage count: shared memory (227 KB) and the tensor-memory A ring (48 columns per stage
-  // behind the accumulators, 512 columns in all).
-  const int kps = 3;   // measured at 1M x 376 -> 100: 2 -> 0.47 ms, 3 -> 0.43, 4 -> 0.42, 5 -> 0.44
-  const size_t stage_bytes = (size_t)kps * (TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
-  int nstages = (int)((227 * 1024 - 512) / stage_bytes);
-  const int tmem_room = (512 - n_acc * acc_cols) / (kps * 16);
-  if (nstages > tmem_room) nstages = tmem_room;
-  if (nstages > TC_STAGES) nstages = TC_STAGES;
+  // and MMA threads) costs 500-1000 cycles whatever the copy size (tools/micro/bulk_rate*.cu), so a stage carries
+  // several k-groups.  Stage count: shared memory (227 KB) and the tensor-memory A ring (16 columns per k-group
+  // behind the accumulators, 512 columns in all).  Measured at 1M x 376 -> 100: one converter group, 5 stages of
+  // 3 k-groups 0.447 ms (2: 0.47, 4: 0.42-0.44, 5: 0.44); two groups, 4 stages of 4: 0.437; two groups, 4 x 3: 0.470;
+  // two groups, 8 x 2: 0.535.
+  static const int kps_env = getenv("MRL_L1_KPS") ? atoi(getenv("MRL_L1_KPS")) : 0;          // experiment knobs
+  static const int cg_env = getenv("MRL_L1_CGROUPS") ? atoi(getenv("MRL_L1_CGROUPS")) : 0;
+  int kps = 0, nstages = 0, cgroups = 1;
+  for (int pass = 0; pass < 2; ++pass) {
+    // first choice: 4 k-groups per stage converted by two groups (needs an even ring of >= 4 stages, see TC_CGROUPS);
+    // otherwise 3 per stage and one group
+    kps = kps_env > 0 ? kps_env : (pass == 0 ? 4 : 3);
+    const size_t sb = (size_t)kps * (TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
+    nstages = (int)((227 * 1024 - 512) / sb);
+    const int tmem_room = (512 - n_acc * acc_cols) / (kps * 16);
+    if (nstages > tmem_room) nstages = tmem_room;
+    if (nstages > TC_STAGES) nstages = TC_STAGES;
+    cgroups = (pass == 0 && nstages >= 4) ? 2 : 1;
+    if (cg_env > 0) cgroups = (cg_env >= 2 && nstages >= 2) ? 2 : 1;
+    if (cgroups == 2) nstages &= ~1;
+    if (cgroups == 2 || cg_env > 0 || kps_env > 0) break;
+  }
   if (nstages < 2) return cudaErrorInvalidConfiguration;
+  const size_t stage_bytes = (size_t)kps * (TC_M * 8 * 4 + 2 * (size_t)nu * 8 * 4);
   int tmem_cols = 32;
   while (tmem_cols < n_acc * acc_cols + nstages * kps * 16) tmem_cols *= 2;
   const size_t smem = 512 + (size_t)nstages * stage_bytes;
@@ -493,7 +517,7 @@ cudaError_t launch_l1_forward_tc(const NetGeom& g, const float* XA, int xa_kgrou
   const int n_mtiles = (n_tiles + 1) / 2;
   const int grid = n_mtiles < sms ? n_mtiles : sms;
   l1_forward_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XA, WB, Zt, g.d0p / 8, xa_kgroups, nu, g.d[1], n_mtiles, n_tiles,
-                                                       acc_cols, n_acc, tmem_cols, nstages, kps);
+                                                       acc_cols, n_acc, tmem_cols, nstages, kps, cgroups);
   return cudaGetLastError();
 }
 
@@ -546,10 +570,14 @@ cudaError_t launch_l1_grad_tc(const NetGeom& g, const float* XG, int xg_ftiles, 
     cudaError_t e = mrl_func_smem((const void*)l1_grad_tc_kernel, smem);
     if (e != cudaSuccess) return e;
   }
+  static const int cg_env = getenv("MRL_L1_CGROUPS") ? atoi(getenv("MRL_L1_CGROUPS")) : 0;   // experiment knob
+  int cgroups = (nts >= 2 && nss >= 4) ? 2 : 1;   // two converter groups need even rings (see TC_CGROUPS)
+  if (cg_env > 0) cgroups = (cg_env >= 2 && nts >= 2 && nss >= 2) ? 2 : 1;
+  if (cgroups == 2) { nts &= ~1; nss &= ~1; }
   const int sms = mrl_sm_count();
   const int grid = n_slabs < sms ? n_slabs : sms;
   l1_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(XG, DG, part1, ftiles, xg_ftiles, nu, g.d[0], g.n1p, slab_tiles,
-                                                    n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts, dg_mn_major);
+                                                    n_tiles, n_slabs, acc_stride, tmem_cols, nss, nts, dg_mn_major, cgroups);
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches_r01.csv profiles/r01_launches.md
   python tools/ncu_summary.py kernel  gpurun_out/prof_r01_X.ncu-rep profiles/r01_X.md
+  python tools/ncu_summary.py traffic profiles/ncu_traffic.json name=rep [name=rep ...]   (DRAM bytes per launch)
 """
 import csv
 import subprocess
@@ -68,5 +69,31 @@ def kernel(src, dst):
     print("wrote", dst)
 
 
+def _to_bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+    return float(value.replace(",", "")) * scale
+
+
+def traffic(dst, *pairs):
+    """Rewrite the `kernels` table of profiles/ncu_traffic.json (bench.py's roofline.traffic) from --set full captures."""
+    import json
+    doc = json.load(open(dst))
+    srcs = []
+    for pair in pairs:
+        name, rep = pair.split("=", 1)
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        d, u = dict(zip(hdr, vals)), dict(zip(hdr, units))
+        doc["kernels"][name] = {"read": _to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]),
+                                "write": _to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])}
+        srcs.append(rep)
+    doc["source"] = ", ".join(srcs)
+    with open(dst, "w") as f:
+        json.dump(doc, f, indent=1)
+    print("wrote", dst, doc["kernels"])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    fn = {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]]
+    fn(*sys.argv[2:])
