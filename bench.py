@@ -713,7 +713,7 @@ def main():
         nvlink = {"tx_kib_per_step": (nv1[0] - nv0[0]) / nsteps, "rx_kib_per_step": (nv1[1] - nv0[1]) / nsteps,
                   "how": "nvidia-smi nvlink -gt d on rank 0's GPU around the warm-up + timed steps",
                   "expected_kib_per_step": 13 * net.P * 8 * (world - 1) / 1024.0,
-                  "what": "each of the 13 sums over ranks per update (1 gradient, 11 Fvp, loss triples apart) pushes P doubles to every peer"}
+                  "what": "each of the 13 sums over ranks per update (1 gradient, 11 Fvp, loss triples apart) reads P doubles from every peer"}
     pms_total, _, _ = timed(step_resident, args.steps, 1, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     nk = lib.mrl_profile_kinds()

@@ -265,7 +265,14 @@ __global__ void zf_sub_kernel(const TX* __restrict__ x, long long N, int d, long
   const int f = (int)(i % d);
   const long long r0 = sb * ZF_SUB, r1 = min(N, r0 + ZF_SUB);
   Wf w = {0.0, 0.0, 0.0};
-  for (long long r = r0; r < r1; ++r) wf_push(w, (double)x[r * d + f]);
+  for (long long rb = r0; rb < r1; rb += 8) {     // 8 rows per batch: the loads are issued before the serial recurrence
+    TX v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = rb + j < r1 ? x[(rb + j) * d + f] : (TX)0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (rb + j < r1) wf_push(w, (double)v[j]);
+  }
   subm[i] = w.m;
   subs[i] = w.s;
 }
@@ -275,15 +282,28 @@ __global__ void zf_super_kernel(long long N, int d, long long n_sb, long long n_
   if (i >= n_su * d) return;
   const long long su = i / d;
   const int f = (int)(i % d);
+  // all loads first: subm / subs are read AND written here, so inside one loop every load would wait behind the
+  // previous iteration's store (measured: 0.49 ms of dependent DRAM round trips for 49 MB)
   Wf acc = {0.0, 0.0, 0.0};
-  for (int j = 0; j < ZF_SUP; ++j) {
-    const long long sb = su * ZF_SUP + j;
-    if (sb >= n_sb) break;
-    const long long r0 = sb * ZF_SUB;
-    Wf t = {(double)(min(N, r0 + ZF_SUB) - r0), subm[sb * d + f], subs[sb * d + f]};
-    subm[sb * d + f] = acc.m;   // exclusive prefix inside the super-block (count = j * ZF_SUB)
-    subs[sb * d + f] = acc.s;
-    acc = wf_merge(acc, t);
+  for (int j0 = 0; j0 < ZF_SUP; j0 += 16) {
+    double bm[16], bs[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const long long sb = su * ZF_SUP + j0 + j;
+      const bool in = sb < n_sb;
+      bm[j] = in ? subm[sb * d + f] : 0.0;
+      bs[j] = in ? subs[sb * d + f] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const long long sb = su * ZF_SUP + j0 + j;
+      if (sb >= n_sb) break;
+      const long long r0 = sb * ZF_SUB;
+      Wf t = {(double)(min(N, r0 + ZF_SUB) - r0), bm[j], bs[j]};
+      subm[sb * d + f] = acc.m;   // exclusive prefix inside the super-block (count = (j0 + j) * ZF_SUB)
+      subs[sb * d + f] = acc.s;
+      acc = wf_merge(acc, t);
+    }
   }
   supm[i] = acc.m;
   sups[i] = acc.s;
@@ -295,12 +315,24 @@ __global__ void zf_chain_kernel(long long N, int d, long long n_su, double n0, c
   if (f >= d) return;
   Wf acc = {n0, M0[f], S0[f]};
   const long long rows_su = (long long)ZF_SUB * ZF_SUP;
-  for (long long su = 0; su < n_su; ++su) {
-    const long long r0 = su * rows_su;
-    Wf t = {(double)(min(N, r0 + rows_su) - r0), supm[su * d + f], sups[su * d + f]};
-    supm[su * d + f] = acc.m;   // exclusive prefix including the incoming state (count = n0 + r0)
-    sups[su * d + f] = acc.s;
-    acc = wf_merge(acc, t);
+  for (long long su0 = 0; su0 < n_su; su0 += 16) {     // 16 super-blocks per batch: loads first (see zf_super_kernel)
+    double bm[16], bs[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const bool in = su0 + j < n_su;
+      bm[j] = in ? supm[(su0 + j) * d + f] : 0.0;
+      bs[j] = in ? sups[(su0 + j) * d + f] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const long long su = su0 + j;
+      if (su >= n_su) break;
+      const long long r0 = su * rows_su;
+      Wf t = {(double)(min(N, r0 + rows_su) - r0), bm[j], bs[j]};
+      supm[su * d + f] = acc.m;   // exclusive prefix including the incoming state (count = n0 + r0)
+      sups[su * d + f] = acc.s;
+      acc = wf_merge(acc, t);
+    }
   }
   state_out[f] = acc.m;
   state_out[d + f] = acc.s;
@@ -320,16 +352,23 @@ __global__ void zf_apply_kernel(const TX* __restrict__ x, long long N, int d, lo
   Wf a = {n0 + (double)(su * ZF_SUB * ZF_SUP), supm[su * d + f], sups[su * d + f]};
   Wf b = {(double)((sb % ZF_SUP) * ZF_SUB), subm[i], subs[i]};
   Wf w = wf_merge(a, b);
-  for (long long r = r0; r < r1; ++r) {
-    double v = (double)x[r * d + f];
-    wf_push(w, v);
-    if (demean) v = v - w.m;
-    if (destd) {
-      const double var = w.n > 1.0 ? w.s / (w.n - 1.0) : w.m * w.m;   // running_stat.py:26-27
-      v = v / (sqrt(var) + 1e-8);
+  for (long long rb = r0; rb < r1; rb += 8) {
+    TX xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = rb + j < r1 ? x[(rb + j) * d + f] : (TX)0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (rb + j >= r1) break;
+      double v = (double)xv[j];
+      wf_push(w, v);
+      if (demean) v = v - w.m;
+      if (destd) {
+        const double var = w.n > 1.0 ? w.s / (w.n - 1.0) : w.m * w.m;   // running_stat.py:26-27
+        v = v / (sqrt(var) + 1e-8);
+      }
+      if (clip != 0.0) v = fmin(fmax(v, -clip), clip);
+      y[(rb + j) * d + f] = (TY)v;
     }
-    if (clip != 0.0) v = fmin(fmax(v, -clip), clip);
-    y[r * d + f] = (TY)v;
   }
 }
 
