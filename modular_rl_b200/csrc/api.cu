@@ -888,6 +888,9 @@ static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
 }
 
 // reverse sweep + layer-1 gradient + slab reduce -> out32 (float[P], device) and out64 (double[P]).
+// With the peer-memory transport the slab reduce also performs the exchange when it has few slabs (its grid must then be
+// resident at once, see reduce_partials_kernel); beyond this many slabs a separate receiving kernel is cheaper.
+#define REDUCE_FUSED_EXCHANGE_MAX_SLABS 400
 static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
                          const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
   const NetGeom& g = n->g;
@@ -938,14 +941,21 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   // over ranks itself (comm.h); otherwise out64 holds this rank's share and NCCL sums it
   P2pPush push;
   P2pGather gather;
+  const bool fused = p2p && pl.n_slabs <= REDUCE_FUSED_EXCHANGE_MAX_SLABS;
   if (p2p) {
     RET(mrl_comm_p2p_begin(n->comm, g.P, &push));
-    RET(mrl_comm_p2p_pending(n->comm, &gather));
+    if (fused) RET(mrl_comm_p2p_pending(n->comm, &gather));
   }
   CKP(PK_REDUCE, launch_reduce_partials(g, n->part1.as<float>(), n->partm.as<float>(), pl.n_slabs, 1.0 / (double)b->Nglobal,
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
-                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, (world > 1 && !p2p) ? nullptr : out32,
-                             out64, p2p ? &push : nullptr, p2p ? &gather : nullptr, st), 1);
+                             mode == MRL_MODE_FVP ? v_dev : nullptr, vls, (world > 1 && !fused) ? nullptr : out32,
+                             (p2p && !fused) ? nullptr : out64, p2p ? &push : nullptr, fused ? &gather : nullptr, st), 1);
+  if (p2p && !fused) {   // many slabs: the reduce keeps its full grid and a small kernel behind it is the receiving side
+    prof_mark(PK_REDUCE, st, true);
+    RET(mrl_comm_p2p_finish(n->comm, g.P, out64, out32, st));
+    prof_mark(PK_REDUCE, st, false);
+    g_launches += 1;
+  }
   if (world > 1 && !p2p) {
     RET(mrl_comm_allreduce_f64(n->comm, out64, g.P, st));
     if (out32) {

@@ -68,7 +68,9 @@ __global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, f
 // vector and the last CTA raises this rank's flag on every peer; phase 2 waits for all ranks' flags, reads the peers'
 // vectors over NVLink - thread row sy reads rank sy, the whole GPU shares the round trips - and writes the sum over
 // ranks (rank order: identical bits everywhere).  CTAs spin in phase 2 while others still work in phase 1, so the
-// launcher sizes such a grid to be resident at once; chunks are dealt grid-stride.
+// launcher sizes such a grid to be resident at once; chunks are dealt grid-stride.  With many slabs the resident grid
+// costs phase 1 more than a launch (651 slabs, 2 ranks: 58-86 us against 42 us + a 10 us gather kernel): the caller
+// then passes no gather and runs p2p_gather_kernel behind this kernel (REDUCE_FUSED_EXCHANGE_MAX_SLABS in api.cu).
 #define RED_PX 32
 #define RED_SY 8
 #define RED_UN 8
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
   }
   if (push.world == 0) return;
   p2p_push_done(push);
+  if (ga.world == 0) return;            // the caller's next kernel is the receiving side (mrl_comm_p2p_finish)
   p2p_wait_flags(ga, sy * RED_PX + px);
   const double* peer = nullptr;          // rank sy's vector (selected without indexing the kernel parameter)
 #pragma unroll
@@ -329,9 +332,9 @@ cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const f
   no_gather.world = 0;
   const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
   int grid = n_chunks;
-  if (push) {
+  if (push && gather) {
     // the exchange phase spins on the peers' flags: every CTA of the grid must be resident
-    if (!gather || gather->world != push->world) return cudaErrorInvalidValue;
+    if (gather->world != push->world) return cudaErrorInvalidValue;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_partials_kernel, RED_PX * RED_SY, 0);
     if (e != cudaSuccess) return e;
@@ -340,7 +343,7 @@ cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const f
     grid = n_chunks < wave ? n_chunks : wave;     // (equal chunk counts per CTA instead: same time, measured at 4 ranks)
   }
   reduce_partials_kernel<<<grid, dim3(RED_PX, RED_SY), 0, st>>>(g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32,
-                                                             out64, push ? *push : no_push, push ? *gather : no_gather);
+                                                             out64, push ? *push : no_push, (push && gather) ? *gather : no_gather);
   return cudaGetLastError();
 }
 
