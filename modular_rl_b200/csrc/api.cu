@@ -888,9 +888,6 @@ static bool cache_ok(const mrl_net* n, const mrl_batch* b) {
 }
 
 // reverse sweep + layer-1 gradient + slab reduce -> out32 (float[P], device) and out64 (double[P]).
-// With the peer-memory transport the slab reduce also performs the exchange when it has few slabs (its grid must then be
-// resident at once, see reduce_partials_kernel); beyond this many slabs a separate receiving kernel is cheaper.
-#define REDUCE_FUSED_EXCHANGE_MAX_SLABS 400
 static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_dev, int reverse_kl,
                          const float* v_dev, double l2c2, float* out32, double* out64, cudaStream_t st) {
   const NetGeom& g = n->g;
@@ -941,7 +938,7 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
   // over ranks itself (comm.h); otherwise out64 holds this rank's share and NCCL sums it
   P2pPush push;
   P2pGather gather;
-  const bool fused = p2p && pl.n_slabs <= REDUCE_FUSED_EXCHANGE_MAX_SLABS;
+  const bool fused = p2p && !getenv("MRL_P2P_SPLIT");   // MRL_P2P_SPLIT=1: separate receiving kernel (A/B comparisons)
   if (p2p) {
     RET(mrl_comm_p2p_begin(n->comm, g.P, &push));
     if (fused) RET(mrl_comm_p2p_pending(n->comm, &gather));
@@ -950,7 +947,7 @@ static int pass_backward(mrl_net* n, mrl_batch* b, int mode, const double* coef_
                              l2c2 != 0.0 ? n->theta.as<float>() : nullptr, l2c2 / world,
                              mode == MRL_MODE_FVP ? v_dev : nullptr, vls, (world > 1 && !fused) ? nullptr : out32,
                              (p2p && !fused) ? nullptr : out64, p2p ? &push : nullptr, fused ? &gather : nullptr, st), 1);
-  if (p2p && !fused) {   // many slabs: the reduce keeps its full grid and a small kernel behind it is the receiving side
+  if (p2p && !fused) {
     prof_mark(PK_REDUCE, st, true);
     RET(mrl_comm_p2p_finish(n->comm, g.P, out64, out32, st));
     prof_mark(PK_REDUCE, st, false);

@@ -65,15 +65,18 @@ __global__ void pack_params_kernel(NetGeom g, const float* __restrict__ theta, f
 // (fvp[logstd] = 2 v_logstd is data independent)
 // fp64 accumulation in a fixed slab order -> deterministic.
 // Data-parallel with the peer-memory transport (push.world > 0): phase 1 writes this rank's sums into its exported
-// vector and the last CTA raises this rank's flag on every peer; phase 2 waits for all ranks' flags, reads the peers'
-// vectors over NVLink - thread row sy reads rank sy, the whole GPU shares the round trips - and writes the sum over
-// ranks (rank order: identical bits everywhere).  CTAs spin in phase 2 while others still work in phase 1, so the
-// launcher sizes such a grid to be resident at once; chunks are dealt grid-stride.  With many slabs the resident grid
-// costs phase 1 more than a launch (651 slabs, 2 ranks: 58-86 us against 42 us + a 10 us gather kernel): the caller
-// then passes no gather and runs p2p_gather_kernel behind this kernel (REDUCE_FUSED_EXCHANGE_MAX_SLABS in api.cu).
+// vector and the last CTA to finish raises this rank's flag on every peer; the last RED_GATHER_CTAS CTAs to finish
+// (by arrival ticket) stay for phase 2: they wait for all ranks' flags, read the peers' vectors over NVLink - thread
+// row sy reads rank sy, batches of reads in flight - and write the sum over ranks (rank order: identical bits
+// everywhere).  At most RED_GATHER_CTAS CTAs ever spin (two per SM), every other CTA leaves after phase 1,
+// so the CTAs that have not started yet always find SM slots: no residency requirement on the grid (round 2 first
+// sized the grid to be resident and let every CTA spin - slower phase 1, and two such kernels on one GPU could have
+// starved each other), and phase 1 keeps its full one-chunk-per-CTA grid.
 #define RED_PX 32
 #define RED_SY 8
 #define RED_UN 8
+#define RED_GATHER_CTAS 296   // CTAs that stay for the exchange phase (two per SM)
+#define RED_GB 5              // chunks per batch of peer reads (Humanoid: 1 391 chunks / 296 = one batch)
 static_assert(RED_SY >= MRL_P2P_MAX_WORLD, "one thread row per rank in the exchange phase");
 __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     NetGeom g, const float* __restrict__ part1, const float* __restrict__ partm, int n_slabs, double scale,
@@ -139,24 +142,37 @@ __global__ void __launch_bounds__(RED_PX * RED_SY) reduce_partials_kernel(
     __syncthreads();                    // acc is reused
   }
   if (push.world == 0) return;
-  p2p_push_done(push);
+  const unsigned int ticket = p2p_push_done(push);
   if (ga.world == 0) return;            // the caller's next kernel is the receiving side (mrl_comm_p2p_finish)
+  // exchange phase: the last RED_GATHER_CTAS CTAs to finish phase 1 stay, everybody else leaves
+  const int total = (int)gridDim.x, stay = total < RED_GATHER_CTAS ? total : RED_GATHER_CTAS;
+  const int j = (int)ticket - (total - stay);
+  if (j < 0) return;
   p2p_wait_flags(ga, sy * RED_PX + px);
   const double* peer = nullptr;          // rank sy's vector (selected without indexing the kernel parameter)
 #pragma unroll
   for (int q = 0; q < MRL_P2P_MAX_WORLD; ++q)
     if (q == sy && q < ga.world) peer = ga.src[q];
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int i = chunk * RED_PX + px;
-    acc[sy][px] = (peer != nullptr && i < g.P) ? p2p_load(peer + i) : 0.0;
-    __syncthreads();
-    if (sy == 0 && i < g.P) {
-      double r = 0.0;
-      for (int q = 0; q < ga.world; ++q) r += acc[q][px];   // rank order
-      if (out32) out32[i] = (float)r;
-      if (out64) out64[i] = r;
+  for (int c0 = j; c0 < n_chunks; c0 += stay * RED_GB) {
+    double v[RED_GB];                    // RED_GB chunks per batch: all NVLink reads in flight before the first sum
+#pragma unroll
+    for (int u = 0; u < RED_GB; ++u) {
+      const int i = (c0 + u * stay) * RED_PX + px;
+      v[u] = (peer != nullptr && c0 + u * stay < n_chunks && i < g.P) ? p2p_load(peer + i) : 0.0;
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < RED_GB; ++u) {
+      const int i = (c0 + u * stay) * RED_PX + px;
+      acc[sy][px] = v[u];
+      __syncthreads();
+      if (sy == 0 && c0 + u * stay < n_chunks && i < g.P) {
+        double r = 0.0;
+        for (int q = 0; q < ga.world; ++q) r += acc[q][px];   // rank order
+        if (out32) out32[i] = (float)r;
+        if (out64) out64[i] = r;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -332,16 +348,7 @@ cudaError_t launch_reduce_partials(const NetGeom& g, const float* part1, const f
   no_gather.world = 0;
   const int n_chunks = (g.P + RED_PX - 1) / RED_PX;
   int grid = n_chunks;
-  if (push && gather) {
-    // the exchange phase spins on the peers' flags: every CTA of the grid must be resident
-    if (gather->world != push->world) return cudaErrorInvalidValue;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_partials_kernel, RED_PX * RED_SY, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    const int wave = mrl_sm_count() * per_sm;
-    grid = n_chunks < wave ? n_chunks : wave;     // (equal chunk counts per CTA instead: same time, measured at 4 ranks)
-  }
+  if (push && gather && gather->world != push->world) return cudaErrorInvalidValue;
   reduce_partials_kernel<<<grid, dim3(RED_PX, RED_SY), 0, st>>>(g, part1, partm, n_slabs, scale, theta, l2c2, vflat, vls, out32,
                                                              out64, push ? *push : no_push, (push && gather) ? *gather : no_gather);
   return cudaGetLastError();

@@ -100,15 +100,21 @@ __device__ __forceinline__ double p2p_gather_sum(const P2pGather& ga, long long 
 __device__ __forceinline__ void p2p_push_value(const P2pPush& p, long long i, double v) { p.own[i] = v; }
 // Call once per CTA after its last p2p_push_value (all threads).  The last CTA to arrive raises the flags: its
 // system-scope fence orders every CTA's stores (seen through the device-scope counter hand-off) before them.
-__device__ __forceinline__ void p2p_push_done(const P2pPush& p) {
+// Returns the CTA's arrival ticket (0 .. CTAs - 1, in order of arrival) to all its threads.
+__device__ __forceinline__ unsigned int p2p_push_done(const P2pPush& p) {
+  __shared__ unsigned int ticket_s;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const unsigned int total = gridDim.x * gridDim.y;
-    if (atomicAdd(p.counter, 1u) == total - 1) {
+    const unsigned int ticket = atomicAdd(p.counter, 1u);
+    if (ticket == total - 1) {
       *p.counter = 0;
       __threadfence_system();   // acquire side of the counter hand-off: every CTA's stores are ordered before the flags
       for (int q = 0; q < p.world; ++q) st_release_sys(p.flag[q], p.seq);
     }
+    ticket_s = ticket;
   }
+  __syncthreads();
+  return ticket_s;
 }
