@@ -345,3 +345,110 @@ def test_sim_agent_replays_snapshot(tmp_path, capsys):
     assert "reward:" in capsys.readouterr().out
     with pytest.raises(ValueError):
         sim_agent.main([str(tmp_path), "--snapname", "0001", "--episodes", "1", "--delay", "0"])
+
+
+# ----------------------------------------------------------------------------- vectorised rollouts / CEM host logic
+class _HostFilter(object):
+    """ZFilter through its per-sample host path only (no filter_batch attribute -> _filter_block goes row by row)."""
+
+    def __init__(self, shape, **kw):
+        from modular_rl_b200.filters import ZFilter
+        self.z = ZFilter(shape, **kw)
+
+    def __call__(self, x, update=True):
+        return self.z(x, update)
+
+
+class _StubPolicy(object):
+    """A linear softmax policy in numpy with the act / act_batch pair of StochPolicy (core.py:261-267)."""
+
+    def __init__(self, w):
+        self.w = w
+
+    def _probs(self, X):
+        z = X @ self.w
+        p = np.exp(z - z.max(axis=1, keepdims=True))
+        return p / p.sum(axis=1, keepdims=True)
+
+    def act(self, ob, stochastic=True):
+        a, info = self.act_batch(ob[None], stochastic)
+        return a[0], {"prob": info["prob"][0]}
+
+    def act_batch(self, X, stochastic=True):
+        p = self._probs(np.asarray(X, np.float64))
+        u = np.random.rand(len(p), 1)
+        a = np.argmax(np.cumsum(p, axis=1) > u, axis=1) if stochastic else p.argmax(axis=1)
+        return a, {"prob": p}
+
+
+class _StubAgent(object):
+    stochastic = True
+
+    def __init__(self, seed):
+        self.policy = _StubPolicy(np.random.default_rng(seed).standard_normal((4, 2)))
+        self.obfilter = _HostFilter((4,), clip=5)
+        self.rewfilter = _HostFilter((), demean=False, clip=10)
+
+    def act(self, ob):
+        return self.policy.act(ob, self.stochastic)
+
+    def obfilt(self, ob):
+        return self.obfilter(ob)
+
+    def rewfilt(self, rew):
+        return self.rewfilter(rew)
+
+
+def test_rollouts_vectorized_host_logic():
+    """core.rollouts_vectorized: with one environment it is `rollout` (same filter updates, same numpy draws); with
+    several it returns one path per environment with the reference's keys, and do_rollouts_vectorized keeps the
+    strict 'more than n_timesteps' stopping rule of core.py:219."""
+    import itertools
+    from modular_rl_b200 import core, envs
+    env_a, env_b = envs.make("CartPole-v0"), envs.make("CartPole-v0")
+    ag_a, ag_b = _StubAgent(3), _StubAgent(3)
+    np.random.seed(11)
+    ref = core.rollout(env_a, ag_a, 200)
+    np.random.seed(11)
+    (vec,) = core.rollouts_vectorized([env_b], ag_b, 200)
+    assert set(vec) == set(ref) and vec["terminated"] == ref["terminated"]
+    for k in ("observation", "action", "reward", "prob"):
+        np.testing.assert_array_equal(vec[k], ref[k])
+    assert ag_a.obfilter.z.rs.n == ag_b.obfilter.z.rs.n and np.array_equal(ag_a.obfilter.z.rs.mean, ag_b.obfilter.z.rs.mean)
+    # three environments in lockstep
+    np.random.seed(5)
+    many = [envs.make("CartPole-v0") for _ in range(3)]
+    paths = core.rollouts_vectorized(many, _StubAgent(4), 60)
+    assert len(paths) == 3
+    for p in paths:
+        T = len(p["reward"])
+        assert 1 <= T <= 60 and p["observation"].shape == (T, 4) and p["prob"].shape == (T, 2) and p["action"].shape == (T,)
+        assert p["terminated"] == (T < 60)
+    seeds = itertools.count()
+    got = core.do_rollouts_vectorized(envs.make("CartPole-v0"), _StubAgent(6), 50, 120, seeds, 4)
+    total = sum(len(p["reward"]) for p in got)
+    assert len(got) % 4 == 0 and total > 120 and total - sum(len(p["reward"]) for p in got[-4:]) <= 120
+
+
+def test_cem_population_hook_and_numa_helper():
+    """cem(): an objective with a `population` attribute is scored with one call per generation and gives the same
+    search as the per-candidate loop; parallel.bind_to_device_numa never raises (0 = nothing bound)."""
+    from modular_rl_b200.cem import cem
+    from modular_rl_b200.parallel import bind_to_device_numa
+    c = np.linspace(-1, 1, 5)
+    f = lambda th: -float(np.sum((th - c) ** 2))
+    calls = []
+
+    def g(th):
+        return f(th)
+    g.population = lambda ths: (calls.append(len(ths)), np.array([f(t) for t in ths]))[1]
+    np.random.seed(2)
+    a = list(cem(f, np.zeros(5), 30, 5, 0.2))
+    np.random.seed(2)
+    b = list(cem(g, np.zeros(5), 30, 5, 0.2))
+    assert calls == [30] * 5
+    for ia, ib in zip(a, b):
+        np.testing.assert_array_equal(ia["ys"], ib["ys"])
+        np.testing.assert_array_equal(ia["th"], ib["th"])
+    assert a[-1]["ymean"] > a[0]["ymean"]
+    assert isinstance(bind_to_device_numa(0), int)
