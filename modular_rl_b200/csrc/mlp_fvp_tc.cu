@@ -120,6 +120,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 // launch gives every thread 128 registers (512 threads = the whole register file); the control warps and the
 // converters hand most of theirs back, the epilogue warps - which keep prefetched activations in registers to hide
 // the L2 latency - take them.
+#ifndef FT_ROT
+#define FT_ROT 1          // rotate the (k) operand stores against bank conflicts (see the delta epilogue)
+#endif
 #define FT_REGS_CTRL 32
 #define FT_REGS_CONV 72
 #define FT_REGS_EPI 88
@@ -649,7 +652,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
       const int e = (warp - 12) >> 2;
       const uint32_t ring = tlane + P.dring_col + 16 * e;
       float* gb1w = gb1s + (warp - 12) * 128;
+#if FT_ROT
       const int rot = (m >> 2) & 7;
+#endif
       const bool cat = g.head == MRL_HEAD_CAT;
       const int nu = a.nu;
       uint32_t u = 0, ue = 0, tcount = 0;
@@ -750,17 +755,27 @@ __global__ void __launch_bounds__(FT_THREADS, 1) fvp_tc_kernel(NetGeom g, FtPlan
                 tmem_st8(ring, hi);
                 tmem_st8(ring + 8, lo);
                 if (c == 0) {
-                  // the same block as the K-major B operand of the (k) GEMM: [n][timestep], rotated so that the 32
-                  // timesteps of a warp hit 32 distinct banks
+                  // the same block as the K-major B operand of the (k) GEMM: [n][timestep].  In the no-swizzle core-matrix
+                  // order the 32 timesteps of a warp at one n hit 4 banks (8-way conflict), so the eight values are
+                  // rotated per lane quad and one store instruction hits 32 banks.  The rotation costs 96 select
+                  // instructions per k-group, but the plain order (FT_ROT=0) measured SLOWER: 1.095 vs 1.046 ms
+                  float* kp = kb + (size_t)kg * 1024;
+#if FT_ROT
                   ft_rot8(hi, rot);
                   ft_rot8(lo, rot);
-                  float* kp = kb + (size_t)kg * 1024;
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const int nn = ((i + rot) & 7) * 4;
                     kp[nn] = __uint_as_float(hi[i]);
                     kp[nn + lo_off] = __uint_as_float(lo[i]);
                   }
+#else
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    kp[4 * i] = __uint_as_float(hi[i]);
+                    kp[4 * i + lo_off] = __uint_as_float(lo[i]);
+                  }
+#endif
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
